@@ -1,0 +1,195 @@
+/*
+ * muopdb_gpu.h -- C ABI of the B200-native (sm_100a) batched ANN search path for MuopDB.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch
+ * types, no exceptions.  Each entry point cites the reference interface it replaces (paths are
+ * relative to the reference checkout, hicder/muopdb @ c520f017).  The reference has no FFI of its
+ * own; INTEGRATION.md shows the Rust `extern "C"` binding a maintainer would add behind
+ * `Quantizer`, `BlockBasedIvf`, `BlockBasedHnsw` and `Spann`.
+ *
+ * Conventions
+ *   - Every function returns an int status: MGPU_OK or a negative MGPU_ERR_* code;
+ *     mgpu_last_error(ctx) returns a human-readable message for the last failure on that ctx.
+ *   - `mem` says where the caller's query/result buffers live: MGPU_HOST (pageable or pinned host
+ *     memory; the call copies in/out and returns when results are in the host buffers) or
+ *     MGPU_DEVICE (device pointers on ctx's device; the call only enqueues work on the ctx stream --
+ *     call mgpu_sync before reading results).
+ *   - Index-construction inputs (`*_create`) are copied to HBM in a scan-friendly layout; the
+ *     caller keeps ownership of its buffers.  Handles are opaque and freed by `*_destroy`.
+ *   - Scores follow the reference: lower is closer; flat L2 = sqrt(sum (a-b)^2)
+ *     (rs/quantization/src/noq/mod.rs:44-51), PQ = squared symmetric distance between the two
+ *     code words' centroids (rs/quantization/src/pq/mod.rs:231-266), dot = -sum a*b
+ *     (rs/utils/src/distance/dot_product.rs:25-27).
+ *   - Doc ids are u128 little-endian: mgpu_u128 {lo, hi}.
+ *   - Result buffers have fixed stride k; out_counts[b] <= k entries are valid for query b.
+ *   - There is no CPU fallback: without a CUDA device mgpu_init fails with MGPU_ERR_NO_DEVICE.
+ *   - Calls on one ctx are serialised by an internal mutex (the reference's `&self` search
+ *     methods are called concurrently from tokio tasks; use one ctx per worker for concurrency).
+ */
+#ifndef MUOPDB_GPU_H
+#define MUOPDB_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGPU_OK 0
+#define MGPU_ERR_INVALID_ARG (-1)
+#define MGPU_ERR_OUT_OF_RANGE (-2) /* e.g. nprobe == 0 || nprobe > nlist: the reference panics (ivf/block_based/index.rs:158) */
+#define MGPU_ERR_CUDA (-3)
+#define MGPU_ERR_OOM (-4)
+#define MGPU_ERR_UNSUPPORTED (-5)
+#define MGPU_ERR_NO_DEVICE (-6)
+#define MGPU_ERR_NCCL (-7)
+
+enum { MGPU_L2 = 0, MGPU_DOT = 1 };            /* DistanceCalculator impls: rs/utils/src/distance/{l2,dot_product}.rs */
+enum { MGPU_QUANT_NONE = 0, MGPU_QUANT_PQ = 1 }; /* NoQuantizer / ProductQuantizer: rs/quantization/src/{noq,pq}/mod.rs */
+enum { MGPU_HOST = 0, MGPU_DEVICE = 1 };
+
+/* kernel classes for mgpu_profile_* */
+enum {
+  MGPU_K_COARSE = 0,   /* query x centroid distances */
+  MGPU_K_SELECT = 1,   /* per-query top-nprobe */
+  MGPU_K_QUANTIZE = 2, /* PQ encode */
+  MGPU_K_SCAN = 3,     /* posting-list scan (PQ LUT scan or flat) */
+  MGPU_K_FINALIZE = 4, /* exact re-rank + ordering + doc-id remap */
+  MGPU_K_HNSW = 5,     /* graph beam search */
+  MGPU_K_MERGE = 6,    /* shard top-k merge */
+  MGPU_K_OTHER = 7,
+  MGPU_K_COUNT = 8
+};
+
+typedef struct { uint64_t lo, hi; } mgpu_u128;
+
+typedef struct mgpu_ctx mgpu_ctx;
+typedef struct mgpu_pq mgpu_pq;
+typedef struct mgpu_ivf mgpu_ivf;
+typedef struct mgpu_hnsw mgpu_hnsw;
+typedef struct mgpu_spann mgpu_spann;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int mgpu_init(int device, mgpu_ctx **out);
+void mgpu_destroy(mgpu_ctx *ctx);
+const char *mgpu_last_error(mgpu_ctx *ctx);
+const char *mgpu_version(void);
+int mgpu_sync(mgpu_ctx *ctx);                    /* wait for everything enqueued on the ctx stream */
+void *mgpu_stream(mgpu_ctx *ctx);                /* the cudaStream_t all kernels of this ctx run on */
+int mgpu_device_sm_count(mgpu_ctx *ctx);
+
+/* CUDA-event timing on the ctx stream (bench.py times device work with these). */
+int mgpu_timer_start(mgpu_ctx *ctx);
+int mgpu_timer_stop(mgpu_ctx *ctx, float *elapsed_ms); /* records, synchronises, returns elapsed */
+
+/* Per-kernel-class profiling: when on, every launch of a class is bracketed by events. */
+int mgpu_profile_enable(mgpu_ctx *ctx, int on);
+int mgpu_profile_reset(mgpu_ctx *ctx);
+int mgpu_profile_get(mgpu_ctx *ctx, int kernel_class, float *total_ms, uint64_t *launches);
+uint64_t mgpu_launch_count(mgpu_ctx *ctx);       /* kernels launched by this ctx since creation */
+
+/* ---- DistanceCalculator (rs/utils/src/lib.rs:17-40) ---------------------------------------- */
+/* out[i*nB + j] = calculate(A[i], B[j]) (or calculate_squared when `squared` != 0; dot ignores it),
+ * bit-identical to L2DistanceCalculator (distance/l2.rs:30-74) / DotProductDistanceCalculator
+ * (distance/dot_product.rs:38-71) including their lane structure and summation order. */
+int mgpu_distance_batch(mgpu_ctx *ctx, const float *A, uint64_t nA, const float *B, uint64_t nB, uint32_t dim,
+                        int metric, int squared, float *out, int mem);
+
+/* ---- ProductQuantizer (rs/quantization/src/pq/mod.rs:23-286, Quantizer trait quantization.rs:6-38) */
+/* codebook: m * 2^nbits * dsub floats laid out [subspace][centroid][dsub] (pq/mod.rs:155-167), host memory. */
+int mgpu_pq_create(mgpu_ctx *ctx, uint32_t dim, uint32_t dsub, uint32_t nbits, const float *codebook, int metric,
+                   mgpu_pq **out);
+void mgpu_pq_destroy(mgpu_pq *pq);
+/* Quantizer::quantize over a batch (pq/mod.rs:152-177): first-minimum argmin per subspace. codes: n x (dim/dsub). */
+int mgpu_pq_quantize_batch(mgpu_pq *pq, const float *X, uint64_t n, uint8_t *codes, int mem);
+/* Quantizer::distance(a[i], b[i], StreamingSIMD) for n code-word pairs (pq/mod.rs:231-266). */
+int mgpu_pq_distance_batch(mgpu_pq *pq, const uint8_t *a, const uint8_t *b, uint64_t n, float *out, int mem);
+
+/* ---- BlockBasedIvf<Q> (rs/index/src/ivf/block_based/index.rs:22-471) ---------------------- */
+/* Arrays are what BlockBasedIvf::new reads from `index` + `vectors` (ivf/writer.rs:300-353):
+ *   centroids      nlist x dim f32
+ *   list_offsets   nlist+1 prefix offsets into list_point_ids
+ *   list_point_ids point ids (ascending inside a list; a point may appear in several lists)
+ *   rows           N x dim f32 (MGPU_QUANT_NONE) or N x (dim/dsub) u8 codes (MGPU_QUANT_PQ), indexed by point id;
+ *                  rows_mem says whether `rows` is a host or device pointer
+ *   doc_ids        N u128 (NULL => doc id == point id)
+ * All other array arguments are host pointers.  `pq` must outlive the index when quant == MGPU_QUANT_PQ. */
+int mgpu_ivf_create(mgpu_ctx *ctx, uint32_t dim, uint32_t nlist, const float *centroids, const uint64_t *list_offsets,
+                    const uint32_t *list_point_ids, int quant, int metric, mgpu_pq *pq, const void *rows, int rows_mem,
+                    uint64_t n, const mgpu_u128 *doc_ids, mgpu_ivf **out);
+void mgpu_ivf_destroy(mgpu_ivf *ivf);
+uint64_t mgpu_ivf_num_vectors(mgpu_ivf *ivf);  /* index.rs:343-345 */
+uint32_t mgpu_ivf_num_clusters(mgpu_ivf *ivf); /* index.rs:334-336 */
+/* invalidate_batch by point id (index.rs:430-471 family): skipped before any distance work (index.rs:198-200). */
+int mgpu_ivf_invalidate(mgpu_ivf *ivf, const uint32_t *point_ids, uint32_t n);
+int mgpu_ivf_is_invalidated(mgpu_ivf *ivf, uint32_t point_id, int *out);
+
+/* find_nearest_centroids (index.rs:147-163) for B queries: the nprobe smallest sqrt-L2 centroid distances,
+ * nearest first, ties by centroid index.  out_ids: B x nprobe; out_dist (may be NULL): B x nprobe. */
+int mgpu_ivf_coarse(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t nprobe, uint32_t *out_ids, float *out_dist,
+                    int mem);
+/* search_with_centroids (index.rs:250-285) for B queries with explicit probe lists.
+ * probe_ids: B x max_probes; probe_counts: B (NULL => max_probes each).  Results ordered by (distance, point_id). */
+int mgpu_ivf_scan(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint32_t *probe_ids, uint32_t max_probes,
+                  const uint32_t *probe_counts, uint32_t k, uint32_t *out_point_ids, float *out_scores,
+                  uint32_t *out_counts, int mem);
+/* search_with_centroids_and_remap (index.rs:298-332): as above, then doc ids, ordered by (score, doc_id). */
+int mgpu_ivf_scan_remap(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint32_t *probe_ids, uint32_t max_probes,
+                        const uint32_t *probe_counts, uint32_t k, mgpu_u128 *out_doc_ids, float *out_scores,
+                        uint32_t *out_counts, int mem);
+/* BlockBasedIvf::search (index.rs:396-412): coarse + scan + remap. */
+int mgpu_ivf_search(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, mgpu_u128 *out_doc_ids,
+                    float *out_scores, uint32_t *out_counts, int mem);
+/* Algorithmic bytes of the last scan on this index (sum over queries of L(q) x bytes/row + 4). */
+uint64_t mgpu_ivf_last_scan_bytes(mgpu_ivf *ivf);
+uint64_t mgpu_ivf_last_scan_rows(mgpu_ivf *ivf);
+
+/* ---- Build-time assignment (rs/index/src/ivf/builder.rs:268-366, kmeans_builder.rs:199-221) - */
+/* Squared-L2 to every centroid; the max_clusters nearest; keep those with |d - dmin| <= dmin * threshold.
+ * out_cids: n x max_clusters (UINT32_MAX padded), out_counts: n. */
+int mgpu_ivf_assign(mgpu_ctx *ctx, const float *X, uint64_t n, const float *centroids, uint32_t nlist, uint32_t dim,
+                    uint32_t max_clusters, float threshold, uint32_t *out_cids, uint32_t *out_counts, int mem);
+
+/* ---- BlockBasedHnsw<Q> (rs/index/src/hnsw/block_based/index.rs:55-298) --------------------- */
+/* Graph arrays exactly as in the `hnsw/index` file (hnsw/block_based/graph_storage.rs:122-193):
+ * level_offsets has num_layers+1 entries, top layer first; layer 0 is addressed by point id. */
+int mgpu_hnsw_create(mgpu_ctx *ctx, uint32_t dim, uint32_t num_layers, const uint32_t *edges, uint64_t n_edges,
+                     const uint32_t *points, uint64_t n_points, const uint64_t *edge_offsets, uint64_t n_edge_offsets,
+                     const uint64_t *level_offsets, int quant, int metric, mgpu_pq *pq, const void *rows, int rows_mem,
+                     uint64_t n, const mgpu_u128 *doc_ids, mgpu_hnsw **out);
+void mgpu_hnsw_destroy(mgpu_hnsw *h);
+/* ann_search (index.rs:159-210) for B queries.  out_stats (may be NULL): B x 2 = {#distance evals, #expansions}. */
+int mgpu_hnsw_search(mgpu_hnsw *h, const float *Q, uint32_t B, uint32_t k, uint32_t ef, mgpu_u128 *out_doc_ids,
+                     float *out_scores, uint32_t *out_counts, uint64_t *out_stats, int mem);
+
+/* ---- Spann<Q> (rs/index/src/spann/index.rs:15-266) ---------------------------------------- */
+/* centroids: HNSW over the IVF centroids with NoQuantizer<L2> whose doc ids are centroid indices. */
+int mgpu_spann_create(mgpu_ctx *ctx, mgpu_hnsw *centroids, mgpu_ivf *posting_lists, mgpu_spann **out);
+void mgpu_spann_destroy(mgpu_spann *s);
+/* Spann::search (spann/index.rs:211-266) with SearchParams {top_k, ef_construction, num_explored_centroids,
+ * centroid_distance_ratio} (rs/config/src/search_params.rs:2-34).  out_counts[b] == UINT32_MAX encodes `None`. */
+int mgpu_spann_search(mgpu_spann *s, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef,
+                      uint32_t num_explored_centroids, float centroid_distance_ratio, mgpu_u128 *out_doc_ids,
+                      float *out_scores, uint32_t *out_counts, int mem);
+
+/* ---- Cross-segment / cross-shard merge (rs/index/src/collection/snapshot.rs:49-63,79-108) -- */
+/* Concatenate S partial results per query, sort by (score, doc_id) (utils.rs:95-114), truncate to k.
+ * doc_ids/scores: S x B x k, counts: S x B. */
+int mgpu_merge_topk(mgpu_ctx *ctx, const mgpu_u128 *doc_ids, const float *scores, const uint32_t *counts, uint32_t S,
+                    uint32_t B, uint32_t k, mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, int mem);
+
+/* Multi-GPU: one process per GPU, each holding one doc-shard (rs/aggregator/src/aggregator.rs:81-132 is the
+ * semantic model).  mgpu_comm_* wraps an NCCL communicator (libnccl is dlopen'ed on first use). */
+int mgpu_comm_unique_id(uint8_t out_id[128]);
+int mgpu_comm_init(mgpu_ctx *ctx, int nranks, int rank, const uint8_t id[128]);
+int mgpu_comm_destroy(mgpu_ctx *ctx);
+/* All-gather every rank's B x k partial result over NVLink and merge locally (every rank gets the merged top-k).
+ * Buffers are DEVICE pointers. */
+int mgpu_shard_allgather_merge(mgpu_ctx *ctx, const mgpu_u128 *local_doc_ids, const float *local_scores,
+                               const uint32_t *local_counts, uint32_t B, uint32_t k, mgpu_u128 *out_doc_ids,
+                               float *out_scores, uint32_t *out_counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUOPDB_GPU_H */

@@ -1,0 +1,621 @@
+"""muopdb_b200 -- B200-native (sm_100a) batched ANN search path for MuopDB.
+
+Host-side mirror of the reference's interfaces for the search hot path, over the C ABI of include/muopdb_gpu.h:
+
+    reference (Rust)                                              here
+    utils::distance::l2::L2DistanceCalculator                     L2DistanceCalculator
+    utils::distance::dot_product::DotProductDistanceCalculator    DotProductDistanceCalculator
+    quantization::noq::NoQuantizer<D>                             NoQuantizer
+    quantization::pq::ProductQuantizer<D>                         ProductQuantizer
+    index::ivf::block_based::index::BlockBasedIvf<Q>              BlockBasedIvf
+    index::hnsw::block_based::index::BlockBasedHnsw<Q>            BlockBasedHnsw
+    index::spann::index::Spann<Q>                                 Spann
+    config::search_params::SearchParams                           SearchParams
+    index::utils::{IdWithScore, SearchResult}                     IdWithScore, SearchResult
+
+Every method that computes runs hand-written CUDA kernels; there is no CPU fallback (a missing library or device
+raises).  Single-query methods keep the reference's names and argument meaning; `*_batch` methods are the batched
+entry points the GPU path is built for.  Array arguments may be numpy arrays (host) or torch CUDA tensors (device).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import NamedTuple, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import (DEVICE, DOT, HOST, L2, QUANT_NONE, QUANT_PQ, InvalidArgument, MuopdbGpuError, NoDevice, OutOfRange,
+                   Unsupported)
+
+__all__ = ["Context", "default_context", "L2DistanceCalculator", "DotProductDistanceCalculator", "NoQuantizer",
+           "ProductQuantizer", "BlockBasedIvf", "BlockBasedHnsw", "Spann", "SearchParams", "IdWithScore", "SearchResult",
+           "merge_topk", "assign_to_centroids", "L2", "DOT", "MuopdbGpuError", "OutOfRange", "InvalidArgument", "Unsupported",
+           "NoDevice"]
+
+
+# ---- buffers ---------------------------------------------------------------------------------------------------------
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class _Buf:
+    """Pointer + residency of an array argument (numpy host array or torch CUDA tensor)."""
+
+    def __init__(self, x, dtype, shape=None, allow_none=False):
+        self.keep = None
+        if x is None:
+            assert allow_none
+            self.ptr, self.mem = None, None
+            return
+        if _is_torch(x):
+            import torch
+            tdt = {np.float32: torch.float32, np.uint8: torch.uint8, np.uint32: torch.int32, np.int32: torch.int32,
+                   np.uint64: torch.int64}[dtype]
+            if x.dtype != tdt and not (dtype == np.uint32 and x.dtype in (torch.int32, torch.uint32)) \
+                    and not (dtype == np.uint64 and x.dtype in (torch.int64, torch.uint64)):
+                raise InvalidArgument(_lib.ERR_INVALID_ARG, f"tensor dtype {x.dtype} != {tdt}")
+            if not x.is_contiguous():
+                x = x.contiguous()
+            self.keep = x
+            self.ptr = x.data_ptr()
+            self.mem = DEVICE if x.is_cuda else HOST
+            self.shape = tuple(x.shape)
+        else:
+            a = np.ascontiguousarray(x, dtype=dtype)
+            self.keep = a
+            self.ptr = a.ctypes.data
+            self.mem = HOST
+            self.shape = a.shape
+        if shape is not None:
+            a_shape = self.shape
+            for want, got in zip(shape, a_shape):
+                if want is not None and want != got:
+                    raise InvalidArgument(_lib.ERR_INVALID_ARG, f"shape {a_shape} does not match {shape}")
+
+
+def _pairs_to_ints(p: np.ndarray) -> list:
+    p = np.asarray(p, dtype=np.uint64).reshape(-1, 2)
+    return [int(lo) | (int(hi) << 64) for lo, hi in p]
+
+
+def _ints_to_pairs(ids) -> Optional[np.ndarray]:
+    if ids is None:
+        return None
+    a = np.asarray(ids)
+    if a.dtype == np.uint64 and a.ndim == 2 and a.shape[1] == 2:
+        return np.ascontiguousarray(a)
+    if a.dtype != object and a.ndim == 1 and a.dtype.kind in "iu":
+        out = np.zeros((a.shape[0], 2), dtype=np.uint64)
+        out[:, 0] = a.astype(np.uint64)
+        return out
+    out = np.empty((len(ids), 2), dtype=np.uint64)
+    for i, d in enumerate(ids):
+        d = int(d)
+        out[i, 0] = d & 0xFFFFFFFFFFFFFFFF
+        out[i, 1] = d >> 64
+    return out
+
+
+# ---- context ---------------------------------------------------------------------------------------------------------
+class Context:
+    """One mgpu_ctx: a device, a stream and a workspace.  Calls on one context are serialised."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self.lib.mgpu_init(device, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _lib.check(self.lib.mgpu_sync(self.h), self.h)
+
+    @property
+    def sm_count(self) -> int:
+        return self.lib.mgpu_device_sm_count(self.h)
+
+    @property
+    def stream(self) -> int:
+        return self.lib.mgpu_stream(self.h)
+
+    def timer_start(self):
+        _lib.check(self.lib.mgpu_timer_start(self.h), self.h)
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        _lib.check(self.lib.mgpu_timer_stop(self.h, C.byref(ms)), self.h)
+        return ms.value
+
+    def profile_enable(self, on=True):
+        _lib.check(self.lib.mgpu_profile_enable(self.h, int(on)), self.h)
+
+    def profile_reset(self):
+        _lib.check(self.lib.mgpu_profile_reset(self.h), self.h)
+
+    def profile_get(self, kernel_class: int):
+        ms, n = C.c_float(), C.c_uint64()
+        _lib.check(self.lib.mgpu_profile_get(self.h, kernel_class, C.byref(ms), C.byref(n)), self.h)
+        return ms.value, n.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.mgpu_launch_count(self.h))
+
+    # multi-GPU (one process per GPU)
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _lib.check(self.lib.mgpu_comm_init(self.h, nranks, rank, C.addressof(buf)), self.h)
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _lib.check(_lib.load().mgpu_comm_unique_id(C.addressof(buf)))
+        return bytes(buf)
+
+    def shard_allgather_merge(self, local_doc_ids, local_scores, local_counts, B, k, out_doc_ids, out_scores, out_counts):
+        """All device tensors: doc ids (B,k,2) int64, scores (B,k) f32, counts (B,) int32."""
+        _lib.check(self.lib.mgpu_shard_allgather_merge(self.h, local_doc_ids.data_ptr(), local_scores.data_ptr(),
+                                                       local_counts.data_ptr(), B, k, out_doc_ids.data_ptr(),
+                                                       out_scores.data_ptr(), out_counts.data_ptr()), self.h)
+
+
+_default_ctx = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+# ---- DistanceCalculator (rs/utils/src/lib.rs:17-40) ---------------------------------------------------------------------
+class _DistanceCalculator:
+    METRIC = L2
+
+    @classmethod
+    def calculate_batch(cls, A, B, squared=False, ctx: Optional[Context] = None):
+        """All pairs: out[i, j] = calculate(A[i], B[j]) (calculate_squared when squared=True)."""
+        ctx = ctx or default_context()
+        a, b = _Buf(A, np.float32), _Buf(B, np.float32)
+        if len(a.shape) != 2 or len(b.shape) != 2 or a.shape[1] != b.shape[1]:
+            raise InvalidArgument(_lib.ERR_INVALID_ARG, "calculate_batch expects (nA, dim) and (nB, dim)")
+        if a.mem != b.mem:
+            raise InvalidArgument(_lib.ERR_INVALID_ARG, "A and B must live in the same memory space")
+        nA, dim = a.shape
+        nB = b.shape[0]
+        if a.mem == DEVICE:
+            import torch
+            out = torch.empty((nA, nB), dtype=torch.float32, device=A.device)
+            optr = out.data_ptr()
+        else:
+            out = np.empty((nA, nB), dtype=np.float32)
+            optr = out.ctypes.data
+        _lib.check(ctx.lib.mgpu_distance_batch(ctx.h, a.ptr, nA, b.ptr, nB, dim, cls.METRIC, int(squared), optr, a.mem), ctx.h)
+        return out
+
+    @classmethod
+    def calculate(cls, a, b) -> float:
+        """DistanceCalculator::calculate(a, b) -> f32."""
+        a = np.asarray(a, dtype=np.float32).reshape(1, -1)
+        b = np.asarray(b, dtype=np.float32).reshape(1, -1)
+        return float(cls.calculate_batch(a, b)[0, 0])
+
+    @classmethod
+    def calculate_squared(cls, a, b) -> float:
+        """CalculateSquared::calculate_squared(a, b) -> f32."""
+        a = np.asarray(a, dtype=np.float32).reshape(1, -1)
+        b = np.asarray(b, dtype=np.float32).reshape(1, -1)
+        return float(cls.calculate_batch(a, b, squared=True)[0, 0])
+
+
+class L2DistanceCalculator(_DistanceCalculator):
+    """rs/utils/src/distance/l2.rs:17-100"""
+    METRIC = L2
+
+
+class DotProductDistanceCalculator(_DistanceCalculator):
+    """rs/utils/src/distance/dot_product.rs:7-99 (negated dot; calculate_squared forwards to calculate)"""
+    METRIC = DOT
+
+
+# ---- Quantizers (rs/quantization/src/quantization.rs:6-38) ----------------------------------------------------------------
+class NoQuantizer:
+    """rs/quantization/src/noq/mod.rs:14-60"""
+    QUANT = QUANT_NONE
+
+    def __init__(self, dimension: int, distance=L2DistanceCalculator):
+        self.dimension = dimension
+        self.calculator = distance
+        self.metric = distance.METRIC
+        self.handle = None
+
+    def quantize(self, value):
+        return np.array(value, dtype=np.float32, copy=True)
+
+    def quantized_dimension(self) -> int:
+        return self.dimension
+
+    def original_vector(self, quantized):
+        return np.array(quantized, dtype=np.float32, copy=True)
+
+    def distance(self, query, point) -> float:
+        return self.calculator.calculate(query, point)
+
+
+class ProductQuantizer:
+    """rs/quantization/src/pq/mod.rs:23-286.  The codebook ([subspace][centroid][dsub] f32) is an input."""
+    QUANT = QUANT_PQ
+
+    def __init__(self, dimension: int, subvector_dimension: int, num_bits: int, codebook, distance=L2DistanceCalculator,
+                 ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        self.dimension, self.subvector_dimension, self.num_bits = dimension, subvector_dimension, num_bits
+        self.metric = distance.METRIC
+        cb = np.ascontiguousarray(codebook, dtype=np.float32).reshape(-1)
+        if subvector_dimension <= 0 or dimension % subvector_dimension != 0:
+            raise InvalidArgument(_lib.ERR_INVALID_ARG, "Dimensions are not valid")  # pq/mod.rs:41-46
+        if cb.size != dimension * (1 << num_bits):
+            raise InvalidArgument(_lib.ERR_INVALID_ARG, "codebook size does not match dimension * 2^num_bits")
+        self.codebook = cb
+        h = C.c_void_p()
+        _lib.check(self.ctx.lib.mgpu_pq_create(self.ctx.h, dimension, subvector_dimension, num_bits, cb.ctypes.data,
+                                               self.metric, C.byref(h)), self.ctx.h)
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx.lib.mgpu_pq_destroy(self.handle)
+        except Exception:
+            pass
+
+    def quantized_dimension(self) -> int:
+        return self.dimension // self.subvector_dimension
+
+    def quantize(self, value):
+        """Quantizer::quantize; accepts one vector or a batch (n, dim)."""
+        single = (not _is_torch(value)) and np.ndim(value) == 1
+        x = _Buf(np.asarray(value, dtype=np.float32).reshape(1, -1) if single else value, np.float32, (None, self.dimension))
+        n = x.shape[0]
+        m = self.quantized_dimension()
+        if x.mem == DEVICE:
+            import torch
+            out = torch.empty((n, m), dtype=torch.uint8, device=value.device)
+            optr = out.data_ptr()
+        else:
+            out = np.empty((n, m), dtype=np.uint8)
+            optr = out.ctypes.data
+        _lib.check(self.ctx.lib.mgpu_pq_quantize_batch(self.handle, x.ptr, n, optr, x.mem), self.ctx.h)
+        return out[0] if single else out
+
+    def original_vector(self, quantized):
+        """pq/mod.rs:184-200 -- a gather from the codebook (no arithmetic)."""
+        q = np.asarray(quantized, dtype=np.uint8)
+        cb = self.codebook.reshape(self.quantized_dimension(), 1 << self.num_bits, self.subvector_dimension)
+        return cb[np.arange(q.size), q].reshape(-1).copy()
+
+    def distance(self, a, b):
+        """Quantizer::distance(a, b, StreamingSIMD); a and b are code words (m,) or batches (n, m) -> (n,)."""
+        single = np.ndim(a) == 1
+        a2 = np.ascontiguousarray(np.asarray(a, dtype=np.uint8).reshape(-1, self.quantized_dimension()))
+        b2 = np.ascontiguousarray(np.asarray(b, dtype=np.uint8).reshape(-1, self.quantized_dimension()))
+        out = np.empty(a2.shape[0], dtype=np.float32)
+        _lib.check(self.ctx.lib.mgpu_pq_distance_batch(self.handle, a2.ctypes.data, b2.ctypes.data, a2.shape[0],
+                                                       out.ctypes.data, HOST), self.ctx.h)
+        return float(out[0]) if single else out
+
+
+# ---- results --------------------------------------------------------------------------------------------------------------
+class IdWithScore(NamedTuple):
+    """rs/index/src/utils.rs:89-93"""
+    doc_id: int
+    score: float
+
+
+@dataclass
+class SearchResult:
+    """rs/index/src/utils.rs:152-155 (stats.num_pages_accessed has no meaning for an HBM-resident index: always 0)"""
+    id_with_scores: list
+    num_pages_accessed: int = 0
+
+
+@dataclass
+class SearchParams:
+    """rs/config/src/search_params.rs:2-34"""
+    top_k: int
+    ef_construction: int
+    record_pages: bool = False
+    num_explored_centroids: Optional[int] = None
+    centroid_distance_ratio: float = 0.1
+
+    def explored(self) -> int:
+        return self.top_k if self.num_explored_centroids is None else self.num_explored_centroids
+
+
+class BatchResult(NamedTuple):
+    doc_ids: object   # (B, k, 2) uint64 (numpy) / int64 (torch): (lo, hi) of each u128 doc id
+    scores: object    # (B, k) float32
+    counts: object    # (B,) number of valid entries per query (UINT32_MAX encodes None for Spann)
+
+    def to_results(self):
+        d, s, c = (np.asarray(x.cpu()) if _is_torch(x) else x for x in (self.doc_ids, self.scores, self.counts))
+        d = d.view(np.uint64) if d.dtype != np.uint64 else d
+        out = []
+        for b in range(len(c)):
+            n = int(np.uint32(c[b]))
+            if n == 0xFFFFFFFF:
+                out.append(None)
+                continue
+            ids = _pairs_to_ints(d[b, :n])
+            out.append(SearchResult([IdWithScore(i, float(x)) for i, x in zip(ids, s[b, :n])]))
+        return out
+
+
+def _alloc_out(B, k, device_like, u128=True):
+    k = max(int(k), 1)
+    if device_like is not None:
+        import torch
+        ids = torch.zeros((B, k, 2) if u128 else (B, k), dtype=torch.int64 if u128 else torch.int32, device=device_like.device)
+        scores = torch.zeros((B, k), dtype=torch.float32, device=device_like.device)
+        counts = torch.zeros((B,), dtype=torch.int32, device=device_like.device)
+        return ids, scores, counts, ids.data_ptr(), scores.data_ptr(), counts.data_ptr()
+    ids = np.zeros((B, k, 2) if u128 else (B, k), dtype=np.uint64 if u128 else np.uint32)
+    scores = np.zeros((B, k), dtype=np.float32)
+    counts = np.zeros((B,), dtype=np.uint32)
+    return ids, scores, counts, ids.ctypes.data, scores.ctypes.data, counts.ctypes.data
+
+
+# ---- BlockBasedIvf<Q> (rs/index/src/ivf/block_based/index.rs) ---------------------------------------------------------------
+class BlockBasedIvf:
+    """HBM-resident IVF index.  Inputs are the arrays BlockBasedIvf::new reads from the `index` and `vectors` files
+    (ivf/writer.rs:300-353): centroids, posting lists (offsets + ascending point ids), rows by point id, doc ids."""
+
+    def __init__(self, centroids, list_offsets, list_point_ids, rows, quantizer, doc_ids=None, ctx: Optional[Context] = None):
+        self.ctx = ctx or getattr(quantizer, "ctx", None) or default_context()
+        self.quantizer = quantizer
+        cent = np.ascontiguousarray(centroids, dtype=np.float32)
+        if cent.ndim != 2:
+            raise InvalidArgument(_lib.ERR_INVALID_ARG, "centroids must be (nlist, dim)")
+        self.nlist, self.dim = cent.shape
+        lo = np.ascontiguousarray(list_offsets, dtype=np.uint64)
+        ids = np.ascontiguousarray(list_point_ids, dtype=np.uint32)
+        if lo.size != self.nlist + 1:
+            raise InvalidArgument(_lib.ERR_INVALID_ARG, "list_offsets must have nlist + 1 entries")
+        rdt = np.uint8 if quantizer.QUANT == QUANT_PQ else np.float32
+        r = _Buf(rows, rdt, (None, quantizer.quantized_dimension()))
+        n = r.shape[0]
+        docs = _ints_to_pairs(doc_ids)
+        if docs is not None and docs.shape[0] != n:
+            raise InvalidArgument(_lib.ERR_INVALID_ARG, "doc_ids must have one entry per row")
+        h = C.c_void_p()
+        _lib.check(self.ctx.lib.mgpu_ivf_create(self.ctx.h, self.dim, self.nlist, cent.ctypes.data, lo.ctypes.data,
+                                                ids.ctypes.data if ids.size else None, quantizer.QUANT, quantizer.metric,
+                                                quantizer.handle, r.ptr, r.mem, n,
+                                                docs.ctypes.data if docs is not None else None, C.byref(h)), self.ctx.h)
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx.lib.mgpu_ivf_destroy(self.handle)
+        except Exception:
+            pass
+
+    def num_clusters(self) -> int:
+        return int(self.ctx.lib.mgpu_ivf_num_clusters(self.handle))
+
+    def num_vectors(self) -> int:
+        return int(self.ctx.lib.mgpu_ivf_num_vectors(self.handle))
+
+    def invalidate_batch(self, point_ids: Sequence[int]):
+        a = np.ascontiguousarray(point_ids, dtype=np.uint32)
+        _lib.check(self.ctx.lib.mgpu_ivf_invalidate(self.handle, a.ctypes.data, a.size), self.ctx.h)
+
+    def invalidate(self, point_id: int):
+        self.invalidate_batch([point_id])
+
+    def is_invalidated(self, point_id: int) -> bool:
+        o = C.c_int()
+        _lib.check(self.ctx.lib.mgpu_ivf_is_invalidated(self.handle, point_id, C.byref(o)), self.ctx.h)
+        return bool(o.value)
+
+    # -- batched entry points
+    def find_nearest_centroids_batch(self, Q, num_probes: int, with_distances=False):
+        q = _Buf(Q, np.float32, (None, self.dim))
+        B = q.shape[0]
+        p = max(num_probes, 1)
+        if q.mem == DEVICE:
+            import torch
+            ids = torch.zeros((B, p), dtype=torch.int32, device=Q.device)
+            ds = torch.zeros((B, p), dtype=torch.float32, device=Q.device)
+            ip, dp = ids.data_ptr(), ds.data_ptr()
+        else:
+            ids = np.zeros((B, p), dtype=np.uint32)
+            ds = np.zeros((B, p), dtype=np.float32)
+            ip, dp = ids.ctypes.data, ds.ctypes.data
+        _lib.check(self.ctx.lib.mgpu_ivf_coarse(self.handle, q.ptr, B, num_probes, ip, dp, q.mem), self.ctx.h)
+        return (ids, ds) if with_distances else ids
+
+    def search_with_centroids_batch(self, Q, centroid_ids, k: int, counts=None, remap=True):
+        """search_with_centroids(_and_remap) for a batch; centroid_ids (B, P), counts (B,) optional."""
+        q = _Buf(Q, np.float32, (None, self.dim))
+        B = q.shape[0]
+        pr = _Buf(centroid_ids, np.uint32, (B, None))
+        pc = _Buf(counts, np.uint32, (B,), allow_none=True)
+        if pr.mem != q.mem or (pc.mem is not None and pc.mem != q.mem):
+            raise InvalidArgument(_lib.ERR_INVALID_ARG, "queries and probe lists must live in the same memory space")
+        P = pr.shape[1]
+        ids, scores, cnt, ip, sp, cp = _alloc_out(B, k, Q if q.mem == DEVICE else None, u128=remap)
+        f = self.ctx.lib.mgpu_ivf_scan_remap if remap else self.ctx.lib.mgpu_ivf_scan
+        _lib.check(f(self.handle, q.ptr, B, pr.ptr, P, pc.ptr, k, ip, sp, cp, q.mem), self.ctx.h)
+        return BatchResult(ids, scores, cnt)
+
+    def search_batch(self, Q, k: int, num_probes: int, out=None) -> BatchResult:
+        """BlockBasedIvf::search for a batch of queries: coarse scoring + list scan + remap, all on the GPU."""
+        q = _Buf(Q, np.float32, (None, self.dim))
+        B = q.shape[0]
+        if out is None:
+            ids, scores, cnt, ip, sp, cp = _alloc_out(B, k, Q if q.mem == DEVICE else None)
+        else:
+            ids, scores, cnt = out
+            ip, sp, cp = (x.data_ptr() if _is_torch(x) else x.ctypes.data for x in out)
+        _lib.check(self.ctx.lib.mgpu_ivf_search(self.handle, q.ptr, B, k, num_probes, ip, sp, cp, q.mem), self.ctx.h)
+        return BatchResult(ids, scores, cnt)
+
+    def last_scan_rows(self) -> int:
+        return int(self.ctx.lib.mgpu_ivf_last_scan_rows(self.handle))
+
+    def last_scan_bytes(self) -> int:
+        return int(self.ctx.lib.mgpu_ivf_last_scan_bytes(self.handle))
+
+    # -- the reference's single-query methods
+    def find_nearest_centroids(self, vector, num_probes: int) -> list:
+        """index.rs:147-163"""
+        ids = self.find_nearest_centroids_batch(np.asarray(vector, dtype=np.float32).reshape(1, -1), num_probes)
+        return [int(x) for x in ids[0]]
+
+    def search_with_centroids_and_remap(self, query, nearest_centroid_ids, k: int) -> SearchResult:
+        """index.rs:298-332"""
+        c = np.asarray(nearest_centroid_ids, dtype=np.uint32).reshape(1, -1)
+        if c.size == 0:
+            return SearchResult([])
+        r = self.search_with_centroids_batch(np.asarray(query, dtype=np.float32).reshape(1, -1), c, k)
+        return r.to_results()[0]
+
+    def search(self, query, k: int, num_probes: int) -> Optional[SearchResult]:
+        """index.rs:396-412"""
+        return self.search_batch(np.asarray(query, dtype=np.float32).reshape(1, -1), k, num_probes).to_results()[0]
+
+
+# ---- BlockBasedHnsw<Q> (rs/index/src/hnsw/block_based/index.rs) --------------------------------------------------------------
+class BlockBasedHnsw:
+    """HBM-resident HNSW graph in the array layout of the `hnsw/index` file (graph_storage.rs:122-193)."""
+
+    def __init__(self, num_layers, edges, points, edge_offsets, level_offsets, rows, quantizer, doc_ids=None,
+                 ctx: Optional[Context] = None):
+        self.ctx = ctx or getattr(quantizer, "ctx", None) or default_context()
+        self.quantizer = quantizer
+        e = np.ascontiguousarray(edges, dtype=np.uint32)
+        p = np.ascontiguousarray(points, dtype=np.uint32)
+        eo = np.ascontiguousarray(edge_offsets, dtype=np.uint64)
+        lo = np.ascontiguousarray(level_offsets, dtype=np.uint64)
+        if lo.size != num_layers + 1:
+            raise InvalidArgument(_lib.ERR_INVALID_ARG, "level_offsets must have num_layers + 1 entries")
+        rdt = np.uint8 if quantizer.QUANT == QUANT_PQ else np.float32
+        r = _Buf(rows, rdt, (None, quantizer.quantized_dimension()))
+        n = r.shape[0]
+        self.dim = quantizer.dimension
+        docs = _ints_to_pairs(doc_ids)
+        h = C.c_void_p()
+        _lib.check(self.ctx.lib.mgpu_hnsw_create(self.ctx.h, self.dim, int(num_layers), e.ctypes.data if e.size else None,
+                                                 e.size, p.ctypes.data if p.size else None, p.size, eo.ctypes.data, eo.size,
+                                                 lo.ctypes.data, quantizer.QUANT, quantizer.metric, quantizer.handle, r.ptr,
+                                                 r.mem, n, docs.ctypes.data if docs is not None else None, C.byref(h)),
+                   self.ctx.h)
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx.lib.mgpu_hnsw_destroy(self.handle)
+        except Exception:
+            pass
+
+    def ann_search_batch(self, Q, k: int, ef: int, with_stats=False):
+        q = _Buf(Q, np.float32, (None, self.dim))
+        B = q.shape[0]
+        ids, scores, cnt, ip, sp, cp = _alloc_out(B, k, Q if q.mem == DEVICE else None)
+        stats, stp = None, None
+        if with_stats:
+            if q.mem == DEVICE:
+                import torch
+                stats = torch.zeros((B, 2), dtype=torch.int64, device=Q.device)
+                stp = stats.data_ptr()
+            else:
+                stats = np.zeros((B, 2), dtype=np.uint64)
+                stp = stats.ctypes.data
+        _lib.check(self.ctx.lib.mgpu_hnsw_search(self.handle, q.ptr, B, k, ef, ip, sp, cp, stp, q.mem), self.ctx.h)
+        r = BatchResult(ids, scores, cnt)
+        return (r, stats) if with_stats else r
+
+    def ann_search(self, query, k: int, ef: int) -> SearchResult:
+        """index.rs:159-210"""
+        return self.ann_search_batch(np.asarray(query, dtype=np.float32).reshape(1, -1), k, ef).to_results()[0]
+
+
+# ---- Spann<Q> (rs/index/src/spann/index.rs) ---------------------------------------------------------------------------------
+class Spann:
+    def __init__(self, centroids: BlockBasedHnsw, posting_lists: BlockBasedIvf):
+        self.ctx = posting_lists.ctx
+        self.centroids, self.posting_lists = centroids, posting_lists
+        h = C.c_void_p()
+        _lib.check(self.ctx.lib.mgpu_spann_create(self.ctx.h, centroids.handle, posting_lists.handle, C.byref(h)), self.ctx.h)
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx.lib.mgpu_spann_destroy(self.handle)
+        except Exception:
+            pass
+
+    def search_batch(self, Q, params: SearchParams) -> BatchResult:
+        q = _Buf(Q, np.float32, (None, self.posting_lists.dim))
+        B = q.shape[0]
+        ids, scores, cnt, ip, sp, cp = _alloc_out(B, params.top_k, Q if q.mem == DEVICE else None)
+        _lib.check(self.ctx.lib.mgpu_spann_search(self.handle, q.ptr, B, params.top_k, params.ef_construction,
+                                                  params.explored(), float(params.centroid_distance_ratio), ip, sp, cp,
+                                                  q.mem), self.ctx.h)
+        return BatchResult(ids, scores, cnt)
+
+    def search(self, query, params: SearchParams) -> Optional[SearchResult]:
+        """spann/index.rs:211-266"""
+        return self.search_batch(np.asarray(query, dtype=np.float32).reshape(1, -1), params).to_results()[0]
+
+
+# ---- merge / assignment ---------------------------------------------------------------------------------------------------
+def merge_topk(doc_ids, scores, counts, k: int, ctx: Optional[Context] = None) -> BatchResult:
+    """Snapshot merge (collection/snapshot.rs:49-63,79-108): doc_ids (S,B,k,2), scores (S,B,k), counts (S,B)."""
+    ctx = ctx or default_context()
+    d, s, c = _Buf(doc_ids, np.uint64), _Buf(scores, np.float32), _Buf(counts, np.uint32)
+    S, B = s.shape[0], s.shape[1]
+    kk = s.shape[2]
+    if kk != k:
+        raise InvalidArgument(_lib.ERR_INVALID_ARG, "partial results must have stride k")
+    ids, sc, cnt, ip, sp, cp = _alloc_out(B, k, doc_ids if d.mem == DEVICE else None)
+    _lib.check(ctx.lib.mgpu_merge_topk(ctx.h, d.ptr, s.ptr, c.ptr, S, B, k, ip, sp, cp, d.mem), ctx.h)
+    return BatchResult(ids, sc, cnt)
+
+
+def assign_to_centroids(X, centroids, max_clusters_per_vector=1, distance_threshold=0.1, ctx: Optional[Context] = None):
+    """IvfBuilder::find_nearest_centroids + acceptance rule (ivf/builder.rs:268-329) for a batch of vectors.
+    -> (cids (n, max_clusters) padded with UINT32_MAX, counts (n,))"""
+    ctx = ctx or default_context()
+    x, c = _Buf(X, np.float32), _Buf(centroids, np.float32)
+    if x.mem != c.mem:
+        raise InvalidArgument(_lib.ERR_INVALID_ARG, "X and centroids must live in the same memory space")
+    n, dim = x.shape
+    r = max_clusters_per_vector
+    if x.mem == DEVICE:
+        import torch
+        cids = torch.zeros((n, r), dtype=torch.int32, device=X.device)
+        cnt = torch.zeros((n,), dtype=torch.int32, device=X.device)
+        ip, cp = cids.data_ptr(), cnt.data_ptr()
+    else:
+        cids = np.zeros((n, r), dtype=np.uint32)
+        cnt = np.zeros((n,), dtype=np.uint32)
+        ip, cp = cids.ctypes.data, cnt.ctypes.data
+    _lib.check(ctx.lib.mgpu_ivf_assign(ctx.h, x.ptr, n, c.ptr, c.shape[0], dim, r, float(distance_threshold), ip, cp, x.mem), ctx.h)
+    return cids, cnt

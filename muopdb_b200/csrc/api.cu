@@ -1,0 +1,959 @@
+// api.cu -- the extern "C" boundary declared in include/muopdb_gpu.h: contexts, resident index handles and the
+// per-call orchestration (H2D staging -> kernels on the ctx stream -> D2H).  No CPU compute fallback exists:
+// every entry point that computes needs a CUDA device.
+#include <dlfcn.h>
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "internal.cuh"
+
+int mgpu_fail(mgpu_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+int mgpu_ws_reserve(mgpu_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->ws_bytes) return MGPU_OK;
+  if (ctx->ws) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->ws); ctx->ws = nullptr; ctx->ws_bytes = 0; }
+  size_t want = bytes + bytes / 4;
+  CUDA_TRY(ctx, cudaMalloc(&ctx->ws, want));
+  ctx->ws_bytes = want;
+  return MGPU_OK;
+}
+
+int mgpu_pinned_reserve(mgpu_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->pinned_bytes) return MGPU_OK;
+  if (ctx->pinned) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
+  size_t want = bytes + bytes / 4;
+  CUDA_TRY(ctx, cudaMallocHost(&ctx->pinned, want));
+  ctx->pinned_bytes = want;
+  return MGPU_OK;
+}
+
+template <class T>
+static int dev_alloc_copy(mgpu_ctx *ctx, T **dst, const T *src, size_t n, bool src_is_device = false) {
+  *dst = nullptr;
+  if (n == 0) n = 1;
+  CUDA_TRY(ctx, cudaMalloc((void **)dst, n * sizeof(T)));
+  if (src) CUDA_TRY(ctx, cudaMemcpyAsync(*dst, src, n * sizeof(T), src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  return MGPU_OK;
+}
+
+extern "C" {
+
+const char *mgpu_version(void) { return "muopdb_b200 0.1 (sm_100a)"; }
+
+int mgpu_init(int device, mgpu_ctx **out) {
+  if (!out) return MGPU_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return MGPU_ERR_NO_DEVICE;
+  if (device < 0 || device >= count) return MGPU_ERR_INVALID_ARG;
+  mgpu_ctx *ctx = new mgpu_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return MGPU_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return MGPU_ERR_CUDA; }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MGPU_ERR_CUDA; }
+  cudaEventCreate(&ctx->t0);
+  cudaEventCreate(&ctx->t1);
+  *out = ctx;
+  return MGPU_OK;
+}
+
+void mgpu_destroy(mgpu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  mgpu_comm_destroy(ctx);
+  mgpu_profile_reset(ctx);
+  if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  cudaEventDestroy(ctx->t0);
+  cudaEventDestroy(ctx->t1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *mgpu_last_error(mgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int mgpu_sync(mgpu_ctx *ctx) {
+  if (!ctx) return MGPU_ERR_INVALID_ARG;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return MGPU_OK;
+}
+void *mgpu_stream(mgpu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int mgpu_device_sm_count(mgpu_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+int mgpu_timer_start(mgpu_ctx *ctx) {
+  if (!ctx) return MGPU_ERR_INVALID_ARG;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->t0, ctx->stream));
+  return MGPU_OK;
+}
+int mgpu_timer_stop(mgpu_ctx *ctx, float *ms) {
+  if (!ctx || !ms) return MGPU_ERR_INVALID_ARG;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->t1, ctx->stream));
+  CUDA_TRY(ctx, cudaEventSynchronize(ctx->t1));
+  CUDA_TRY(ctx, cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+  return MGPU_OK;
+}
+
+int mgpu_profile_enable(mgpu_ctx *ctx, int on) {
+  if (!ctx) return MGPU_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->profiling = on != 0;
+  return MGPU_OK;
+}
+int mgpu_profile_reset(mgpu_ctx *ctx) {
+  if (!ctx) return MGPU_ERR_INVALID_ARG;
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &p : ctx->prof) {
+    for (auto e : p.ev) cudaEventDestroy(e);
+    p.ev.clear(); p.launches = 0; p.done_ms = 0.f;
+  }
+  return MGPU_OK;
+}
+int mgpu_profile_get(mgpu_ctx *ctx, int cls, float *total_ms, uint64_t *launches) {
+  if (!ctx || cls < 0 || cls >= MGPU_K_COUNT) return MGPU_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  auto &p = ctx->prof[cls];
+  for (size_t i = 0; i + 1 < p.ev.size(); i += 2) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.ev[i], p.ev[i + 1]);
+    p.done_ms += ms;
+  }
+  for (auto e : p.ev) cudaEventDestroy(e);
+  p.ev.clear();
+  if (total_ms) *total_ms = p.done_ms;
+  if (launches) *launches = p.launches;
+  return MGPU_OK;
+}
+uint64_t mgpu_launch_count(mgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- helpers: stage caller buffers ------------------------------------------------------------------------------------
+// in: returns a device pointer holding `bytes` of src (copying through the workspace when src is host memory)
+static int stage_in(mgpu_ctx *ctx, const void *src, size_t bytes, int mem, void *ws_slot, const void **dptr) {
+  if (mem == MGPU_DEVICE) { *dptr = src; return MGPU_OK; }
+  CUDA_TRY(ctx, cudaMemcpyAsync(ws_slot, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  *dptr = ws_slot;
+  return MGPU_OK;
+}
+static int stage_out(mgpu_ctx *ctx, void *dst, const void *dsrc, size_t bytes, int mem) {
+  if (mem == MGPU_DEVICE || dst == nullptr) return MGPU_OK;
+  CUDA_TRY(ctx, cudaMemcpyAsync(dst, dsrc, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return MGPU_OK;
+}
+
+// ---- distances ------------------------------------------------------------------------------------------------------------
+int mgpu_distance_batch(mgpu_ctx *ctx, const float *A, uint64_t nA, const float *B, uint64_t nB, uint32_t dim,
+                        int metric, int squared, float *out, int mem) {
+  if (!ctx || !A || !B || !out || dim == 0) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "distance_batch: null/zero argument");
+  if (metric != MGPU_L2 && metric != MGPU_DOT) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "distance_batch: bad metric");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  size_t bA = nA * dim * 4, bB = nB * dim * 4, bO = nA * nB * 4;
+  const float *dA = A, *dB = B;
+  float *dO = out;
+  if (mem == MGPU_HOST) {
+    size_t need = ws_need(ws_need(ws_need(0, bA), bB), bO);
+    MGPU_TRY(mgpu_ws_reserve(ctx, need));
+    WsAlloc w(ctx->ws, ctx->ws_bytes);
+    float *a = w.get<float>(nA * dim), *b = w.get<float>(nB * dim);
+    dO = w.get<float>(nA * nB);
+    CUDA_TRY(ctx, cudaMemcpyAsync(a, A, bA, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(b, B, bB, cudaMemcpyHostToDevice, ctx->stream));
+    dA = a; dB = b;
+  }
+  MGPU_TRY(launch_distance_matrix(ctx, dA, nA, dB, nB, dim, metric, squared ? 0 : 1, dO, MGPU_K_OTHER));
+  if (mem == MGPU_HOST) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, dO, bO, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return MGPU_OK;
+}
+
+// ---- product quantizer ----------------------------------------------------------------------------------------------------
+int mgpu_pq_create(mgpu_ctx *ctx, uint32_t dim, uint32_t dsub, uint32_t nbits, const float *codebook, int metric,
+                   mgpu_pq **out) {
+  if (!ctx || !out || !codebook) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "pq_create: null argument");
+  *out = nullptr;
+  // ProductQuantizerConfig::validate (pq/mod.rs:41-46)
+  if (dsub == 0 || dim == 0 || dim % dsub != 0) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "pq_create: Dimensions are not valid");
+  if (nbits == 0 || nbits > 8) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "pq_create: num_bits must be in 1..8 (codes are u8)");
+  if (metric != MGPU_L2 && metric != MGPU_DOT) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "pq_create: bad metric");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  mgpu_pq *pq = new mgpu_pq();
+  pq->ctx = ctx; pq->dim = dim; pq->dsub = dsub; pq->nbits = nbits; pq->m = dim / dsub; pq->K = 1u << nbits; pq->metric = metric;
+  size_t ncb = (size_t)pq->m * pq->K * dsub;
+  int s = dev_alloc_copy(ctx, &pq->d_cb, codebook, ncb);
+  if (s == MGPU_OK) s = dev_alloc_copy<float>(ctx, &pq->d_table, nullptr, (size_t)pq->m * pq->K * pq->K);
+  if (s == MGPU_OK) s = dev_alloc_copy<float>(ctx, &pq->d_rowmin, nullptr, (size_t)pq->m * pq->K);
+  if (s == MGPU_OK) s = dev_alloc_copy<float>(ctx, &pq->d_rowmax, nullptr, (size_t)pq->m * pq->K);
+  if (s == MGPU_OK) s = launch_pq_build_table(pq);
+  if (s == MGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) s = mgpu_fail(ctx, MGPU_ERR_CUDA, "pq_create: table build failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (s != MGPU_OK) { mgpu_pq_destroy(pq); return s; }
+  *out = pq;
+  return MGPU_OK;
+}
+
+void mgpu_pq_destroy(mgpu_pq *pq) {
+  if (!pq) return;
+  cudaSetDevice(pq->ctx->device);
+  cudaFree(pq->d_cb); cudaFree(pq->d_table); cudaFree(pq->d_rowmin); cudaFree(pq->d_rowmax);
+  delete pq;
+}
+
+int mgpu_pq_quantize_batch(mgpu_pq *pq, const float *X, uint64_t n, uint8_t *codes, int mem) {
+  if (!pq || (n && (!X || !codes))) return MGPU_ERR_INVALID_ARG;
+  mgpu_ctx *ctx = pq->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (n == 0) return MGPU_OK;
+  const float *dX = X;
+  uint8_t *dC = codes;
+  if (mem == MGPU_HOST) {
+    // bounded staging: encode in slabs so that huge inputs do not need a huge workspace
+    const uint64_t slab = std::max<uint64_t>(1, (256ull << 20) / ((uint64_t)pq->dim * 4));
+    MGPU_TRY(mgpu_ws_reserve(ctx, ws_need(ws_need(0, slab * pq->dim * 4), slab * pq->m)));
+    WsAlloc w(ctx->ws, ctx->ws_bytes);
+    float *dx = w.get<float>(slab * pq->dim);
+    uint8_t *dc = w.get<uint8_t>(slab * pq->m);
+    for (uint64_t i = 0; i < n; i += slab) {
+      uint64_t cnt = std::min(slab, n - i);
+      CUDA_TRY(ctx, cudaMemcpyAsync(dx, X + i * pq->dim, cnt * pq->dim * 4, cudaMemcpyHostToDevice, ctx->stream));
+      MGPU_TRY(launch_pq_quantize(pq, dx, cnt, dc));
+      CUDA_TRY(ctx, cudaMemcpyAsync(codes + i * pq->m, dc, cnt * pq->m, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MGPU_OK;
+  }
+  return launch_pq_quantize(pq, dX, n, dC);
+}
+
+int mgpu_pq_distance_batch(mgpu_pq *pq, const uint8_t *a, const uint8_t *b, uint64_t n, float *out, int mem) {
+  if (!pq || (n && (!a || !b || !out))) return MGPU_ERR_INVALID_ARG;
+  mgpu_ctx *ctx = pq->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (n == 0) return MGPU_OK;
+  if (mem == MGPU_DEVICE) return launch_pq_distance_pairs(pq, a, b, n, out);
+  size_t bc = n * pq->m;
+  MGPU_TRY(mgpu_ws_reserve(ctx, ws_need(ws_need(ws_need(0, bc), bc), n * 4)));
+  WsAlloc w(ctx->ws, ctx->ws_bytes);
+  uint8_t *da = w.get<uint8_t>(bc), *db = w.get<uint8_t>(bc);
+  float *dout = w.get<float>(n);
+  CUDA_TRY(ctx, cudaMemcpyAsync(da, a, bc, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(db, b, bc, cudaMemcpyHostToDevice, ctx->stream));
+  MGPU_TRY(launch_pq_distance_pairs(pq, da, db, n, dout));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return MGPU_OK;
+}
+
+// ---- IVF ------------------------------------------------------------------------------------------------------------------
+int mgpu_ivf_create(mgpu_ctx *ctx, uint32_t dim, uint32_t nlist, const float *centroids, const uint64_t *list_offsets,
+                    const uint32_t *list_point_ids, int quant, int metric, mgpu_pq *pq, const void *rows, int rows_mem,
+                    uint64_t n, const mgpu_u128 *doc_ids, mgpu_ivf **out) {
+  if (!ctx || !out) return MGPU_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (!centroids || !list_offsets || dim == 0 || nlist == 0) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "ivf_create: null/zero argument");
+  if (quant == MGPU_QUANT_PQ && (!pq || pq->dim != dim)) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "ivf_create: PQ quantizer missing or of the wrong dimension");
+  if (quant != MGPU_QUANT_PQ && quant != MGPU_QUANT_NONE) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "ivf_create: bad quantizer kind");
+  if (n >= 0xFFFFFFFFull) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "ivf_create: point ids are u32");
+  uint64_t total_ids = list_offsets[nlist];
+  if (total_ids && (!list_point_ids || !rows)) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "ivf_create: null rows/ids");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+
+  mgpu_ivf *ivf = new mgpu_ivf();
+  ivf->ctx = ctx; ivf->dim = dim; ivf->nlist = nlist; ivf->n = n; ivf->quant = quant;
+  ivf->metric = quant == MGPU_QUANT_PQ ? pq->metric : metric;
+  ivf->pq = quant == MGPU_QUANT_PQ ? pq : nullptr;
+  ivf->dim4 = (dim + 3) / 4;
+  // chunked slot table on the host
+  std::vector<uint32_t> chunk_start(nlist + 1), list_len(nlist);
+  uint64_t chunks = 0;
+  for (uint32_t c = 0; c < nlist; c++) {
+    if (list_offsets[c + 1] < list_offsets[c]) { delete ivf; return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "ivf_create: list_offsets not monotone"); }
+    uint64_t len = list_offsets[c + 1] - list_offsets[c];
+    chunk_start[c] = (uint32_t)chunks;
+    list_len[c] = (uint32_t)len;
+    chunks += (len + 31) / 32;
+  }
+  chunk_start[nlist] = (uint32_t)chunks;
+  if (chunks * 32 >= 0xFFFFFFFFull) { delete ivf; return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "ivf_create: more than 2^32 padded slots"); }
+  ivf->total_chunks = chunks;
+  std::vector<uint32_t> slot_pid(std::max<uint64_t>(chunks * 32, 1), MGPU_EMPTY_SLOT);
+  for (uint32_t c = 0; c < nlist; c++) {
+    uint64_t b = list_offsets[c], len = list_len[c];
+    for (uint64_t i = 0; i < len; i++) {
+      uint32_t pid = list_point_ids[b + i];
+      if (pid >= n) { delete ivf; return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "ivf_create: point id %u out of range", pid); }
+      slot_pid[(uint64_t)chunk_start[c] * 32 + i] = pid;
+    }
+  }
+  ivf->h_list_len = list_len;
+  int s = dev_alloc_copy(ctx, &ivf->d_centroids, centroids, (size_t)nlist * dim);
+  if (s == MGPU_OK) s = dev_alloc_copy(ctx, &ivf->d_chunk_start, chunk_start.data(), nlist + 1);
+  if (s == MGPU_OK) s = dev_alloc_copy(ctx, &ivf->d_list_len, list_len.data(), nlist);
+  if (s == MGPU_OK) s = dev_alloc_copy(ctx, &ivf->d_slot_pid, slot_pid.data(), slot_pid.size());
+  if (s == MGPU_OK && doc_ids) s = dev_alloc_copy(ctx, &ivf->d_doc_ids, doc_ids, n);
+  if (s == MGPU_OK) {
+    s = dev_alloc_copy<uint32_t>(ctx, &ivf->d_invalid, nullptr, (n + 31) / 32 + 1);
+    if (s == MGPU_OK && cudaMemsetAsync(ivf->d_invalid, 0, ((n + 31) / 32 + 1) * 4, ctx->stream) != cudaSuccess) s = MGPU_ERR_CUDA;
+  }
+  if (s == MGPU_OK) {
+    s = dev_alloc_copy<unsigned long long>(ctx, &ivf->d_scan_rows, nullptr, 1);
+    if (s == MGPU_OK) cudaMemsetAsync(ivf->d_scan_rows, 0, 8, ctx->stream);
+  }
+  // rows -> chunked layout
+  void *d_src = nullptr;
+  bool own_src = false;
+  size_t row_bytes = quant == MGPU_QUANT_PQ ? pq->m : (size_t)dim * 4;
+  if (s == MGPU_OK && chunks) {
+    if (rows_mem == MGPU_DEVICE) d_src = const_cast<void *>(rows);
+    else {
+      if (cudaMalloc(&d_src, std::max<size_t>(n * row_bytes, 16)) != cudaSuccess) s = mgpu_fail(ctx, MGPU_ERR_OOM, "ivf_create: staging %zu bytes of rows failed", n * row_bytes);
+      else { own_src = true; if (cudaMemcpyAsync(d_src, rows, n * row_bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) s = MGPU_ERR_CUDA; }
+    }
+  }
+  if (s == MGPU_OK) {
+    size_t nslots = std::max<uint64_t>(chunks * 32, 1);
+    if (quant == MGPU_QUANT_PQ) {
+      ivf->pq_fast = pq->nbits == 8 && pq->m % 32 == 0 && pq->m / 32 <= 4;
+      ivf->ng = ivf->pq_fast ? pq->m / 32 : 0;
+      ivf->bytes_per_row = pq->m + 4;
+      s = dev_alloc_copy<uint8_t>(ctx, &ivf->d_codes, nullptr, nslots * pq->m);
+    } else {
+      ivf->bytes_per_row = (uint64_t)dim * 4 + 4;
+      s = dev_alloc_copy<float>(ctx, &ivf->d_rows, nullptr, nslots * ivf->dim4 * 4);
+    }
+  }
+  if (s == MGPU_OK && chunks) s = launch_build_layout(ivf, d_src);
+  if (s == MGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+    s = mgpu_fail(ctx, MGPU_ERR_CUDA, "ivf_create: layout build failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (own_src) cudaFree(d_src);
+  if (s != MGPU_OK) { mgpu_ivf_destroy(ivf); return s; }
+  *out = ivf;
+  return MGPU_OK;
+}
+
+void mgpu_ivf_destroy(mgpu_ivf *ivf) {
+  if (!ivf) return;
+  cudaSetDevice(ivf->ctx->device);
+  cudaStreamSynchronize(ivf->ctx->stream);
+  cudaFree(ivf->d_centroids); cudaFree(ivf->d_chunk_start); cudaFree(ivf->d_list_len); cudaFree(ivf->d_slot_pid);
+  cudaFree(ivf->d_codes); cudaFree(ivf->d_rows); cudaFree(ivf->d_doc_ids); cudaFree(ivf->d_invalid); cudaFree(ivf->d_scan_rows);
+  delete ivf;
+}
+
+uint64_t mgpu_ivf_num_vectors(mgpu_ivf *ivf) { return ivf ? ivf->n : 0; }
+uint32_t mgpu_ivf_num_clusters(mgpu_ivf *ivf) { return ivf ? ivf->nlist : 0; }
+
+__global__ void k_set_bits(uint32_t *bitmap, const uint32_t *ids, uint32_t n, uint64_t limit) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && ids[i] < limit) atomicOr(&bitmap[ids[i] >> 5], 1u << (ids[i] & 31));
+}
+
+int mgpu_ivf_invalidate(mgpu_ivf *ivf, const uint32_t *point_ids, uint32_t n) {
+  if (!ivf || (n && !point_ids)) return MGPU_ERR_INVALID_ARG;
+  mgpu_ctx *ctx = ivf->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (n == 0) return MGPU_OK;
+  MGPU_TRY(mgpu_ws_reserve(ctx, (size_t)n * 4));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ws, point_ids, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    LaunchScope ls(ctx, MGPU_K_OTHER);
+    k_set_bits<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ivf->d_invalid, (const uint32_t *)ctx->ws, n, ivf->n);
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ivf->n_invalid += n;
+  return MGPU_OK;
+}
+
+int mgpu_ivf_is_invalidated(mgpu_ivf *ivf, uint32_t point_id, int *out) {
+  if (!ivf || !out) return MGPU_ERR_INVALID_ARG;
+  mgpu_ctx *ctx = ivf->ctx;
+  if (point_id >= ivf->n) { *out = 0; return MGPU_OK; }
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  uint32_t w = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&w, ivf->d_invalid + (point_id >> 5), 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = (w >> (point_id & 31)) & 1;
+  return MGPU_OK;
+}
+
+uint64_t mgpu_ivf_last_scan_rows(mgpu_ivf *ivf) {
+  if (!ivf) return 0;
+  std::lock_guard<std::mutex> g(ivf->ctx->mu);
+  cudaSetDevice(ivf->ctx->device);
+  unsigned long long v = 0;
+  cudaMemcpyAsync(&v, ivf->d_scan_rows, 8, cudaMemcpyDeviceToHost, ivf->ctx->stream);
+  cudaStreamSynchronize(ivf->ctx->stream);
+  return v;
+}
+uint64_t mgpu_ivf_last_scan_bytes(mgpu_ivf *ivf) { return ivf ? mgpu_ivf_last_scan_rows(ivf) * ivf->bytes_per_row : 0; }
+
+// coarse scoring on device buffers: dQ (B x dim) -> d_ids (B x nprobe), d_dist (optional)
+static int ivf_coarse_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, uint32_t nprobe, float *dD, uint32_t *d_ids, float *d_dist) {
+  mgpu_ctx *ctx = ivf->ctx;
+  // always the L2 calculator with sqrt (index.rs:155), whatever the quantizer's metric
+  MGPU_TRY(launch_distance_matrix(ctx, dQ, B, ivf->d_centroids, ivf->nlist, ivf->dim, MGPU_L2, 1, dD, MGPU_K_COARSE));
+  return launch_select_smallest(ctx, dD, B, ivf->nlist, nprobe, d_ids, d_dist);
+}
+
+int mgpu_ivf_coarse(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t nprobe, uint32_t *out_ids, float *out_dist, int mem) {
+  if (!ivf || (B && (!Q || !out_ids))) return MGPU_ERR_INVALID_ARG;
+  mgpu_ctx *ctx = ivf->ctx;
+  if (nprobe == 0 || nprobe > ivf->nlist) return mgpu_fail(ctx, MGPU_ERR_OUT_OF_RANGE, "num_probes %u out of range 1..%u (the reference panics)", nprobe, ivf->nlist);
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (B == 0) return MGPU_OK;
+  size_t bQ = (size_t)B * ivf->dim * 4, bD = (size_t)B * ivf->nlist * 4, bI = (size_t)B * nprobe * 4;
+  size_t need = ws_need(ws_need(ws_need(ws_need(0, bQ), bD), bI), bI);
+  MGPU_TRY(mgpu_ws_reserve(ctx, need));
+  WsAlloc w(ctx->ws, ctx->ws_bytes);
+  float *sQ = w.get<float>((size_t)B * ivf->dim);
+  float *dD = w.get<float>((size_t)B * ivf->nlist);
+  uint32_t *sI = w.get<uint32_t>((size_t)B * nprobe);
+  float *sV = w.get<float>((size_t)B * nprobe);
+  const void *dQ;
+  MGPU_TRY(stage_in(ctx, Q, bQ, mem, sQ, &dQ));
+  uint32_t *dI = mem == MGPU_DEVICE ? out_ids : sI;
+  float *dV = mem == MGPU_DEVICE ? out_dist : (out_dist ? sV : nullptr);
+  MGPU_TRY(ivf_coarse_dev(ivf, (const float *)dQ, B, nprobe, dD, dI, dV));
+  MGPU_TRY(stage_out(ctx, out_ids, dI, bI, mem));
+  MGPU_TRY(stage_out(ctx, out_dist, dV, bI, mem));
+  if (mem == MGPU_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return MGPU_OK;
+}
+
+// scan + finalize on device buffers
+static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32_t *d_probes, uint32_t max_probes,
+                        const uint32_t *d_counts, uint32_t k, uint8_t *d_qcodes, uint64_t *d_ckey, uint32_t *d_cslot,
+                        uint32_t *d_out_pids, mgpu_u128 *d_out_docs, float *d_out_scores, uint32_t *d_out_counts) {
+  mgpu_ctx *ctx = ivf->ctx;
+  CUDA_TRY(ctx, cudaMemsetAsync(ivf->d_scan_rows, 0, 8, ctx->stream));
+  ScanArgs a;
+  memset(&a, 0, sizeof(a));
+  a.chunk_start = ivf->d_chunk_start; a.list_len = ivf->d_list_len; a.slot_pid = ivf->d_slot_pid;
+  a.invalid = ivf->n_invalid ? ivf->d_invalid : nullptr;
+  a.codes = ivf->d_codes; a.rows = ivf->d_rows; a.dim = ivf->dim; a.dim4 = ivf->dim4; a.ng = ivf->ng;
+  a.Q = dQ; a.B = B; a.probes = d_probes; a.max_probes = max_probes; a.probe_counts = d_counts;
+  a.cand_key = d_ckey; a.cand_slot = d_cslot; a.rows_scanned = ivf->d_scan_rows; a.metric = ivf->metric;
+  if (ivf->quant == MGPU_QUANT_PQ) {
+    mgpu_pq *pq = ivf->pq;
+    a.m = pq->m; a.K = pq->K; a.table = pq->d_table; a.rowmin = pq->d_rowmin; a.rowmax = pq->d_rowmax;
+    // the query is quantized with the same codebook (index.rs:193) -- once per query here, not once per list
+    MGPU_TRY(launch_pq_quantize(pq, dQ, B, d_qcodes));
+    a.qcodes = d_qcodes;
+  }
+  MGPU_TRY(launch_scan(ivf, a));
+  FinalizeArgs f;
+  memset(&f, 0, sizeof(f));
+  f.cand_key = d_ckey; f.cand_slot = d_cslot; f.B = B; f.k = k; f.slot_pid = ivf->d_slot_pid; f.metric = ivf->metric;
+  if (ivf->quant == MGPU_QUANT_PQ) {
+    f.cb = ivf->pq->d_cb; f.codes = ivf->d_codes; f.qcodes = d_qcodes; f.m = ivf->pq->m; f.K = ivf->pq->K;
+    f.dsub = ivf->pq->dsub; f.ng = ivf->ng; f.pq_fast = ivf->pq_fast;
+  }
+  f.doc_ids = ivf->d_doc_ids;
+  f.out_pids = d_out_pids; f.out_docs = d_out_docs; f.out_scores = d_out_scores; f.out_counts = d_out_counts;
+  return launch_finalize(ctx, f);
+}
+
+// shared implementation of scan / scan_remap / search
+static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint32_t *probe_ids, uint32_t max_probes,
+                           const uint32_t *probe_counts, uint32_t nprobe_coarse, uint32_t k, uint32_t *out_pids,
+                           mgpu_u128 *out_docs, float *out_scores, uint32_t *out_counts, int mem) {
+  mgpu_ctx *ctx = ivf->ctx;
+  const bool do_coarse = probe_ids == nullptr;
+  if (do_coarse) {
+    if (nprobe_coarse == 0 || nprobe_coarse > ivf->nlist)
+      return mgpu_fail(ctx, MGPU_ERR_OUT_OF_RANGE, "num_probes %u out of range 1..%u (the reference panics)", nprobe_coarse, ivf->nlist);
+    max_probes = nprobe_coarse;
+  }
+  if (k > MGPU_NCAND) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported yet", k, MGPU_NCAND);
+  if (B && (!Q || !out_scores || !out_counts || (!out_pids && !out_docs))) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "search: null buffer");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (B == 0) return MGPU_OK;
+  if (k == 0) {  // heap of capacity 0 keeps nothing (index.rs:265-274)
+    if (mem == MGPU_HOST) memset(out_counts, 0, (size_t)B * 4);
+    else CUDA_TRY(ctx, cudaMemsetAsync(out_counts, 0, (size_t)B * 4, ctx->stream));
+    return MGPU_OK;
+  }
+  if (max_probes == 0) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "search: max_probes == 0");
+  const uint32_t m = ivf->pq ? ivf->pq->m : 0;
+  size_t bQ = (size_t)B * ivf->dim * 4, bP = (size_t)B * max_probes * 4;
+  size_t need = 0;
+  need = ws_need(need, bQ);                                   // Q
+  need = ws_need(need, bP);                                   // probes
+  need = ws_need(need, (size_t)B * 4);                        // probe counts
+  need = ws_need(need, do_coarse ? (size_t)B * ivf->nlist * 4 : 0);  // distance matrix
+  need = ws_need(need, (size_t)B * m);                        // query codes
+  need = ws_need(need, (size_t)B * MGPU_NCAND * 8);           // cand keys
+  need = ws_need(need, (size_t)B * MGPU_NCAND * 4);           // cand slots
+  need = ws_need(need, (size_t)B * k * 16);                   // out docs
+  need = ws_need(need, (size_t)B * k * 4);                    // out pids
+  need = ws_need(need, (size_t)B * k * 4);                    // out scores
+  need = ws_need(need, (size_t)B * 4);                        // out counts
+  MGPU_TRY(mgpu_ws_reserve(ctx, need));
+  WsAlloc w(ctx->ws, ctx->ws_bytes);
+  float *sQ = w.get<float>((size_t)B * ivf->dim);
+  uint32_t *sP = w.get<uint32_t>((size_t)B * max_probes);
+  uint32_t *sPC = w.get<uint32_t>(B);
+  float *dD = w.get<float>(do_coarse ? (size_t)B * ivf->nlist : 0);
+  uint8_t *dQC = w.get<uint8_t>((size_t)B * m);
+  uint64_t *dCK = w.get<uint64_t>((size_t)B * MGPU_NCAND);
+  uint32_t *dCS = w.get<uint32_t>((size_t)B * MGPU_NCAND);
+  mgpu_u128 *sDocs = w.get<mgpu_u128>((size_t)B * k);
+  uint32_t *sPids = w.get<uint32_t>((size_t)B * k);
+  float *sScores = w.get<float>((size_t)B * k);
+  uint32_t *sCounts = w.get<uint32_t>(B);
+
+  const void *dQ;
+  MGPU_TRY(stage_in(ctx, Q, bQ, mem, sQ, &dQ));
+  const uint32_t *dP, *dPC = nullptr;
+  if (do_coarse) {
+    MGPU_TRY(ivf_coarse_dev(ivf, (const float *)dQ, B, nprobe_coarse, dD, sP, nullptr));
+    dP = sP;
+  } else {
+    const void *t;
+    MGPU_TRY(stage_in(ctx, probe_ids, bP, mem, sP, &t));
+    dP = (const uint32_t *)t;
+    if (probe_counts) { MGPU_TRY(stage_in(ctx, probe_counts, (size_t)B * 4, mem, sPC, &t)); dPC = (const uint32_t *)t; }
+  }
+  uint32_t *oP = out_pids ? (mem == MGPU_DEVICE ? out_pids : sPids) : nullptr;
+  mgpu_u128 *oD = out_docs ? (mem == MGPU_DEVICE ? out_docs : sDocs) : nullptr;
+  float *oS = mem == MGPU_DEVICE ? out_scores : sScores;
+  uint32_t *oC = mem == MGPU_DEVICE ? out_counts : sCounts;
+  MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, dP, max_probes, dPC, k, dQC, dCK, dCS, oP, oD, oS, oC));
+  if (mem == MGPU_HOST) {
+    MGPU_TRY(stage_out(ctx, out_pids, oP, (size_t)B * k * 4, mem));
+    MGPU_TRY(stage_out(ctx, out_docs, oD, (size_t)B * k * 16, mem));
+    MGPU_TRY(stage_out(ctx, out_scores, oS, (size_t)B * k * 4, mem));
+    MGPU_TRY(stage_out(ctx, out_counts, oC, (size_t)B * 4, mem));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return MGPU_OK;
+}
+
+static int check_probes_host(mgpu_ivf *ivf, const uint32_t *probe_ids, uint32_t B, uint32_t max_probes,
+                             const uint32_t *probe_counts, int mem) {
+  if (mem != MGPU_HOST || !probe_ids) return MGPU_OK;
+  for (uint32_t b = 0; b < B; b++) {
+    uint32_t np = probe_counts ? std::min(probe_counts[b], max_probes) : max_probes;
+    for (uint32_t i = 0; i < np; i++)
+      if (probe_ids[(size_t)b * max_probes + i] >= ivf->nlist)
+        return mgpu_fail(ivf->ctx, MGPU_ERR_OUT_OF_RANGE, "centroid id %u out of range", probe_ids[(size_t)b * max_probes + i]);
+  }
+  return MGPU_OK;
+}
+
+int mgpu_ivf_scan(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint32_t *probe_ids, uint32_t max_probes,
+                  const uint32_t *probe_counts, uint32_t k, uint32_t *out_point_ids, float *out_scores,
+                  uint32_t *out_counts, int mem) {
+  if (!ivf) return MGPU_ERR_INVALID_ARG;
+  if (B && !probe_ids) return mgpu_fail(ivf->ctx, MGPU_ERR_INVALID_ARG, "ivf_scan: null probe list");
+  MGPU_TRY(check_probes_host(ivf, probe_ids, B, max_probes, probe_counts, mem));
+  return ivf_search_impl(ivf, Q, B, probe_ids, max_probes, probe_counts, 0, k, out_point_ids, nullptr, out_scores, out_counts, mem);
+}
+
+int mgpu_ivf_scan_remap(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint32_t *probe_ids, uint32_t max_probes,
+                        const uint32_t *probe_counts, uint32_t k, mgpu_u128 *out_doc_ids, float *out_scores,
+                        uint32_t *out_counts, int mem) {
+  if (!ivf) return MGPU_ERR_INVALID_ARG;
+  if (B && !probe_ids) return mgpu_fail(ivf->ctx, MGPU_ERR_INVALID_ARG, "ivf_scan_remap: null probe list");
+  MGPU_TRY(check_probes_host(ivf, probe_ids, B, max_probes, probe_counts, mem));
+  return ivf_search_impl(ivf, Q, B, probe_ids, max_probes, probe_counts, 0, k, nullptr, out_doc_ids, out_scores, out_counts, mem);
+}
+
+int mgpu_ivf_search(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, mgpu_u128 *out_doc_ids,
+                    float *out_scores, uint32_t *out_counts, int mem) {
+  if (!ivf) return MGPU_ERR_INVALID_ARG;
+  return ivf_search_impl(ivf, Q, B, nullptr, 0, nullptr, nprobe, k, nullptr, out_doc_ids, out_scores, out_counts, mem);
+}
+
+// ---- build-time assignment -----------------------------------------------------------------------------------------------
+int mgpu_ivf_assign(mgpu_ctx *ctx, const float *X, uint64_t n, const float *centroids, uint32_t nlist, uint32_t dim,
+                    uint32_t max_clusters, float threshold, uint32_t *out_cids, uint32_t *out_counts, int mem) {
+  if (!ctx || (n && (!X || !centroids || !out_cids || !out_counts))) return MGPU_ERR_INVALID_ARG;
+  if (max_clusters == 0 || max_clusters > nlist) return mgpu_fail(ctx, MGPU_ERR_OUT_OF_RANGE, "max_clusters_per_vector %u out of range 1..%u (the reference panics)", max_clusters, nlist);
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (n == 0) return MGPU_OK;
+  const uint32_t r = max_clusters;
+  // slabs of rows so the n x nlist matrix stays bounded
+  uint64_t slab = std::max<uint64_t>(32, std::min<uint64_t>(n, (512ull << 20) / ((uint64_t)nlist * 4)));
+  slab = std::min<uint64_t>(slab, 65535ull * 32);
+  size_t need = 0;
+  need = ws_need(need, (size_t)nlist * dim * 4);
+  need = ws_need(need, slab * dim * 4);
+  need = ws_need(need, slab * nlist * 4);
+  need = ws_need(need, slab * r * 4);
+  need = ws_need(need, slab * r * 4);
+  need = ws_need(need, slab * r * 4);
+  need = ws_need(need, slab * 4);
+  MGPU_TRY(mgpu_ws_reserve(ctx, need));
+  WsAlloc w(ctx->ws, ctx->ws_bytes);
+  float *sC = w.get<float>((size_t)nlist * dim);
+  float *sX = w.get<float>(slab * dim);
+  float *dD = w.get<float>(slab * nlist);
+  uint32_t *dSelI = w.get<uint32_t>(slab * r);
+  float *dSelV = w.get<float>(slab * r);
+  uint32_t *sCid = w.get<uint32_t>(slab * r);
+  uint32_t *sCnt = w.get<uint32_t>(slab);
+  const void *dC;
+  MGPU_TRY(stage_in(ctx, centroids, (size_t)nlist * dim * 4, mem, sC, &dC));
+  for (uint64_t i = 0; i < n; i += slab) {
+    uint64_t cnt = std::min(slab, n - i);
+    const void *dX;
+    MGPU_TRY(stage_in(ctx, X + i * dim, cnt * dim * 4, mem, sX, &dX));
+    MGPU_TRY(launch_distance_matrix(ctx, (const float *)dX, cnt, (const float *)dC, nlist, dim, MGPU_L2, 0, dD, MGPU_K_COARSE));
+    MGPU_TRY(launch_select_smallest(ctx, dD, (uint32_t)cnt, nlist, r, dSelI, dSelV));
+    uint32_t *oI = mem == MGPU_DEVICE ? out_cids + i * r : sCid;
+    uint32_t *oN = mem == MGPU_DEVICE ? out_counts + i : sCnt;
+    MGPU_TRY(launch_assign_filter(ctx, dSelI, dSelV, cnt, r, threshold, oI, oN));
+    if (mem == MGPU_HOST) {
+      CUDA_TRY(ctx, cudaMemcpyAsync(out_cids + i * r, oI, cnt * r * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(out_counts + i, oN, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  return MGPU_OK;
+}
+
+// ---- merge ----------------------------------------------------------------------------------------------------------------
+int mgpu_merge_topk(mgpu_ctx *ctx, const mgpu_u128 *doc_ids, const float *scores, const uint32_t *counts, uint32_t S,
+                    uint32_t B, uint32_t k, mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, int mem) {
+  if (!ctx) return MGPU_ERR_INVALID_ARG;
+  if (B && S && k && (!doc_ids || !scores || !counts || !out_doc_ids || !out_scores || !out_counts)) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "merge_topk: null buffer");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (B == 0) return MGPU_OK;
+  if (k == 0 || S == 0) {
+    if (mem == MGPU_HOST) memset(out_counts, 0, (size_t)B * 4);
+    else CUDA_TRY(ctx, cudaMemsetAsync(out_counts, 0, (size_t)B * 4, ctx->stream));
+    return MGPU_OK;
+  }
+  if (mem == MGPU_DEVICE) return launch_merge_topk(ctx, doc_ids, scores, counts, S, B, k, out_doc_ids, out_scores, out_counts);
+  size_t nin = (size_t)S * B * k, nout = (size_t)B * k;
+  size_t need = 0;
+  need = ws_need(need, nin * 16); need = ws_need(need, nin * 4); need = ws_need(need, (size_t)S * B * 4);
+  need = ws_need(need, nout * 16); need = ws_need(need, nout * 4); need = ws_need(need, (size_t)B * 4);
+  MGPU_TRY(mgpu_ws_reserve(ctx, need));
+  WsAlloc w(ctx->ws, ctx->ws_bytes);
+  mgpu_u128 *dD = w.get<mgpu_u128>(nin); float *dS = w.get<float>(nin); uint32_t *dC = w.get<uint32_t>((size_t)S * B);
+  mgpu_u128 *oD = w.get<mgpu_u128>(nout); float *oS = w.get<float>(nout); uint32_t *oC = w.get<uint32_t>(B);
+  CUDA_TRY(ctx, cudaMemcpyAsync(dD, doc_ids, nin * 16, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(dS, scores, nin * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(dC, counts, (size_t)S * B * 4, cudaMemcpyHostToDevice, ctx->stream));
+  MGPU_TRY(launch_merge_topk(ctx, dD, dS, dC, S, B, k, oD, oS, oC));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_doc_ids, oD, nout * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_scores, oS, nout * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_counts, oC, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return MGPU_OK;
+}
+
+// ---- NCCL (dlopen'ed; the library has no link-time dependency on it) ------------------------------------------------------
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef int (*fn_ncclGetUniqueId)(nccl_uid_t *);
+typedef int (*fn_ncclCommInitRank)(void **, int, nccl_uid_t, int);
+typedef int (*fn_ncclCommDestroy)(void *);
+typedef int (*fn_ncclAllGather)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef const char *(*fn_ncclGetErrorString)(int);
+
+static void *g_nccl = nullptr;
+static void *nccl_sym(const char *name) {
+  if (!g_nccl) {
+    // a process that already imported torch has its bundled libnccl mapped: prefer that copy
+    const char *cands[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    for (int i = 0; cands[i] && !g_nccl; i++) g_nccl = dlopen(cands[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!g_nccl) {
+      const char *env = getenv("MGPU_NCCL_LIB");
+      if (env) g_nccl = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    }
+    if (!g_nccl) return nullptr;
+  }
+  return dlsym(g_nccl, name);
+}
+
+int mgpu_comm_unique_id(uint8_t out_id[128]) {
+  auto f = (fn_ncclGetUniqueId)nccl_sym("ncclGetUniqueId");
+  if (!f) return MGPU_ERR_NCCL;
+  nccl_uid_t id;
+  if (f(&id) != 0) return MGPU_ERR_NCCL;
+  memcpy(out_id, id.internal, 128);
+  return MGPU_OK;
+}
+
+int mgpu_comm_init(mgpu_ctx *ctx, int nranks, int rank, const uint8_t id[128]) {
+  if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return MGPU_ERR_INVALID_ARG;
+  auto f = (fn_ncclCommInitRank)nccl_sym("ncclCommInitRank");
+  if (!f) return mgpu_fail(ctx, MGPU_ERR_NCCL, "libnccl not found (set MGPU_NCCL_LIB)");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  nccl_uid_t uid;
+  memcpy(uid.internal, id, 128);
+  int r = f(&ctx->nccl_comm, nranks, uid, rank);
+  if (r != 0) {
+    auto es = (fn_ncclGetErrorString)nccl_sym("ncclGetErrorString");
+    return mgpu_fail(ctx, MGPU_ERR_NCCL, "ncclCommInitRank failed: %s", es ? es(r) : "?");
+  }
+  ctx->nranks = nranks; ctx->rank = rank;
+  return MGPU_OK;
+}
+
+int mgpu_comm_destroy(mgpu_ctx *ctx) {
+  if (!ctx) return MGPU_ERR_INVALID_ARG;
+  if (ctx->nccl_comm) {
+    auto f = (fn_ncclCommDestroy)nccl_sym("ncclCommDestroy");
+    if (f) f(ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+  }
+  return MGPU_OK;
+}
+
+int mgpu_shard_allgather_merge(mgpu_ctx *ctx, const mgpu_u128 *local_doc_ids, const float *local_scores,
+                               const uint32_t *local_counts, uint32_t B, uint32_t k, mgpu_u128 *out_doc_ids,
+                               float *out_scores, uint32_t *out_counts) {
+  if (!ctx) return MGPU_ERR_INVALID_ARG;
+  if (!ctx->nccl_comm) return mgpu_fail(ctx, MGPU_ERR_NCCL, "shard_allgather_merge: communicator not initialised");
+  auto ag = (fn_ncclAllGather)nccl_sym("ncclAllGather");
+  if (!ag) return mgpu_fail(ctx, MGPU_ERR_NCCL, "ncclAllGather not found");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (B == 0 || k == 0) return MGPU_OK;
+  const uint32_t S = (uint32_t)ctx->nranks;
+  size_t nloc = (size_t)B * k;
+  size_t need = 0;
+  need = ws_need(need, S * nloc * 16); need = ws_need(need, S * nloc * 4); need = ws_need(need, (size_t)S * B * 4);
+  MGPU_TRY(mgpu_ws_reserve(ctx, need));
+  WsAlloc w(ctx->ws, ctx->ws_bytes);
+  mgpu_u128 *gD = w.get<mgpu_u128>(S * nloc); float *gS = w.get<float>(S * nloc); uint32_t *gC = w.get<uint32_t>((size_t)S * B);
+  // ncclChar = 0; three small all-gathers over NVLink (B*k*20 + B*4 bytes per rank)
+  int r = ag(local_doc_ids, gD, nloc * 16, 0, ctx->nccl_comm, ctx->stream);
+  if (r == 0) r = ag(local_scores, gS, nloc * 4, 0, ctx->nccl_comm, ctx->stream);
+  if (r == 0) r = ag(local_counts, gC, (size_t)B * 4, 0, ctx->nccl_comm, ctx->stream);
+  if (r != 0) return mgpu_fail(ctx, MGPU_ERR_NCCL, "ncclAllGather failed (%d)", r);
+  ctx->launches += 3;
+  return launch_merge_topk(ctx, gD, gS, gC, S, B, k, out_doc_ids, out_scores, out_counts);
+}
+
+}  // extern "C"
+
+// ---- HNSW / SPANN ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int mgpu_hnsw_create(mgpu_ctx *ctx, uint32_t dim, uint32_t num_layers, const uint32_t *edges, uint64_t n_edges,
+                     const uint32_t *points, uint64_t n_points, const uint64_t *edge_offsets, uint64_t n_edge_offsets,
+                     const uint64_t *level_offsets, int quant, int metric, mgpu_pq *pq, const void *rows, int rows_mem,
+                     uint64_t n, const mgpu_u128 *doc_ids, mgpu_hnsw **out) {
+  if (!ctx || !out) return MGPU_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (dim == 0 || num_layers == 0 || !edge_offsets || !level_offsets || n_edge_offsets == 0 || (n && !rows))
+    return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "hnsw_create: null/zero argument");
+  if (quant == MGPU_QUANT_PQ && (!pq || pq->dim != dim)) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "hnsw_create: PQ quantizer missing or of the wrong dimension");
+  if (n_edges && !edges) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "hnsw_create: null edges");
+  if (level_offsets[num_layers] + 1 > n_edge_offsets || level_offsets[num_layers - 1] > n_points)
+    return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "hnsw_create: level_offsets inconsistent with points/edge_offsets");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  mgpu_hnsw *h = new mgpu_hnsw();
+  h->ctx = ctx; h->dim = dim; h->num_layers = num_layers; h->n = n; h->n_edges = n_edges; h->n_points = n_points;
+  h->n_edge_offsets = n_edge_offsets; h->quant = quant; h->metric = quant == MGPU_QUANT_PQ ? pq->metric : metric;
+  h->pq = quant == MGPU_QUANT_PQ ? pq : nullptr;
+  h->qdim = quant == MGPU_QUANT_PQ ? pq->m : dim;
+  h->h_level_offsets.assign(level_offsets, level_offsets + num_layers + 1);
+  // entry point (graph_storage.rs:527-554)
+  h->entry_point = 0;
+  if (num_layers == 1) {
+    for (uint64_t i = 0; i + 1 < n_edge_offsets; i++) if (edge_offsets[i + 1] > edge_offsets[i]) { h->entry_point = (uint32_t)i; break; }
+  } else if (n_points > level_offsets[0]) h->entry_point = points[level_offsets[0]];
+  // per-layer sorted (point id -> first position) tables replace the reference's linear scan (graph_storage.rs:423-449)
+  uint64_t n_upper = level_offsets[num_layers - 1];
+  std::vector<uint32_t> spid(std::max<uint64_t>(n_upper, 1)), spos(std::max<uint64_t>(n_upper, 1));
+  for (uint32_t li = 0; li + 1 < num_layers; li++) {
+    uint64_t s = level_offsets[li], e = level_offsets[li + 1];
+    std::vector<std::pair<uint32_t, uint32_t>> v;
+    v.reserve(e - s);
+    for (uint64_t i = s; i < e; i++) v.push_back({points[i], (uint32_t)i});
+    std::stable_sort(v.begin(), v.end(), [](const std::pair<uint32_t, uint32_t> &x, const std::pair<uint32_t, uint32_t> &y) { return x.first < y.first; });
+    for (uint64_t i = s; i < e; i++) { spid[i] = v[i - s].first; spos[i] = v[i - s].second; }
+  }
+  size_t row_bytes = quant == MGPU_QUANT_PQ ? pq->m : (size_t)dim * 4;
+  int s = dev_alloc_copy(ctx, &h->d_edges, edges, n_edges);
+  if (s == MGPU_OK) s = dev_alloc_copy(ctx, &h->d_points, points, n_points);
+  if (s == MGPU_OK) s = dev_alloc_copy(ctx, &h->d_edge_offsets, edge_offsets, n_edge_offsets);
+  if (s == MGPU_OK) s = dev_alloc_copy(ctx, &h->d_level_offsets, level_offsets, num_layers + 1);
+  if (s == MGPU_OK) s = dev_alloc_copy(ctx, &h->d_upper_sorted_pid, spid.data(), spid.size());
+  if (s == MGPU_OK) s = dev_alloc_copy(ctx, &h->d_upper_sorted_pos, spos.data(), spos.size());
+  if (s == MGPU_OK) s = dev_alloc_copy(ctx, (uint8_t **)&h->d_rows, (const uint8_t *)rows, n * row_bytes, rows_mem == MGPU_DEVICE);
+  if (s == MGPU_OK && doc_ids) s = dev_alloc_copy(ctx, &h->d_doc_ids, doc_ids, n);
+  if (s == MGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) s = mgpu_fail(ctx, MGPU_ERR_CUDA, "hnsw_create: upload failed");
+  if (s != MGPU_OK) { mgpu_hnsw_destroy(h); return s; }
+  *out = h;
+  return MGPU_OK;
+}
+
+void mgpu_hnsw_destroy(mgpu_hnsw *h) {
+  if (!h) return;
+  cudaSetDevice(h->ctx->device);
+  cudaStreamSynchronize(h->ctx->stream);
+  cudaFree(h->d_edges); cudaFree(h->d_points); cudaFree(h->d_edge_offsets); cudaFree(h->d_level_offsets);
+  cudaFree(h->d_upper_sorted_pid); cudaFree(h->d_upper_sorted_pos); cudaFree(h->d_rows); cudaFree(h->d_doc_ids);
+  delete h;
+}
+
+int mgpu_hnsw_search(mgpu_hnsw *h, const float *Q, uint32_t B, uint32_t k, uint32_t ef, mgpu_u128 *out_doc_ids,
+                     float *out_scores, uint32_t *out_counts, uint64_t *out_stats, int mem) {
+  if (!h) return MGPU_ERR_INVALID_ARG;
+  mgpu_ctx *ctx = h->ctx;
+  if (B && (!Q || !out_doc_ids || !out_scores || !out_counts)) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "hnsw_search: null buffer");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (B == 0) return MGPU_OK;
+  if (h->n == 0) {
+    if (mem == MGPU_HOST) memset(out_counts, 0, (size_t)B * 4); else CUDA_TRY(ctx, cudaMemsetAsync(out_counts, 0, (size_t)B * 4, ctx->stream));
+    return MGPU_OK;
+  }
+  HnswSearchArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.k = k; a.ef = ef;
+  if (mem == MGPU_DEVICE) {
+    a.Q = Q; a.out_docs = out_doc_ids; a.out_scores = out_scores; a.out_counts = out_counts; a.out_stats = out_stats;
+    return launch_hnsw_search(h, a);
+  }
+  size_t kk = std::max<uint32_t>(k, 1);
+  size_t need = 0;
+  need = ws_need(need, (size_t)B * h->dim * 4); need = ws_need(need, (size_t)B * kk * 16); need = ws_need(need, (size_t)B * kk * 4);
+  need = ws_need(need, (size_t)B * 4); need = ws_need(need, (size_t)B * 16);
+  MGPU_TRY(mgpu_ws_reserve(ctx, need));
+  WsAlloc w(ctx->ws, ctx->ws_bytes);
+  float *dQ = w.get<float>((size_t)B * h->dim);
+  mgpu_u128 *dD = w.get<mgpu_u128>((size_t)B * kk); float *dS = w.get<float>((size_t)B * kk);
+  uint32_t *dC = w.get<uint32_t>(B); uint64_t *dSt = w.get<uint64_t>((size_t)B * 2);
+  CUDA_TRY(ctx, cudaMemcpyAsync(dQ, Q, (size_t)B * h->dim * 4, cudaMemcpyHostToDevice, ctx->stream));
+  a.Q = dQ; a.out_docs = dD; a.out_scores = dS; a.out_counts = dC; a.out_stats = out_stats ? dSt : nullptr;
+  MGPU_TRY(launch_hnsw_search(h, a));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_doc_ids, dD, (size_t)B * k * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_scores, dS, (size_t)B * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_counts, dC, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_stats) CUDA_TRY(ctx, cudaMemcpyAsync(out_stats, dSt, (size_t)B * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return MGPU_OK;
+}
+
+int mgpu_spann_create(mgpu_ctx *ctx, mgpu_hnsw *centroids, mgpu_ivf *posting_lists, mgpu_spann **out) {
+  if (!ctx || !out) return MGPU_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (!centroids || !posting_lists) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "spann_create: null index");
+  if (centroids->ctx != ctx || posting_lists->ctx != ctx) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "spann_create: indices belong to another context");
+  if (centroids->dim != posting_lists->dim) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "spann_create: dimension mismatch");
+  mgpu_spann *s = new mgpu_spann();
+  s->ctx = ctx; s->centroids = centroids; s->lists = posting_lists;
+  *out = s;
+  return MGPU_OK;
+}
+void mgpu_spann_destroy(mgpu_spann *s) { delete s; }
+
+// centroid-ratio pruning (spann/index.rs:233-246): keep centroids with score - nearest <= nearest * ratio
+__global__ void k_spann_prune(const mgpu_u128 *__restrict__ cdocs, const float *__restrict__ cscores,
+                              const uint32_t *__restrict__ ccounts, uint32_t B, uint32_t ne, float ratio, uint32_t nlist,
+                              uint32_t *__restrict__ probes, uint32_t *__restrict__ pcounts) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  uint32_t n = ccounts[b];
+  float nearest = 0.0f;
+  for (uint32_t i = 0; i < n; i++) { float s = cscores[(size_t)b * ne + i]; if (i == 0 || s < nearest) nearest = s; }
+  uint32_t kept = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    float s = cscores[(size_t)b * ne + i];
+    uint32_t cid = (uint32_t)cdocs[(size_t)b * ne + i].lo;
+    if (__fsub_rn(s, nearest) <= __fmul_rn(nearest, ratio) && cid < nlist) probes[(size_t)b * ne + kept++] = cid;
+  }
+  pcounts[b] = kept;
+}
+
+__global__ void k_spann_mark_none(const uint32_t *__restrict__ ccounts, uint32_t B, uint32_t *__restrict__ out_counts) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B && ccounts[b] == 0) out_counts[b] = 0xFFFFFFFFu;
+}
+
+int mgpu_spann_search(mgpu_spann *sp, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef,
+                      uint32_t num_explored_centroids, float ratio, mgpu_u128 *out_doc_ids, float *out_scores,
+                      uint32_t *out_counts, int mem) {
+  if (!sp) return MGPU_ERR_INVALID_ARG;
+  mgpu_ctx *ctx = sp->ctx;
+  mgpu_ivf *ivf = sp->lists;
+  mgpu_hnsw *hn = sp->centroids;
+  if (B && (!Q || !out_doc_ids || !out_scores || !out_counts)) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "spann_search: null buffer");
+  if (top_k > MGPU_NCAND) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported yet", top_k, MGPU_NCAND);
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (B == 0) return MGPU_OK;
+  const uint32_t ne = num_explored_centroids;
+  if (ne == 0 || hn->n == 0) {  // empty centroid result => None (spann/index.rs:229-231)
+    if (mem == MGPU_HOST) memset(out_counts, 0xFF, (size_t)B * 4); else CUDA_TRY(ctx, cudaMemsetAsync(out_counts, 0xFF, (size_t)B * 4, ctx->stream));
+    return MGPU_OK;
+  }
+  const uint32_t k = std::max<uint32_t>(top_k, 1);
+  const uint32_t m = ivf->pq ? ivf->pq->m : 0;
+  size_t need = 0;
+  need = ws_need(need, (size_t)B * ivf->dim * 4);
+  need = ws_need(need, (size_t)B * ne * 16); need = ws_need(need, (size_t)B * ne * 4); need = ws_need(need, (size_t)B * 4);
+  need = ws_need(need, (size_t)B * ne * 4); need = ws_need(need, (size_t)B * 4);
+  need = ws_need(need, (size_t)B * m); need = ws_need(need, (size_t)B * MGPU_NCAND * 8); need = ws_need(need, (size_t)B * MGPU_NCAND * 4);
+  need = ws_need(need, (size_t)B * k * 16); need = ws_need(need, (size_t)B * k * 4); need = ws_need(need, (size_t)B * 4);
+  MGPU_TRY(mgpu_ws_reserve(ctx, need));
+  WsAlloc w(ctx->ws, ctx->ws_bytes);
+  float *sQ = w.get<float>((size_t)B * ivf->dim);
+  mgpu_u128 *cD = w.get<mgpu_u128>((size_t)B * ne); float *cS = w.get<float>((size_t)B * ne); uint32_t *cC = w.get<uint32_t>(B);
+  uint32_t *pr = w.get<uint32_t>((size_t)B * ne); uint32_t *pc = w.get<uint32_t>(B);
+  uint8_t *dQC = w.get<uint8_t>((size_t)B * m); uint64_t *dCK = w.get<uint64_t>((size_t)B * MGPU_NCAND); uint32_t *dCS = w.get<uint32_t>((size_t)B * MGPU_NCAND);
+  mgpu_u128 *sD = w.get<mgpu_u128>((size_t)B * k); float *sS = w.get<float>((size_t)B * k); uint32_t *sC = w.get<uint32_t>(B);
+  const void *dQ;
+  MGPU_TRY(stage_in(ctx, Q, (size_t)B * ivf->dim * 4, mem, sQ, &dQ));
+  HnswSearchArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Q = (const float *)dQ; a.B = B; a.k = ne; a.ef = ef; a.out_docs = cD; a.out_scores = cS; a.out_counts = cC;
+  MGPU_TRY(launch_hnsw_search(hn, a));
+  {
+    LaunchScope ls(ctx, MGPU_K_OTHER);
+    k_spann_prune<<<(B + 127) / 128, 128, 0, ctx->stream>>>(cD, cS, cC, B, ne, ratio, ivf->nlist, pr, pc);
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  mgpu_u128 *oD = mem == MGPU_DEVICE ? out_doc_ids : sD;
+  float *oS = mem == MGPU_DEVICE ? out_scores : sS;
+  uint32_t *oC = mem == MGPU_DEVICE ? out_counts : sC;
+  if (top_k == 0) CUDA_TRY(ctx, cudaMemsetAsync(oC, 0, (size_t)B * 4, ctx->stream));
+  else MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, pr, ne, pc, top_k, dQC, dCK, dCS, nullptr, oD, oS, oC));
+  {
+    LaunchScope ls(ctx, MGPU_K_OTHER);
+    k_spann_mark_none<<<(B + 127) / 128, 128, 0, ctx->stream>>>(cC, B, oC);
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  if (mem == MGPU_HOST) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_doc_ids, oD, (size_t)B * top_k * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_scores, oS, (size_t)B * top_k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_counts, oC, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return MGPU_OK;
+}
+
+}  // extern "C"

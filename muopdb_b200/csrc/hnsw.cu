@@ -1,0 +1,316 @@
+// hnsw.cu -- batched HNSW beam search, strict reference semantics.
+//   BlockBasedHnsw::ann_search   rs/index/src/hnsw/block_based/index.rs:159-210
+//   BlockBasedHnsw::search_layer rs/index/src/hnsw/block_based/index.rs:212-287
+//   get_edges_for_point / entry  rs/index/src/hnsw/block_based/graph_storage.rs:459-554
+//
+// One CTA (4 warps) per query.  The beam state lives in shared memory as two SORTED arrays of 64-bit composites:
+//   W  working list, ascending (distance key, point id)       -- max-heap `working_list` of the reference
+//   C  candidates,   ascending (distance key, ~point id)      -- min-heap `candidates` (pop = nearest, ties: larger id)
+// Any priority structure that realises the same total order reproduces the reference's pops/evictions exactly.
+// Candidates farther than the current furthest of a full W can never be expanded (they only trigger the `break`), so C is
+// truncated to distance <= furthest -- it stays bounded by ef + ties.
+// Per expansion: the neighbour list is filtered against the per-query visited bitmap (atomicOr, edge order preserved),
+// the unvisited rows are gathered from HBM and scored bit-exactly in the reference's 16-lane order (two rows per warp:
+// lane h of a half-warp owns lane-accumulator h, 64-byte coalesced row reads), then warp 0 applies the admissions
+// sequentially in edge order, exactly like index.rs:255-281.
+#include "internal.cuh"
+#include "pq_device.cuh"
+
+#define HN_THREADS 128
+#define HN_WARPS 4
+
+struct HnswDev {
+  const uint32_t *edges, *points, *upper_pid, *upper_pos;
+  const uint64_t *edge_offsets, *level_offsets;
+  const void *rows;
+  const mgpu_u128 *doc_ids;
+  const float *cb;
+  uint32_t dim, qdim, num_layers, entry_point, m, K, dsub;
+  uint64_t n, n_edge_offsets;
+};
+
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// warp-collective insert of `key` into the ascending array A[lo, n) (shared memory); returns the new n
+__device__ __forceinline__ int warp_sorted_insert(uint64_t *A, int lo, int n, uint64_t key) {
+  const int lane = lane_id();
+  uint32_t cnt = 0;
+  for (int i = lo + lane; i < n; i += 32) cnt += (A[i] <= key) ? 1u : 0u;
+  const int pos = lo + (int)warp_sum_u32(cnt);
+  for (int base = n - 1; base >= pos; base -= 32) {
+    int i = base - lane;
+    uint64_t v = 0;
+    if (i >= pos) v = A[i];
+    __syncwarp();
+    if (i >= pos) A[i + 1] = v;
+    __syncwarp();
+  }
+  if (lane == 0) A[pos] = key;
+  __syncwarp();
+  return n + 1;
+}
+
+template <int QUANT, int METRIC>
+__global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswDev g, HnswSearchArgs a, uint32_t *__restrict__ visited_all,
+                                                             uint32_t vis_words, const uint8_t *__restrict__ qcodes_all,
+                                                             uint32_t capC, uint32_t *__restrict__ err_flags) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t ef = a.ef;
+  uint64_t *W = (uint64_t *)smem;                 // ef + 1
+  uint64_t *C = W + (ef + 2);                     // capC + 1
+  float *sq = (float *)(C + capC + 2);            // dim floats (flat) / unused
+  uint32_t *nb = (uint32_t *)(sq + ((g.dim + 3) & ~3u));  // 32 neighbour ids
+  uint32_t *nbk = nb + 32;                        // 32 distance keys
+  int *st = (int *)(nbk + 32);                    // state: [0]=nW [1]=headC [2]=nC [3]=cur point [4]=stop [5]=nu
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t q = blockIdx.x;
+  uint32_t *visited = visited_all + (size_t)q * vis_words;
+  const uint8_t *qc = QUANT == MGPU_QUANT_PQ ? qcodes_all + (size_t)q * g.m : nullptr;
+  if (QUANT == MGPU_QUANT_NONE)
+    for (uint32_t d = tid; d < g.dim; d += HN_THREADS) sq[d] = a.Q[(size_t)q * g.dim + d];
+  __syncthreads();
+
+  unsigned long long n_dist = 0, n_expand = 0;  // tracked by thread 0
+
+  // distance of the query to point `pid`; called by a full half-warp for flat rows (returns on all 16 lanes) or by a
+  // single thread for PQ rows
+  auto flat_distance_halfwarp = [&](uint32_t pid) -> float {
+    const float *row = (const float *)g.rows + (size_t)pid * g.dim;
+    const int h = lane & 15;
+    const int n = (int)g.dim;
+    float ret = 0.0f;
+    int p = 0;
+    const bool go16 = METRIC == MGPU_L2 ? (n / 16 > 0) : (n > 16);
+    if (go16) {
+      const int chunks = n / 16;
+      float acc = 0.0f;
+#pragma unroll 8
+      for (int c = 0; c < chunks; c++) {
+        float x = sq[c * 16 + h], y = __ldg(row + c * 16 + h);
+        if (METRIC == MGPU_L2) { float d = __fsub_rn(x, y); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
+        else acc = __fadd_rn(acc, __fmul_rn(x, y));
+      }
+      float s = -0.0f;
+      const int basel = lane & 16;
+#pragma unroll
+      for (int l = 0; l < 16; l++) s = __fadd_rn(s, __shfl_sync(0xffffffffu, acc, basel + l));
+      ret = __fadd_rn(ret, s);
+      p = chunks * 16;
+    }
+    if (p < n) ret = ref_tail<METRIC>(PtrAcc{sq}, PtrAcc{row}, p, n, ret);  // every lane redundantly; tiny
+    if (METRIC == MGPU_L2) return sqrtf(ret);  // NoQuantizer::distance -> D::calculate (noq/mod.rs:44-51)
+    return -ret;
+  };
+  auto pq_distance_thread = [&](uint32_t pid) -> float {
+    return pq_distance_streaming<METRIC>(g.cb, g.m, g.K, g.dsub, RowMajorCode{qc},
+                                         RowMajorCode{(const uint8_t *)g.rows + (size_t)pid * g.m});
+  };
+
+  uint32_t ep = g.entry_point;
+  for (int layer = (int)g.num_layers - 1; layer >= 0; layer--) {
+    // ---- search_layer(ep, ef, layer) -------------------------------------------------------------------------------
+    const uint64_t lvl_s = g.level_offsets[g.num_layers - 1 - layer];
+    const uint64_t lvl_e = g.level_offsets[g.num_layers - layer];
+    // entry: set_visited(ep); distance; push to both heaps (index.rs:219-233)
+    float ed = 0.0f;
+    if (QUANT == MGPU_QUANT_NONE) { if (warp == 0) ed = flat_distance_halfwarp(ep); }
+    else if (tid == 0) ed = pq_distance_thread(ep);
+    if (tid == 0) {
+      if (ep < g.n) atomicOr(&visited[ep >> 5], 1u << (ep & 31));
+      uint32_t kd = f2key(ed);
+      W[0] = ((uint64_t)kd << 32) | ep;
+      C[0] = ((uint64_t)kd << 32) | (uint32_t)~ep;
+      st[0] = 1; st[1] = 0; st[2] = 1; st[4] = 0;
+      n_dist++;
+    }
+    __syncthreads();
+    for (;;) {
+      // ---- pop the nearest candidate (index.rs:235-247)
+      if (tid == 0) {
+        int head = st[1], nC = st[2], nW = st[0];
+        int stop = 0;
+        uint32_t cur = 0;
+        for (;;) {
+          if (head >= nC) { stop = 1; break; }
+          uint64_t c = C[head++];
+          if (nW == 0) continue;                                       // peek() == None => continue
+          uint32_t ck = (uint32_t)(c >> 32), fk = (uint32_t)(W[nW - 1] >> 32);
+          if (ck > fk) { stop = 1; break; }                            // strictly farther than the furthest => break
+          cur = ~(uint32_t)c;
+          break;
+        }
+        st[1] = head; st[3] = (int)cur; st[4] = stop;
+      }
+      __syncthreads();
+      if (st[4]) break;
+      const uint32_t cur = (uint32_t)st[3];
+      // ---- edges of cur at this layer (graph_storage.rs:459-521)
+      long long idx = -1;
+      if (layer == 0) idx = cur;
+      else {
+        // first position of `cur` inside points[lvl_s, lvl_e): binary search in the per-layer sorted copy
+        long long lo = (long long)lvl_s, hi = (long long)lvl_e - 1;
+        while (lo <= hi) {
+          long long mid = (lo + hi) >> 1;
+          uint32_t v = g.upper_pid[mid];
+          if (v < cur) lo = mid + 1; else hi = mid - 1;
+        }
+        if (lo < (long long)lvl_e && g.upper_pid[lo] == cur) idx = (long long)g.upper_pos[lo] - (long long)lvl_s;
+      }
+      uint64_t e_begin = 0, e_end = 0;
+      if (idx >= 0 && lvl_s + (uint64_t)idx + 1 < g.n_edge_offsets) {
+        e_begin = g.edge_offsets[lvl_s + idx];
+        e_end = g.edge_offsets[lvl_s + idx + 1];
+      }
+      if (e_begin == e_end) { __syncthreads(); continue; }  // None => continue (uniform across the CTA)
+      if (tid == 0) n_expand++;
+      for (uint64_t eb = e_begin; eb < e_end; eb += 32) {
+        // ---- visited filter, edge order preserved (index.rs:255-259)
+        if (warp == 0) {
+          uint64_t ei = eb + lane;
+          uint32_t e = 0;
+          bool fresh = false;
+          if (ei < e_end) {
+            e = g.edges[ei];
+            if (e < g.n) {
+              uint32_t bit = 1u << (e & 31);
+              uint32_t old = atomicOr(&visited[e >> 5], bit);
+              fresh = !(old & bit);
+            }
+          }
+          unsigned mk = __ballot_sync(0xffffffffu, fresh);
+          if (fresh) nb[__popc(mk & ((1u << lane) - 1))] = e;
+          if (lane == 0) st[5] = __popc(mk);
+        }
+        __syncthreads();
+        const int nu = st[5];
+        // ---- distances (index.rs:264 -> :289-298)
+        if (QUANT == MGPU_QUANT_NONE) {
+          const int rounds = (nu + HN_WARPS * 2 - 1) / (HN_WARPS * 2);
+          for (int r = 0; r < rounds; r++) {
+            // both half-warps stay in the loop together (the lane reduction shuffles are full-warp);
+            // an out-of-range half re-scores the last neighbour and discards the result
+            int j = r * HN_WARPS * 2 + warp * 2 + (lane >> 4);
+            int jj = j < nu ? j : (nu - 1);
+            float d = flat_distance_halfwarp(nb[jj]);
+            if (j < nu && (lane & 15) == 0) nbk[j] = f2key(d);
+          }
+        } else {
+          if (tid < nu) nbk[tid] = f2key(pq_distance_thread(nb[tid]));
+        }
+        __syncthreads();
+        // ---- admissions, sequential in edge order (index.rs:260-281)
+        if (warp == 0) {
+          int nW = st[0], head = st[1], nC = st[2];
+          for (int j = 0; j < nu; j++) {
+            if (nW == 0) continue;  // peek() == None => continue (only when ef == 0)
+            uint32_t kd = nbk[j], e = nb[j];
+            uint32_t fk = (uint32_t)(W[nW - 1] >> 32);
+            if (kd < fk || nW < (int)ef) {
+              if (nC + 1 > (int)capC) {
+                // compact C (drop the consumed prefix)
+                int live = nC - head;
+                for (int base = 0; base < live; base += 32) {
+                  int i = base + lane;
+                  uint64_t v = 0;
+                  if (i < live) v = C[head + i];
+                  __syncwarp();
+                  if (i < live) C[i] = v;
+                  __syncwarp();
+                }
+                head = 0; nC = live;
+                if (nC + 1 > (int)capC) { if (lane == 0) err_flags[q] = 1; nC = capC - 1; }
+              }
+              nC = warp_sorted_insert(C, head, nC, ((uint64_t)kd << 32) | (uint32_t)~e);
+              nW = warp_sorted_insert(W, 0, nW, ((uint64_t)kd << 32) | e);
+              if (nW > (int)ef) nW--;  // pop the furthest (index.rs:277-279)
+              if (nW == (int)ef && nW > 0) {
+                // candidates strictly farther than the furthest can never be expanded: truncate the sorted tail
+                uint32_t fk2 = (uint32_t)(W[nW - 1] >> 32);
+                while (nC > head && (uint32_t)(C[nC - 1] >> 32) > fk2) nC--;
+              }
+            }
+          }
+          if (lane == 0) { st[0] = nW; st[1] = head; st[2] = nC; }
+        }
+        if (tid == 0) n_dist += nu;
+        __syncthreads();
+      }
+    }
+    // ---- next layer's entry: min_by distance over the sorted working list == W[0] (index.rs:176-181)
+    if (layer > 0) {
+      if (st[0] > 0) ep = (uint32_t)W[0];
+      __syncthreads();
+    }
+  }
+  // ---- results: working list is already sorted by (distance, point_id); truncate to k, map to doc ids (index.rs:185-204)
+  const int nW = st[0];
+  const uint32_t cnt = min((uint32_t)nW, a.k);
+  for (uint32_t i = tid; i < cnt; i += HN_THREADS) {
+    uint64_t w = W[i];
+    uint32_t pid = (uint32_t)w, kd = (uint32_t)(w >> 32);
+    uint32_t u = (kd & 0x80000000u) ? (kd ^ 0x80000000u) : ~kd;
+    a.out_scores[(size_t)q * a.k + i] = __uint_as_float(u);
+    if (a.out_pids) a.out_pids[(size_t)q * a.k + i] = pid;
+    if (a.out_docs) {
+      mgpu_u128 d;
+      if (g.doc_ids) d = g.doc_ids[pid]; else { d.lo = pid; d.hi = 0; }
+      a.out_docs[(size_t)q * a.k + i] = d;
+    }
+  }
+  if (tid == 0) {
+    a.out_counts[q] = cnt;
+    if (a.out_stats) { a.out_stats[2 * (size_t)q] = n_dist; a.out_stats[2 * (size_t)q + 1] = n_expand; }
+  }
+}
+
+int launch_hnsw_search(mgpu_hnsw *h, const HnswSearchArgs &a) {
+  mgpu_ctx *ctx = h->ctx;
+  if (a.B == 0) return MGPU_OK;
+  const uint32_t ef = a.ef;
+  const uint32_t capC = 2 * ef + 256;
+  const uint32_t vis_words = (uint32_t)((h->n + 31) / 32) + 1;
+  size_t smem = (size_t)(ef + 2) * 8 + (size_t)(capC + 2) * 8 + (size_t)((h->dim + 3) & ~3u) * 4 + 64 * 4 + 16 * 4;
+  if (smem > ctx->smem_optin) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "hnsw search: ef=%u needs %zu bytes of shared memory", ef, smem);
+  // workspace: visited bitmaps, query codes, error flags
+  size_t need = 0;
+  need = ws_need(need, (size_t)a.B * vis_words * 4);
+  need = ws_need(need, (size_t)a.B * (h->pq ? h->pq->m : 0));
+  need = ws_need(need, (size_t)a.B * 4);
+  // NOTE: the caller's staged buffers live at the front of the workspace; this launcher uses a private allocation
+  uint8_t *priv = nullptr;
+  CUDA_TRY(ctx, cudaMallocAsync((void **)&priv, need + 256, ctx->stream));
+  WsAlloc w(priv, need + 256);
+  uint32_t *visited = w.get<uint32_t>((size_t)a.B * vis_words);
+  uint8_t *qcodes = w.get<uint8_t>((size_t)a.B * (h->pq ? h->pq->m : 0));
+  uint32_t *err = w.get<uint32_t>(a.B);
+  CUDA_TRY(ctx, cudaMemsetAsync(visited, 0, (size_t)a.B * vis_words * 4, ctx->stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(err, 0, (size_t)a.B * 4, ctx->stream));
+  HnswDev g;
+  g.edges = h->d_edges; g.points = h->d_points; g.upper_pid = h->d_upper_sorted_pid; g.upper_pos = h->d_upper_sorted_pos;
+  g.edge_offsets = h->d_edge_offsets; g.level_offsets = h->d_level_offsets; g.rows = h->d_rows; g.doc_ids = h->d_doc_ids;
+  g.cb = h->pq ? h->pq->d_cb : nullptr; g.dim = h->dim; g.qdim = h->qdim; g.num_layers = h->num_layers;
+  g.entry_point = h->entry_point; g.m = h->pq ? h->pq->m : 0; g.K = h->pq ? h->pq->K : 0; g.dsub = h->pq ? h->pq->dsub : 0;
+  g.n = h->n; g.n_edge_offsets = h->n_edge_offsets;
+  int s = MGPU_OK;
+  if (h->quant == MGPU_QUANT_PQ) s = launch_pq_quantize(h->pq, a.Q, a.B, qcodes);  // index.rs:168
+  if (s == MGPU_OK) {
+    LaunchScope ls(ctx, MGPU_K_HNSW);
+#define HN_LAUNCH(QT, MT)                                                                                       \
+  do {                                                                                                          \
+    cudaFuncSetAttribute(k_hnsw_search<QT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    k_hnsw_search<QT, MT><<<a.B, HN_THREADS, smem, ctx->stream>>>(g, a, visited, vis_words, qcodes, capC, err); \
+  } while (0)
+    if (h->quant == MGPU_QUANT_NONE) { if (h->metric == MGPU_L2) HN_LAUNCH(MGPU_QUANT_NONE, MGPU_L2); else HN_LAUNCH(MGPU_QUANT_NONE, MGPU_DOT); }
+    else { if (h->metric == MGPU_L2) HN_LAUNCH(MGPU_QUANT_PQ, MGPU_L2); else HN_LAUNCH(MGPU_QUANT_PQ, MGPU_DOT); }
+#undef HN_LAUNCH
+    if (cudaGetLastError() != cudaSuccess) s = mgpu_fail(ctx, MGPU_ERR_CUDA, "hnsw search launch failed");
+  }
+  cudaFreeAsync(priv, ctx->stream);
+  return s;
+}

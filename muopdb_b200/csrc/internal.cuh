@@ -1,0 +1,125 @@
+// internal.cuh -- handle layouts and kernel launcher prototypes (host side).
+#pragma once
+#include "common.cuh"
+
+// ---- ProductQuantizer resident state ----------------------------------------------------------
+struct mgpu_pq {
+  mgpu_ctx *ctx;
+  uint32_t dim, dsub, nbits, m, K;
+  int metric;
+  float *d_cb = nullptr;      // [m][K][dsub] as in pq/mod.rs:155-167
+  float *d_table = nullptr;   // [m][K][K] score contribution of (query code a, row code b): L2 -> ||ca-cb||^2, dot -> -<ca,cb>
+  float *d_rowmin = nullptr;  // [m][K] min_b table[m][a][b]
+  float *d_rowmax = nullptr;  // [m][K]
+};
+
+// ---- IVF resident state -------------------------------------------------------------------------
+// HBM layout: every posting list is padded to a multiple of 32 rows ("chunks"); slot = chunk*32 + lane.
+//   slot_pid[slot]          point id of the row in that slot, MGPU_EMPTY_SLOT for padding
+//   PQ fast layout (m % 32 == 0, nbits == 8): per chunk, per 32-subspace group g, two 512-byte units;
+//       unit u holds for lane l the 16 bytes t = 16u .. 16u+15 where byte t = code of subspace 32g + (l ^ t).
+//       A warp reads a unit with one fully coalesced 16-byte-per-lane load, and at step t the 32 lanes touch 32
+//       different LUT columns (l ^ t) -> shared-memory lookups are bank-conflict free for ANY code values.
+//   PQ generic layout: codes_rm[slot][m] row-major.
+//   flat layout: per chunk [dim4][32 lanes] float4 (dim padded to a multiple of 4): lane = row, coalesced 512 B reads.
+struct mgpu_ivf {
+  mgpu_ctx *ctx;
+  uint32_t dim, nlist;
+  uint64_t n;
+  int quant, metric;
+  mgpu_pq *pq = nullptr;
+  float *d_centroids = nullptr;
+  uint32_t *d_chunk_start = nullptr;  // nlist+1, in chunks
+  uint32_t *d_list_len = nullptr;     // nlist
+  uint64_t total_chunks = 0;
+  uint32_t *d_slot_pid = nullptr;
+  bool pq_fast = false;
+  uint32_t ng = 0;                    // m / 32 when pq_fast
+  uint8_t *d_codes = nullptr;         // fast or generic layout
+  float *d_rows = nullptr;            // flat interleaved
+  uint32_t dim4 = 0;
+  mgpu_u128 *d_doc_ids = nullptr;     // null => identity
+  uint32_t *d_invalid = nullptr;      // bitmap over point ids
+  uint64_t n_invalid = 0;
+  unsigned long long *d_scan_rows = nullptr;  // rows scanned by the last scan
+  uint64_t bytes_per_row = 0;
+  std::vector<uint32_t> h_list_len;
+};
+
+struct mgpu_hnsw {
+  mgpu_ctx *ctx;
+  uint32_t dim, num_layers;
+  uint64_t n, n_edges, n_points, n_edge_offsets;
+  int quant, metric;
+  mgpu_pq *pq = nullptr;
+  uint32_t *d_edges = nullptr, *d_points = nullptr;
+  uint64_t *d_edge_offsets = nullptr, *d_level_offsets = nullptr;
+  void *d_rows = nullptr;  // row-major, indexed by point id
+  uint32_t qdim = 0;
+  mgpu_u128 *d_doc_ids = nullptr;
+  uint32_t entry_point = 0;
+  uint32_t max_degree = 0;
+  std::vector<uint64_t> h_level_offsets;
+  // upper-layer point -> position lookup: sorted (point, pos) pairs per layer
+  uint32_t *d_upper_sorted_pid = nullptr, *d_upper_sorted_pos = nullptr;
+};
+
+struct mgpu_spann {
+  mgpu_ctx *ctx;
+  mgpu_hnsw *centroids;
+  mgpu_ivf *lists;
+};
+
+// ---- candidates produced by a scan: per query 32 (composite key, slot) pairs -------------------
+#define MGPU_NCAND 32
+
+struct ScanArgs {
+  // index
+  const uint32_t *chunk_start, *list_len, *slot_pid, *invalid;
+  const uint8_t *codes; const float *rows;
+  uint32_t dim, dim4, m, K, ng;
+  // pq
+  const float *table, *rowmin, *rowmax;
+  const uint8_t *qcodes;  // B x m
+  // queries
+  const float *Q; uint32_t B;
+  const uint32_t *probes; uint32_t max_probes; const uint32_t *probe_counts;
+  // out
+  uint64_t *cand_key; uint32_t *cand_slot;  // B x 32
+  unsigned long long *rows_scanned;
+  int metric;
+};
+
+int launch_pq_build_table(mgpu_pq *pq);
+int launch_pq_quantize(mgpu_pq *pq, const float *dX, uint64_t n, uint8_t *dcodes);
+int launch_pq_distance_pairs(mgpu_pq *pq, const uint8_t *da, const uint8_t *db, uint64_t n, float *dout);
+int launch_build_layout(mgpu_ivf *ivf, const void *d_rows_by_pid);
+int launch_scan(mgpu_ivf *ivf, const ScanArgs &a);
+size_t scan_max_probes_supported(mgpu_ivf *ivf);
+
+struct FinalizeArgs {
+  const uint64_t *cand_key; const uint32_t *cand_slot; uint32_t B, k;
+  const uint32_t *slot_pid;
+  // exact PQ re-rank inputs (null for flat: keys are already exact)
+  const float *cb; const uint8_t *codes; const uint8_t *qcodes; uint32_t m, K, dsub, ng; bool pq_fast; int metric;
+  const mgpu_u128 *doc_ids;
+  // outputs (either may be null)
+  uint32_t *out_pids; mgpu_u128 *out_docs; float *out_scores; uint32_t *out_counts;
+};
+int launch_finalize(mgpu_ctx *ctx, const FinalizeArgs &a);
+
+int launch_distance_matrix(mgpu_ctx *ctx, const float *dA, uint64_t nA, const float *dB, uint64_t nB, uint32_t dim,
+                           int metric, int mode /*0 squared,1 sqrt*/, float *dout, int kernel_class);
+int launch_select_smallest(mgpu_ctx *ctx, const float *dD, uint32_t B, uint32_t C, uint32_t nsel, uint32_t *out_ids,
+                           float *out_vals);
+int launch_assign_filter(mgpu_ctx *ctx, const uint32_t *sel_ids, const float *sel_vals, uint64_t n, uint32_t r,
+                         float threshold, uint32_t *out_cids, uint32_t *out_counts);
+int launch_merge_topk(mgpu_ctx *ctx, const mgpu_u128 *docs, const float *scores, const uint32_t *counts, uint32_t S,
+                      uint32_t B, uint32_t k, mgpu_u128 *out_docs, float *out_scores, uint32_t *out_counts);
+
+struct HnswSearchArgs {
+  const float *Q; uint32_t B, k, ef;
+  mgpu_u128 *out_docs; float *out_scores; uint32_t *out_counts; uint64_t *out_stats;
+  uint32_t *out_pids;  // optional
+};
+int launch_hnsw_search(mgpu_hnsw *h, const HnswSearchArgs &a);

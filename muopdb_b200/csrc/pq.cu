@@ -1,0 +1,114 @@
+// pq.cu -- ProductQuantizer kernels: code-pair table, batch quantize, batch SDC distance.
+// Reference: rs/quantization/src/pq/mod.rs:152-177 (quantize), :202-278 (distance).
+#include "internal.cuh"
+#include "pq_device.cuh"
+
+// table[s][a][b] = score contribution of subspace s when the query code is a and the row code is b.
+//   L2 : ||cb[s][a] - cb[s][b]||^2   (calculate_squared on the dsub-long centroids)
+//   dot: -<cb[s][a], cb[s][b]>
+// Used by the scan to build the per-query LUT as a 1 KB row gather instead of re-reading the whole codebook.
+// One block per (s, a); also reduces rowmin/rowmax for the fixed-point LUT scaling.
+template <int METRIC>
+__global__ void k_pq_build_table(const float *__restrict__ cb, uint32_t dsub, uint32_t K, float *__restrict__ table,
+                                 float *__restrict__ rowmin, float *__restrict__ rowmax) {
+  uint32_t s = blockIdx.y, a = blockIdx.x;
+  const float *ca = cb + ((size_t)s * K + a) * dsub;
+  float mn = 3.4e38f, mx = -3.4e38f;
+  for (uint32_t b = threadIdx.x; b < K; b += blockDim.x) {
+    const float *cbv = cb + ((size_t)s * K + b) * dsub;
+    float v = ref_distance<METRIC>(PtrAcc{ca}, PtrAcc{cbv}, (int)dsub);
+    table[((size_t)s * K + a) * K + b] = v;
+    mn = fminf(mn, v); mx = fmaxf(mx, v);
+  }
+  __shared__ float smn[32], smx[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane_id() == 0) { smn[w] = mn; smx[w] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < nw; i++) { mn = fminf(mn, smn[i]); mx = fmaxf(mx, smx[i]); }
+    rowmin[(size_t)s * K + a] = mn; rowmax[(size_t)s * K + a] = mx;
+  }
+}
+
+int launch_pq_build_table(mgpu_pq *pq) {
+  mgpu_ctx *ctx = pq->ctx;
+  dim3 grid(pq->K, pq->m);
+  int threads = pq->K >= 256 ? 256 : (pq->K >= 32 ? (int)pq->K : 32);
+  LaunchScope ls(ctx, MGPU_K_OTHER);
+  if (pq->metric == MGPU_L2)
+    k_pq_build_table<MGPU_L2><<<grid, threads, 0, ctx->stream>>>(pq->d_cb, pq->dsub, pq->K, pq->d_table, pq->d_rowmin, pq->d_rowmax);
+  else
+    k_pq_build_table<MGPU_DOT><<<grid, threads, 0, ctx->stream>>>(pq->d_cb, pq->dsub, pq->K, pq->d_table, pq->d_rowmin, pq->d_rowmax);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return MGPU_OK;
+}
+
+// Quantizer::quantize for a batch (pq/mod.rs:152-177): grid = (row tiles, subspaces).  The subspace's centroids sit in
+// shared memory (every lane reads the same centroid -> broadcast), each thread owns one input row and keeps the
+// first minimum of the bit-exact calculate_squared.  ALWAYS the L2 calculator, whatever D is (pq/mod.rs:168).
+#define QT_ROWS 128
+__global__ void __launch_bounds__(QT_ROWS) k_pq_quantize(const float *__restrict__ X, uint64_t n, uint32_t dim,
+                                                          const float *__restrict__ cb, uint32_t dsub, uint32_t K,
+                                                          uint32_t m, uint8_t *__restrict__ codes) {
+  extern __shared__ float sm[];
+  float *scb = sm;                       // K * dsub
+  float *sx = sm + (size_t)K * dsub;     // QT_ROWS * (dsub + 1)
+  uint32_t s = blockIdx.y;
+  uint64_t row0 = (uint64_t)blockIdx.x * QT_ROWS;
+  const float *gcb = cb + (size_t)s * K * dsub;
+  for (uint32_t i = threadIdx.x; i < K * dsub; i += blockDim.x) scb[i] = gcb[i];
+  uint32_t pitch = dsub + 1;
+  for (uint32_t i = threadIdx.x; i < QT_ROWS * dsub; i += blockDim.x) {
+    uint32_t r = i / dsub, d = i % dsub;
+    uint64_t row = row0 + r;
+    sx[r * pitch + d] = row < n ? X[row * dim + (size_t)s * dsub + d] : 0.0f;
+  }
+  __syncthreads();
+  uint64_t row = row0 + threadIdx.x;
+  if (row >= n) return;
+  const float *x = sx + threadIdx.x * pitch;
+  uint32_t best = 0;
+  float best_d = 3.40282347e+38f;
+  for (uint32_t c = 0; c < K; c++) {
+    float d = ref_distance<MGPU_L2>(PtrAcc{x}, PtrAcc{scb + (size_t)c * dsub}, (int)dsub);
+    if (d < best_d) { best_d = d; best = c; }
+  }
+  codes[row * m + s] = (uint8_t)best;
+}
+
+int launch_pq_quantize(mgpu_pq *pq, const float *dX, uint64_t n, uint8_t *dcodes) {
+  mgpu_ctx *ctx = pq->ctx;
+  if (n == 0) return MGPU_OK;
+  size_t smem = ((size_t)pq->K * pq->dsub + (size_t)QT_ROWS * (pq->dsub + 1)) * sizeof(float);
+  if (smem > ctx->smem_optin) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "pq quantize: codebook slice of %zu bytes exceeds shared memory", smem);
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k_pq_quantize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((n + QT_ROWS - 1) / QT_ROWS), pq->m);
+  LaunchScope ls(ctx, MGPU_K_QUANTIZE);
+  k_pq_quantize<<<grid, QT_ROWS, smem, ctx->stream>>>(dX, n, pq->dim, pq->d_cb, pq->dsub, pq->K, pq->m, dcodes);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return MGPU_OK;
+}
+
+template <int METRIC>
+__global__ void k_pq_distance_pairs(const float *__restrict__ cb, uint32_t m, uint32_t K, uint32_t dsub,
+                                    const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, uint64_t n,
+                                    float *__restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = pq_distance_streaming<METRIC>(cb, m, K, dsub, RowMajorCode{a + i * m}, RowMajorCode{b + i * m});
+}
+
+int launch_pq_distance_pairs(mgpu_pq *pq, const uint8_t *da, const uint8_t *db, uint64_t n, float *dout) {
+  mgpu_ctx *ctx = pq->ctx;
+  if (n == 0) return MGPU_OK;
+  unsigned grid = (unsigned)((n + 127) / 128);
+  LaunchScope ls(ctx, MGPU_K_OTHER);
+  if (pq->metric == MGPU_L2) k_pq_distance_pairs<MGPU_L2><<<grid, 128, 0, ctx->stream>>>(pq->d_cb, pq->m, pq->K, pq->dsub, da, db, n, dout);
+  else k_pq_distance_pairs<MGPU_DOT><<<grid, 128, 0, ctx->stream>>>(pq->d_cb, pq->m, pq->K, pq->dsub, da, db, n, dout);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return MGPU_OK;
+}

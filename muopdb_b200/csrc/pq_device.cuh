@@ -1,0 +1,71 @@
+// pq_device.cuh -- bit-exact device restatement of ProductQuantizer::distance (StreamingSIMD).
+#pragma once
+#include "common.cuh"
+
+// ProductQuantizer::distance(a, b, StreamingSIMD) (pq/mod.rs:231-266), bit-exact: lane accumulators shared across
+// subspaces, one ordered reduction at the end, `sum_1 =` assignment for the scalar tail, D::outermost_op.
+template <int METRIC, class CodeA, class CodeB>
+__device__ __forceinline__ float pq_distance_streaming(const float *__restrict__ cb, uint32_t m, uint32_t K,
+                                                       uint32_t dsub, CodeA ca, CodeB cbk) {
+  float s16[16], s8[8], s4[4], s1 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s16[i] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s8[i] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 4; i++) s4[i] = 0.0f;
+  for (uint32_t s = 0; s < m; s++) {
+    const float *av = cb + ((size_t)s * K + ca(s)) * dsub;
+    const float *bv = cb + ((size_t)s * K + cbk(s)) * dsub;
+    uint32_t p = 0, rem = dsub;
+    if (rem / 16 > 0) {
+      uint32_t chunks = rem / 16;
+      for (uint32_t c = 0; c < chunks; c++) {
+#pragma unroll
+        for (int l = 0; l < 16; l++) {
+          float x = av[p + c * 16 + l], y = bv[p + c * 16 + l];
+          if (METRIC == MGPU_L2) { float d = __fsub_rn(x, y); s16[l] = __fadd_rn(s16[l], __fmul_rn(d, d)); }
+          else s16[l] = __fadd_rn(s16[l], __fmul_rn(x, y));
+        }
+      }
+      p += chunks * 16; rem -= chunks * 16;
+    }
+    if (rem / 8 > 0) {
+#pragma unroll
+      for (int l = 0; l < 8; l++) {
+        float x = av[p + l], y = bv[p + l];
+        if (METRIC == MGPU_L2) { float d = __fsub_rn(x, y); s8[l] = __fadd_rn(s8[l], __fmul_rn(d, d)); }
+        else s8[l] = __fadd_rn(s8[l], __fmul_rn(x, y));
+      }
+      p += 8; rem -= 8;
+    }
+    if (rem / 4 > 0) {
+#pragma unroll
+      for (int l = 0; l < 4; l++) {
+        float x = av[p + l], y = bv[p + l];
+        if (METRIC == MGPU_L2) { float d = __fsub_rn(x, y); s4[l] = __fadd_rn(s4[l], __fmul_rn(d, d)); }
+        else s4[l] = __fadd_rn(s4[l], __fmul_rn(x, y));
+      }
+      p += 4; rem -= 4;
+    }
+    if (rem > 0) {
+      float t = 0.0f;
+      for (uint32_t i = 0; i < rem; i++) {
+        float x = av[p + i], y = bv[p + i];
+        if (METRIC == MGPU_L2) { float d = __fsub_rn(x, y); t = __fadd_rn(t, __fmul_rn(d, d)); }
+        else t = __fadd_rn(t, __fmul_rn(x, y));
+      }
+      s1 = t;  // assignment, as in the reference (pq/mod.rs:260)
+    }
+  }
+  float r = __fadd_rn(ordered_reduce(s16, 16), ordered_reduce(s8, 8));
+  r = __fadd_rn(r, ordered_reduce(s4, 4));
+  r = __fadd_rn(r, s1);
+  return METRIC == MGPU_L2 ? r : -r;
+}
+
+struct RowMajorCode {
+  const uint8_t *p;
+  __device__ __forceinline__ uint32_t operator()(uint32_t s) const { return p[s]; }
+};
+

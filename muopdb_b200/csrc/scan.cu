@@ -1,0 +1,434 @@
+// scan.cu -- posting-list scan kernels (the hot loop of BlockBasedIvf::scan_posting_list /
+// search_with_centroids, rs/index/src/ivf/block_based/index.rs:175-285) for a batch of queries.
+//
+// One persistent CTA per SM; a CTA owns one query at a time (LUT / query vector resident in shared memory), its 16
+// warps stride over the 32-row chunks of the query's probed lists, one row per lane.  Every warp keeps its 32 best
+// (score key, point id) pairs sorted across lanes (warp-shuffle insertion); a CTA-wide threshold in shared memory
+// prunes rows that cannot enter any warp's list; the 16 lists are merged with shuffle bitonic merges.
+//
+// Modes
+//   SCAN_PQ_FAST    m % 32 == 0, 8-bit codes: conflict-free fixed-point LUT (see internal.cuh for the code layout)
+//   SCAN_PQ_GENERIC any m / nbits <= 8: natural [m][K] fixed-point LUT, row-major codes
+//   SCAN_FLAT_L2 / SCAN_FLAT_DOT  bit-exact fp32 distances in the reference's 16/8/4-lane order
+//
+// PQ modes rank rows by an order-independent fixed-point sum of LUT entries (exact integer adds, so equal code
+// words always get equal keys, like the reference's exact ties); the 32 survivors per query are re-scored bit-exactly
+// in finalize.cu, which also applies the reference's (distance, point_id) ordering.
+#include "internal.cuh"
+
+#define SCAN_THREADS 512
+#define SCAN_WARPS 16
+enum { SCAN_PQ_FAST = 0, SCAN_PQ_GENERIC = 1, SCAN_FLAT_L2 = 2, SCAN_FLAT_DOT = 3 };
+
+__device__ __forceinline__ uint4 ldg_stream16(const void *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ldg_stream16f(const void *p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+struct ScanSmemLayout {
+  uint32_t pol_bytes, tmp_bytes, total;
+  uint32_t off_tmp, off_pref, off_pcs, off_mkey, off_mpay, off_misc;
+};
+
+__host__ __device__ inline ScanSmemLayout scan_layout(int mode, uint32_t dim, uint32_t m, uint32_t K, uint32_t ng,
+                                                      uint32_t max_probes) {
+  ScanSmemLayout L;
+  if (mode == SCAN_PQ_FAST) { L.pol_bytes = ((ng + 1) / 2) * 65536u; L.tmp_bytes = 32u * 257u * 4u; }
+  else if (mode == SCAN_PQ_GENERIC) { L.pol_bytes = m * K * 4u; L.tmp_bytes = 0; }
+  else { L.pol_bytes = ((dim + 3) / 4) * 16u; L.tmp_bytes = 0; }
+  L.pol_bytes = (L.pol_bytes + 15u) & ~15u;
+  L.off_tmp = L.pol_bytes;
+  L.off_pref = L.off_tmp + L.tmp_bytes;
+  L.off_pcs = L.off_pref + (max_probes + 1) * 4u;
+  L.off_mkey = (L.off_pcs + max_probes * 4u + 15u) & ~15u;
+  L.off_mpay = L.off_mkey + SCAN_WARPS * 32u * 8u;
+  L.off_misc = L.off_mpay + SCAN_WARPS * 32u * 4u;
+  L.total = L.off_misc + 64u + 1024u * 4u + 1024u * 4u;  // flags | soff[1024] | scode[1024]
+  return L;
+}
+
+template <int MODE, int NG>
+__global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(ScanArgs a, ScanSmemLayout L) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *pol = smem;
+  float *tmp = (float *)(smem + L.off_tmp);
+  uint32_t *pref = (uint32_t *)(smem + L.off_pref);
+  uint32_t *pcs = (uint32_t *)(smem + L.off_pcs);
+  uint64_t *mkey = (uint64_t *)(smem + L.off_mkey);
+  uint32_t *mpay = (uint32_t *)(smem + L.off_mpay);
+  uint32_t *sh = (uint32_t *)(smem + L.off_misc);  // [0] threshold key, [1] total chunks, [2..3] scratch
+  float *shf = (float *)(sh + 4);                  // 12 floats of reduction scratch... (64 B block)
+  float *soff = (float *)(smem + L.off_misc + 64);
+  uint32_t *scode = (uint32_t *)(smem + L.off_misc + 64 + 4096);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t m = a.m, K = a.K;
+
+  // lane-dependent LUT column offsets for the conflict-free scan: x_t = ((lane ^ t) * 4), two per register
+  uint32_t xr[16];
+  if (MODE == SCAN_PQ_FAST) {
+#pragma unroll
+    for (int j = 0; j < 16; j++) xr[j] = (uint32_t)((lane ^ (2 * j)) << 2) | ((uint32_t)((lane ^ (2 * j + 1)) << 2) << 8);
+  }
+
+  for (uint32_t q = blockIdx.x; q < a.B; q += gridDim.x) {
+    uint32_t np = a.probe_counts ? min(a.probe_counts[q], a.max_probes) : a.max_probes;
+    // ---- 1. prefix of chunk counts over this query's probe list -------------------------------------------------
+    if (warp == 0) {
+      uint32_t run = 0;
+      unsigned long long rows = 0;
+      for (uint32_t base = 0; base < np; base += 32) {
+        uint32_t i = base + lane, cnt = 0, cs = 0, len = 0;
+        if (i < np) {
+          uint32_t c = a.probes[(size_t)q * a.max_probes + i];
+          cs = a.chunk_start[c];
+          cnt = a.chunk_start[c + 1] - cs;
+          len = a.list_len[c];
+        }
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        if (i < np) { pref[i] = run + incl - cnt; pcs[i] = cs; }
+        run += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) len += __shfl_xor_sync(0xffffffffu, len, o);
+        rows += len;
+      }
+      if (lane == 0) {
+        pref[np] = run;
+        sh[0] = 0xFFFFFFFFu;
+        sh[1] = run;
+        if (a.rows_scanned) atomicAdd(a.rows_scanned, rows);
+      }
+    }
+    // ---- 2. per-query state into shared memory -------------------------------------------------------------------
+    if (MODE == SCAN_PQ_FAST || MODE == SCAN_PQ_GENERIC) {
+      // fixed-point scale: sum over subspaces of the LUT row range must fit 32 bits
+      float part = 0.0f;
+      for (uint32_t s = tid; s < m; s += SCAN_THREADS) {
+        uint32_t code = a.qcodes[(size_t)q * m + s];
+        float mn = a.rowmin[(size_t)s * K + code], mx = a.rowmax[(size_t)s * K + code];
+        soff[s] = mn; scode[s] = code;
+        part += mx - mn;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (lane == 0) shf[warp] = part;
+      __syncthreads();
+      float R = 0.0f;
+#pragma unroll
+      for (int w = 0; w < SCAN_WARPS; w++) R += shf[w];
+      float scale = R > 0.0f ? 4.0e9f / R : 0.0f;
+      if (MODE == SCAN_PQ_FAST) {
+        for (int g = 0; g < NG; g++) {
+          // stage 32 table rows (1 KB each, coalesced) into a padded tile
+          for (int r = warp; r < 32; r += SCAN_WARPS) {
+            uint32_t s = g * 32 + r;
+            const float *src = a.table + ((size_t)s * K + scode[s]) * K;
+#pragma unroll
+            for (int j = lane; j < 256; j += 32) tmp[r * 257 + j] = src[j];
+          }
+          __syncthreads();
+          // transpose + convert: lane <-> LUT column (subspace), warps stride over codes; both sides conflict free
+          float off = soff[g * 32 + lane];
+          uint8_t *dst = pol + (g >> 1) * 65536 + (g & 1) * 128 + lane * 4;
+          for (int j = warp; j < 256; j += SCAN_WARPS) {
+            float v = tmp[lane * 257 + j];
+            *(uint32_t *)(dst + j * 256) = __float2uint_rn(__fmul_rn(__fsub_rn(v, off), scale));
+          }
+          __syncthreads();
+        }
+      } else {
+        uint32_t *lut = (uint32_t *)pol;
+        for (uint32_t s = warp; s < m; s += SCAN_WARPS) {
+          const float *src = a.table + ((size_t)s * K + scode[s]) * K;
+          float off = soff[s];
+          for (uint32_t j = lane; j < K; j += 32) lut[s * K + j] = __float2uint_rn(__fmul_rn(__fsub_rn(src[j], off), scale));
+        }
+      }
+    } else {
+      float *sq = (float *)pol;
+      for (uint32_t d = tid; d < a.dim4 * 4; d += SCAN_THREADS) sq[d] = d < a.dim ? a.Q[(size_t)q * a.dim + d] : 0.0f;
+    }
+    __syncthreads();
+
+    // ---- 3. scan ------------------------------------------------------------------------------------------------
+    const uint32_t total = sh[1];
+    WarpTop32 top;
+    top.init();
+    uint32_t p = 0;
+    for (uint32_t it = warp; it < total; it += SCAN_WARPS) {
+      while (it >= pref[p + 1]) p++;
+      const uint32_t chunk = pcs[p] + (it - pref[p]);
+      const uint32_t slot = chunk * 32 + lane;
+      const uint32_t pid = a.slot_pid[slot];
+      bool valid = pid != MGPU_EMPTY_SLOT;
+      if (a.invalid && valid) valid = !((a.invalid[pid >> 5] >> (pid & 31)) & 1u);  // index.rs:198-200
+
+      uint32_t key;
+      if (MODE == SCAN_PQ_FAST) {
+        const uint4 *base = (const uint4 *)a.codes + (size_t)chunk * (NG * 2 * 32) + lane;
+        uint4 u[NG * 2];
+#pragma unroll
+        for (int i = 0; i < NG * 2; i++) u[i] = ldg_stream16(base + i * 32);
+        uint32_t acc0 = 0, acc1 = 0;
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+          const uint8_t *lut_g = pol + (g >> 1) * 65536 + (g & 1) * 128;
+#pragma unroll
+          for (int wi = 0; wi < 8; wi++) {
+            const uint4 &uu = u[g * 2 + (wi >> 2)];
+            uint32_t w = (wi & 3) == 0 ? uu.x : ((wi & 3) == 1 ? uu.y : ((wi & 3) == 2 ? uu.z : uu.w));
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const int t = wi * 4 + k;
+              uint32_t idx = __byte_perm(w, xr[t >> 1], 0x7600 | (k << 4) | (4 + (t & 1)));
+              uint32_t v = *(const uint32_t *)(lut_g + idx);
+              if (t & 1) acc1 += v; else acc0 += v;
+            }
+          }
+        }
+        key = acc0 + acc1;
+      } else if (MODE == SCAN_PQ_GENERIC) {
+        const uint32_t *lut = (const uint32_t *)pol;
+        const uint8_t *cr = a.codes + (size_t)slot * m;
+        uint32_t acc = 0;
+        for (uint32_t s = 0; s < m; s++) acc += lut[s * K + cr[s]];
+        key = acc;
+      } else {
+        constexpr int METRIC = MODE == SCAN_FLAT_L2 ? MGPU_L2 : MGPU_DOT;
+        const float *sq = (const float *)pol;
+        const float4 *base = (const float4 *)a.rows + (size_t)chunk * a.dim4 * 32 + lane;
+        const int n = (int)a.dim;
+        float ret = 0.0f;
+        int pdim = 0;
+        const bool go16 = METRIC == MGPU_L2 ? (n / 16 > 0) : (n > 16);
+        if (go16) {
+          float acc[16];
+#pragma unroll
+          for (int l = 0; l < 16; l++) acc[l] = 0.0f;
+          const int chunks = n / 16;
+#pragma unroll 2
+          for (int c = 0; c < chunks; c++) {
+            float4 r[4], qq[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) r[j] = ldg_stream16f(base + (size_t)(c * 4 + j) * 32);
+#pragma unroll
+            for (int j = 0; j < 4; j++) qq[j] = *(const float4 *)(sq + c * 16 + j * 4);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const float rv[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
+              const float qv[4] = {qq[j].x, qq[j].y, qq[j].z, qq[j].w};
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                if (METRIC == MGPU_L2) { float d = __fsub_rn(qv[e], rv[e]); acc[j * 4 + e] = __fadd_rn(acc[j * 4 + e], __fmul_rn(d, d)); }
+                else acc[j * 4 + e] = __fadd_rn(acc[j * 4 + e], __fmul_rn(qv[e], rv[e]));
+              }
+            }
+          }
+          ret = __fadd_rn(ret, ordered_reduce(acc, 16));
+          pdim = chunks * 16;
+        }
+        // 8-lane / 4-lane / scalar remainder (l2.rs:45-66, dot_product.rs:51-69)
+        auto rowacc = [&](int i) { return ((const float *)(base + (size_t)(i >> 2) * 32))[i & 3]; };
+        auto qacc = [&](int i) { return sq[i]; };
+#pragma unroll
+        for (int li = 1; li < 3; li++) {
+          const int LN = li == 1 ? 8 : 4;
+          int rem = n - pdim;
+          bool go = METRIC == MGPU_L2 ? (rem / LN > 0) : (rem > LN);
+          if (go) {
+            float acc[8];
+#pragma unroll
+            for (int l = 0; l < 8; l++) acc[l] = 0.0f;
+            int chunks = rem / LN;
+            for (int c = 0; c < chunks; c++) {
+#pragma unroll
+              for (int l = 0; l < 8; l++) {
+                if (l < LN) {
+                  float x = qacc(pdim + c * LN + l), y = rowacc(pdim + c * LN + l);
+                  if (METRIC == MGPU_L2) { float d = __fsub_rn(x, y); acc[l] = __fadd_rn(acc[l], __fmul_rn(d, d)); }
+                  else acc[l] = __fadd_rn(acc[l], __fmul_rn(x, y));
+                }
+              }
+            }
+            float s = -0.0f;
+#pragma unroll
+            for (int l = 0; l < 8; l++) if (l < LN) s = __fadd_rn(s, acc[l]);
+            ret = __fadd_rn(ret, s);
+            pdim += chunks * LN;
+          }
+        }
+        for (; pdim < n; pdim++) {
+          float x = qacc(pdim), y = rowacc(pdim);
+          if (METRIC == MGPU_L2) { float d = __fsub_rn(x, y); ret = __fadd_rn(ret, __fmul_rn(d, d)); }
+          else ret = __fadd_rn(ret, __fmul_rn(x, y));
+        }
+        key = METRIC == MGPU_L2 ? f2key(sqrtf(ret)) : f2key(-ret);  // noq/mod.rs:44-51 -> D::calculate
+      }
+
+      const uint32_t thr = *(volatile uint32_t *)&sh[0];
+      const bool pass = valid && key <= thr;
+      if (__any_sync(0xffffffffu, pass)) {
+        uint32_t worst = top.offer(pass, ((uint64_t)key << 32) | pid, slot);
+        if (lane == 0 && worst < thr) atomicMin(&sh[0], worst);
+      }
+    }
+
+    // ---- 4. merge the 16 warp lists -----------------------------------------------------------------------------
+    mkey[warp * 32 + lane] = top.key;
+    mpay[warp * 32 + lane] = top.pay;
+    __syncthreads();
+#pragma unroll
+    for (int half = SCAN_WARPS / 2; half >= 1; half >>= 1) {
+      if (warp < half) {
+        top.merge(mkey[(warp + half) * 32 + lane], mpay[(warp + half) * 32 + lane]);
+        mkey[warp * 32 + lane] = top.key;
+        mpay[warp * 32 + lane] = top.pay;
+      }
+      __syncthreads();
+    }
+    if (warp == 0) {
+      a.cand_key[(size_t)q * MGPU_NCAND + lane] = top.key;
+      a.cand_slot[(size_t)q * MGPU_NCAND + lane] = top.pay;
+    }
+    __syncthreads();
+  }
+}
+
+static int scan_mode(const mgpu_ivf *ivf) {
+  if (ivf->quant == MGPU_QUANT_PQ) return ivf->pq_fast ? SCAN_PQ_FAST : SCAN_PQ_GENERIC;
+  return ivf->metric == MGPU_L2 ? SCAN_FLAT_L2 : SCAN_FLAT_DOT;
+}
+
+size_t scan_max_probes_supported(mgpu_ivf *ivf) {
+  int mode = scan_mode(ivf);
+  uint32_t m = ivf->pq ? ivf->pq->m : 0, K = ivf->pq ? ivf->pq->K : 0;
+  ScanSmemLayout L0 = scan_layout(mode, ivf->dim, m, K, ivf->ng, 0);
+  if (L0.total > ivf->ctx->smem_optin) return 0;
+  return (ivf->ctx->smem_optin - L0.total) / 8;
+}
+
+template <int MODE, int NG>
+static int launch_scan_t(mgpu_ivf *ivf, const ScanArgs &a, const ScanSmemLayout &L) {
+  mgpu_ctx *ctx = ivf->ctx;
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k_scan<MODE, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  unsigned grid = a.B < (uint32_t)ctx->sm_count ? a.B : (unsigned)ctx->sm_count;
+  LaunchScope ls(ctx, MGPU_K_SCAN);
+  k_scan<MODE, NG><<<grid, SCAN_THREADS, L.total, ctx->stream>>>(a, L);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return MGPU_OK;
+}
+
+int launch_scan(mgpu_ivf *ivf, const ScanArgs &a) {
+  mgpu_ctx *ctx = ivf->ctx;
+  if (a.B == 0) return MGPU_OK;
+  int mode = scan_mode(ivf);
+  ScanSmemLayout L = scan_layout(mode, a.dim, a.m, a.K, a.ng, a.max_probes);
+  if (L.total > ctx->smem_optin)
+    return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "scan needs %u bytes of shared memory (max %zu): m*K or max_probes too large", L.total, ctx->smem_optin);
+  if (a.m > 1024) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "scan supports at most 1024 PQ subspaces");
+  switch (mode) {
+    case SCAN_PQ_FAST:
+      switch (a.ng) {
+        case 1: return launch_scan_t<SCAN_PQ_FAST, 1>(ivf, a, L);
+        case 2: return launch_scan_t<SCAN_PQ_FAST, 2>(ivf, a, L);
+        case 3: return launch_scan_t<SCAN_PQ_FAST, 3>(ivf, a, L);
+        case 4: return launch_scan_t<SCAN_PQ_FAST, 4>(ivf, a, L);
+        default: return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "fast PQ scan supports m in {32,64,96,128}");
+      }
+    case SCAN_PQ_GENERIC: return launch_scan_t<SCAN_PQ_GENERIC, 1>(ivf, a, L);
+    case SCAN_FLAT_L2: return launch_scan_t<SCAN_FLAT_L2, 1>(ivf, a, L);
+    default: return launch_scan_t<SCAN_FLAT_DOT, 1>(ivf, a, L);
+  }
+}
+
+// ---- layout builders --------------------------------------------------------------------------------------------------
+// slot -> point id, then scatter the rows (indexed by point id) into the chunked layouts described in internal.cuh.
+__global__ void k_layout_pq_fast(const uint8_t *__restrict__ codes_by_pid, const uint32_t *__restrict__ slot_pid,
+                                 uint64_t nslots, uint32_t m, uint32_t ng, uint8_t *__restrict__ out) {
+  // one thread per (slot, group, unit): writes 16 bytes
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t total = nslots * ng * 2;
+  if (i >= total) return;
+  uint32_t u = (uint32_t)(i % 2);
+  uint32_t g = (uint32_t)((i / 2) % ng);
+  uint64_t slot = i / (2 * ng);
+  uint32_t lane = (uint32_t)(slot & 31);
+  uint64_t chunk = slot >> 5;
+  uint32_t pid = slot_pid[slot];
+  uint32_t w[4] = {0, 0, 0, 0};
+  if (pid != MGPU_EMPTY_SLOT) {
+    const uint8_t *row = codes_by_pid + (size_t)pid * m + g * 32;
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+      uint32_t t = u * 16 + b;
+      uint32_t code = row[lane ^ t];
+      w[b >> 2] |= code << ((b & 3) * 8);
+    }
+  }
+  uint4 *dst = (uint4 *)out + ((chunk * ng + g) * 2 + u) * 32 + lane;
+  *dst = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void k_layout_pq_generic(const uint8_t *__restrict__ codes_by_pid, const uint32_t *__restrict__ slot_pid,
+                                    uint64_t nslots, uint32_t m, uint8_t *__restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nslots * m) return;
+  uint64_t slot = i / m;
+  uint32_t s = (uint32_t)(i % m);
+  uint32_t pid = slot_pid[slot];
+  out[i] = pid != MGPU_EMPTY_SLOT ? codes_by_pid[(size_t)pid * m + s] : 0;
+}
+
+__global__ void k_layout_flat(const float *__restrict__ rows_by_pid, const uint32_t *__restrict__ slot_pid,
+                              uint64_t nslots, uint32_t dim, uint32_t dim4, float *__restrict__ out) {
+  // one thread per (chunk, d4, lane): writes one float4; consecutive threads -> consecutive lanes (coalesced writes)
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nslots * dim4) return;
+  uint32_t lane = (uint32_t)(i & 31);
+  uint64_t rest = i >> 5;
+  uint32_t d4 = (uint32_t)(rest % dim4);
+  uint64_t chunk = rest / dim4;
+  uint32_t pid = slot_pid[chunk * 32 + lane];
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (pid != MGPU_EMPTY_SLOT) {
+    const float *row = rows_by_pid + (size_t)pid * dim;
+#pragma unroll
+    for (int e = 0; e < 4; e++) if (d4 * 4 + e < dim) v[e] = row[d4 * 4 + e];
+  }
+  ((float4 *)out)[i] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+int launch_build_layout(mgpu_ivf *ivf, const void *d_rows_by_pid) {
+  mgpu_ctx *ctx = ivf->ctx;
+  uint64_t nslots = ivf->total_chunks * 32;
+  if (nslots == 0) return MGPU_OK;
+  LaunchScope ls(ctx, MGPU_K_OTHER);
+  if (ivf->quant == MGPU_QUANT_PQ) {
+    uint32_t m = ivf->pq->m;
+    if (ivf->pq_fast) {
+      uint64_t total = nslots * ivf->ng * 2;
+      k_layout_pq_fast<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t *)d_rows_by_pid, ivf->d_slot_pid, nslots, m, ivf->ng, ivf->d_codes);
+    } else {
+      uint64_t total = nslots * m;
+      k_layout_pq_generic<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t *)d_rows_by_pid, ivf->d_slot_pid, nslots, m, ivf->d_codes);
+    }
+  } else {
+    uint64_t total = nslots * ivf->dim4;
+    k_layout_flat<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const float *)d_rows_by_pid, ivf->d_slot_pid, nslots, ivf->dim, ivf->dim4, ivf->d_rows);
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  return MGPU_OK;
+}

@@ -1,0 +1,380 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bar: bit-exact for codes, ids and scores (the kernels restate the reference's lane order with non-fused fp32 ops);
+doc-id sets compared exactly, including ties.  Each test cites the reference behaviour it pins.
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def M():
+    import muopdb_b200 as M
+    return M
+
+
+def _same_f32(a, b):
+    a, b = np.asarray(a, dtype=np.float32), np.asarray(b, dtype=np.float32)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+# ---- DistanceCalculator -----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [1, 3, 4, 7, 8, 15, 16, 17, 30, 31, 32, 128, 768, 771])
+def test_distance_batch_bit_exact(M, dim):
+    """l2.rs:30-74, dot_product.rs:38-71: every lane-cascade shape (16/8/4/tail), bit-exact."""
+    rng = np.random.default_rng(dim)
+    A = rng.random((37, dim), dtype=np.float32)
+    B = rng.random((53, dim), dtype=np.float32)
+    assert _same_f32(M.L2DistanceCalculator.calculate_batch(A, B), O.distance_batch(A, B, O.L2, False))
+    assert _same_f32(M.L2DistanceCalculator.calculate_batch(A, B, squared=True), O.distance_batch(A, B, O.L2, True))
+    assert _same_f32(M.DotProductDistanceCalculator.calculate_batch(A, B), O.distance_batch(A, B, O.DOT))
+
+
+def test_distance_single_pair_and_device_buffers(M):
+    import torch
+    rng = np.random.default_rng(5)
+    a, b = rng.random(128, dtype=np.float32), rng.random(128, dtype=np.float32)
+    assert M.L2DistanceCalculator.calculate(a, b) == O.l2(a, b)
+    assert M.L2DistanceCalculator.calculate_squared(a, b) == O.l2_squared(a, b)
+    assert M.DotProductDistanceCalculator.calculate(a, b) == O.dot(a, b)
+    A = rng.random((64, 128), dtype=np.float32)
+    B = rng.random((96, 128), dtype=np.float32)
+    out = M.L2DistanceCalculator.calculate_batch(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda())
+    M.default_context().sync()
+    assert _same_f32(out.cpu().numpy(), O.distance_batch(A, B))
+
+
+# ---- ProductQuantizer -------------------------------------------------------------------------------------------------
+def test_pq_known_codes(M):
+    """pq/mod.rs:321-351 and ivf/writer.rs:526-614 golden codes, on the GPU."""
+    cb = []
+    for s in range(5):
+        for i in range(2):
+            cb += [float(s * 2 + i)] * 2
+    pq = M.ProductQuantizer(10, 2, 1, cb)
+    assert pq.quantize([1, 1, 3, 3, 5, 5, 7, 7, 9, 9]).tolist() == [1, 1, 1, 1, 1]
+    pq2 = M.ProductQuantizer(3, 1, 1, [1.5, 4.5, 2.3, 5.3, 3.1, 6.1])
+    assert pq2.quantize(np.array([[1, 2, 3], [4, 5, 6]], dtype=np.float32)).tolist() == [[0, 0, 0], [1, 1, 1]]
+    with pytest.raises(M.InvalidArgument):
+        M.ProductQuantizer(10, 3, 1, [0.0] * 20)  # "Dimensions are not valid" (pq/mod.rs:41-46)
+
+
+@pytest.mark.parametrize("dim,dsub,nbits", [(128, 8, 8), (768, 8, 8), (64, 16, 8), (120, 24, 6), (30, 5, 3), (32, 2, 4), (16, 1, 8)])
+def test_pq_quantize_and_distance_bit_exact(M, dim, dsub, nbits):
+    """pq/mod.rs:152-177 (first-minimum argmin) and :231-266 (StreamingSIMD, incl. the sum_1 assignment quirk)."""
+    rng = np.random.default_rng(dim * 31 + dsub)
+    cb = rng.random(dim * (1 << nbits), dtype=np.float32)
+    # duplicate a few centroids so that exact argmin ties exist (first minimum must win)
+    c3 = cb.reshape(dim // dsub, 1 << nbits, dsub)
+    c3[:, -1] = c3[:, 0]
+    X = rng.random((300, dim), dtype=np.float32)
+    X[:10] = c3[:, 0].reshape(-1)  # rows exactly on a duplicated centroid
+    opq = O.ProductQuantizer(dim, dsub, nbits, cb)
+    gpq = M.ProductQuantizer(dim, dsub, nbits, cb)
+    oc, gc = opq.quantize(X), gpq.quantize(X)
+    assert np.array_equal(oc, gc)
+    a, b = oc[:150], oc[150:]
+    od = np.array([opq.distance(a[i], b[i]) for i in range(150)], dtype=np.float32)
+    assert _same_f32(gpq.distance(a, b), od)
+    # dot-product calculator as the generic D (only reachable from the offline index_writer)
+    opd = O.ProductQuantizer(dim, dsub, nbits, cb, metric=O.DOT)
+    gpd = M.ProductQuantizer(dim, dsub, nbits, cb, distance=M.DotProductDistanceCalculator)
+    od = np.array([opd.distance(a[i], b[i]) for i in range(150)], dtype=np.float32)
+    assert _same_f32(gpd.distance(a, b), od)
+
+
+# ---- IVF --------------------------------------------------------------------------------------------------------------
+def _check_ivf(M, X, nlist, nprobe, k, pq_params=None, max_clusters=1, metric="l2", nq=64, invalidate=None, seed=0,
+               queries=None):
+    rng = np.random.default_rng(seed)
+    cents, offsets, ids = synth.build_ivf_arrays(X, nlist, seed=seed + 1, max_clusters=max_clusters)
+    docs = synth.doc_ids_for(len(X), seed=seed + 2)
+    dim = X.shape[1]
+    if pq_params:
+        dsub, nbits = pq_params
+        cb = O.train_pq_codebook(X[rng.choice(len(X), min(len(X), 2000), replace=False)], dsub, nbits, iters=4, seed=seed)
+        opq = O.ProductQuantizer(dim, dsub, nbits, cb, metric=O.DOT if metric == "dot" else O.L2)
+        gq = M.ProductQuantizer(dim, dsub, nbits, cb, distance=M.DotProductDistanceCalculator if metric == "dot" else M.L2DistanceCalculator)
+        rows = opq.quantize(X)
+        oivf = O.Ivf(cents, offsets, ids, rows, doc_ids=docs, pq=opq)
+    else:
+        rows = X
+        gq = M.NoQuantizer(dim, M.DotProductDistanceCalculator if metric == "dot" else M.L2DistanceCalculator)
+        oivf = O.Ivf(cents, offsets, ids, rows, doc_ids=docs, metric=O.DOT if metric == "dot" else O.L2)
+    givf = M.BlockBasedIvf(cents, offsets, ids, rows, gq, doc_ids=docs)
+    assert givf.num_clusters() == nlist and givf.num_vectors() == len(X)
+    if invalidate is not None:
+        oivf.invalidate_batch(invalidate)
+        givf.invalidate_batch(invalidate)
+        assert givf.is_invalidated(int(invalidate[0]))
+    Q = queries if queries is not None else np.vstack([X[:nq // 2] + 0.01 * rng.standard_normal((nq // 2, dim)).astype(np.float32),
+                                                         rng.random((nq - nq // 2, dim), dtype=np.float32)])
+    # coarse: identical probe lists (distances are bit-exact, ties by centroid index on both sides)
+    gp, gd = givf.find_nearest_centroids_batch(Q, nprobe, with_distances=True)
+    for b in range(len(Q)):
+        op, od = oivf.find_nearest_centroids(Q[b], nprobe, with_dist=True)
+        assert np.array_equal(op, gp[b]), b
+        assert _same_f32(od, gd[b])
+    # full search
+    od, os_, oc = oivf.search_batch(Q, k, nprobe)
+    res = givf.search_batch(Q, k, nprobe)
+    assert np.array_equal(np.asarray(res.counts, dtype=np.int64), oc.astype(np.int64))
+    for b in range(len(Q)):
+        n = oc[b]
+        assert np.array_equal(res.doc_ids[b, :n], od[b, :n]), (b, res.doc_ids[b, :n], od[b, :n], res.scores[b, :n], os_[b, :n])
+        assert _same_f32(res.scores[b, :n], os_[b, :n]), b
+    # search_with_centroids (point ids, ordered by (distance, point_id)) for a few queries
+    r2 = givf.search_with_centroids_batch(Q[:8], gp[:8], k, remap=False)
+    for b in range(8):
+        pids, ds = oivf.search_with_centroids(Q[b], gp[b], k)
+        assert np.array_equal(r2.doc_ids[b, :len(pids)], pids)
+        assert _same_f32(r2.scores[b, :len(pids)], ds)
+    return givf, oivf, Q
+
+
+def test_ivf_flat_config1_fixture(M):
+    """BASELINE config 1 shape on the reference's own committed rows (rs/index/resources/10000_rows_128_dim, first
+    2048 rows committed under tests/golden): IVF flat-L2, 128-d, nlist 64, nprobe 8."""
+    import os
+    X = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "rows_2048x128.f32"), dtype="<f4").reshape(2048, 128)
+    _check_ivf(M, X, nlist=64, nprobe=8, k=10, nq=100)
+
+
+@pytest.mark.parametrize("dim,nlist,nprobe,k", [(4, 10, 2, 5), (30, 16, 16, 10), (128, 32, 5, 1), (768, 24, 6, 10), (20, 7, 7, 32)])
+def test_ivf_flat_l2_parity(M, dim, nlist, nprobe, k):
+    """ivf/block_based/index.rs:147-332 with NoQuantizer<L2>: sqrt scores, (score, doc_id) order."""
+    X = synth.clustered(3000, dim, n_blobs=12, seed=dim)
+    _check_ivf(M, X, nlist, nprobe, k, seed=dim)
+
+
+def test_ivf_flat_dot_parity(M):
+    """NoQuantizer<DotProduct> (index_writer only): negated dot scores; coarse scoring stays sqrt-L2 (index.rs:155)."""
+    X = synth.uniform(2000, 48, seed=9)
+    _check_ivf(M, X, 16, 4, 10, metric="dot", seed=9)
+
+
+@pytest.mark.parametrize("dim,dsub,nbits,nlist,nprobe", [(256, 8, 8, 16, 4), (768, 8, 8, 24, 8), (512, 8, 8, 8, 8), (1024, 8, 8, 6, 3),
+                                                         (128, 8, 8, 32, 8), (64, 16, 4, 8, 3), (30, 5, 3, 8, 8), (128, 4, 8, 10, 4)])
+def test_ivf_pq_parity(M, dim, dsub, nbits, nlist, nprobe):
+    """ProductQuantizer<L2>: symmetric, squared scores (pq/mod.rs:231-266); query quantized with the same codebook
+    (index.rs:193).  m in {32,64,96,128} with 8 bits runs the conflict-free fast scan, the rest the generic one."""
+    X = synth.clustered(4000, dim, n_blobs=16, seed=dim + dsub)
+    _check_ivf(M, X, nlist, nprobe, 10, pq_params=(dsub, nbits), seed=dim + dsub)
+
+
+def test_ivf_pq_exact_ties_and_duplicates(M):
+    """Many rows share a code word (exact score ties) and points live in two lists (max_clusters_per_vector = 2):
+    ties resolve by point id then doc id, duplicates are kept (index.rs:265-274, utils.rs:71-76,95-114)."""
+    rng = np.random.default_rng(77)
+    base = synth.clustered(400, 256, n_blobs=6, seed=77)
+    X = np.repeat(base, 5, axis=0)  # 5 exact copies of every vector
+    X = X[rng.permutation(len(X))]
+    _check_ivf(M, X, nlist=8, nprobe=8, k=16, pq_params=(8, 8), max_clusters=2, seed=78)
+    _check_ivf(M, X, nlist=8, nprobe=3, k=16, max_clusters=2, seed=79)
+
+
+def test_ivf_invalidation_and_short_results(M):
+    """index.rs:198-200: invalidated ids are skipped; fewer than k results are possible."""
+    X = synth.clustered(600, 64, n_blobs=4, seed=5)
+    inv = np.arange(0, 600, 3, dtype=np.uint32)
+    _check_ivf(M, X, nlist=40, nprobe=2, k=32, invalidate=inv, seed=6)
+    _check_ivf(M, X, nlist=40, nprobe=1, k=32, pq_params=(2, 8), invalidate=inv, seed=7)
+
+
+def test_ivf_empty_lists_and_probe_range(M):
+    """Empty posting lists are legal; num_probes == 0 or > num_clusters panics in the reference (index.rs:158)."""
+    X = synth.uniform(50, 16, seed=3)
+    cents = np.vstack([X[:5], 10.0 + synth.uniform(3, 16, seed=4)]).astype(np.float32)  # last 3 lists stay empty
+    offsets, ids = O.build_posting_lists(X, cents)
+    givf = M.BlockBasedIvf(cents, offsets, ids, X, M.NoQuantizer(16))
+    oivf = O.Ivf(cents, offsets, ids, X)
+    Q = synth.uniform(9, 16, seed=5)
+    Q[0] += 10.0  # probes only empty lists with nprobe small
+    for nprobe in (1, 3, 8):
+        od, os_, oc = oivf.search_batch(Q, 10, nprobe)
+        r = givf.search_batch(Q, 10, nprobe)
+        assert np.array_equal(np.asarray(r.counts, dtype=np.int64), oc.astype(np.int64))
+        for b in range(len(Q)):
+            assert np.array_equal(r.doc_ids[b, :oc[b]], od[b, :oc[b]]) and _same_f32(r.scores[b, :oc[b]], os_[b, :oc[b]])
+    with pytest.raises(M.OutOfRange):
+        givf.search_batch(Q, 10, 0)
+    with pytest.raises(M.OutOfRange):
+        givf.search_batch(Q, 10, 9)
+    r = givf.search_batch(Q, 0, 2)  # k == 0: a heap of capacity 0 keeps nothing
+    assert not np.asarray(r.counts).any()
+    assert givf.search(Q[1], 3, 2).id_with_scores[0].score == O.Ivf(cents, offsets, ids, X).search(Q[1], 3, 2)[1][0]
+
+
+def test_ivf_device_buffers_and_scan_accounting(M):
+    """MGPU_DEVICE path: torch CUDA tensors in and out; algorithmic-bytes accounting = sum of probed list lengths."""
+    import torch
+    X = synth.clustered(5000, 256, n_blobs=20, seed=21)
+    cents, offsets, ids = synth.build_ivf_arrays(X, 32, seed=22)
+    cb = O.train_pq_codebook(X[:2000], 8, 8, iters=3, seed=1)
+    opq = O.ProductQuantizer(256, 8, 8, cb)
+    gpq = M.ProductQuantizer(256, 8, 8, cb)
+    codes = opq.quantize(X)
+    oivf = O.Ivf(cents, offsets, ids, codes, pq=opq)
+    givf = M.BlockBasedIvf(cents, offsets, ids, torch.from_numpy(codes).cuda(), gpq)  # rows already resident in HBM
+    Q = X[100:164] + 0.01
+    od, os_, oc = oivf.search_batch(Q, 10, 6)
+    r = givf.search_batch(torch.from_numpy(Q).cuda(), 10, 6)
+    givf.ctx.sync()
+    d = r.doc_ids.cpu().numpy().view(np.uint64)
+    assert np.array_equal(d, od) and _same_f32(r.scores.cpu().numpy(), os_)
+    lens = np.diff(offsets).astype(np.int64)
+    expect_rows = sum(int(lens[oivf.find_nearest_centroids(Q[b], 6)].sum()) for b in range(len(Q)))
+    assert givf.last_scan_rows() == expect_rows
+    assert givf.last_scan_bytes() == expect_rows * (32 + 4)
+
+
+# ---- build-time assignment / merge --------------------------------------------------------------------------------------
+def test_assign_matches_builder_rule(M):
+    """ivf/builder.rs:268-329 incl. the golden case of :810-872."""
+    X = np.arange(1, 7, dtype=np.float32).reshape(6, 1)
+    cents = np.array([[2.5], [5.5]], dtype=np.float32)
+    cids, cnt = M.assign_to_centroids(X, cents, 2, 0.1)
+    assert cnt.tolist() == [1, 1, 1, 2, 1, 1] and cids[3].tolist() == [0, 1] and cids[0, 0] == 0 and cids[5, 0] == 1
+    Xb = synth.clustered(3000, 128, seed=8)
+    cb = O.kmeans(Xb, 50, 4, seed=2)
+    for r, thr in ((1, 0.1), (3, 0.2)):
+        oc, on = O.ivf_assign(Xb, cb, r, thr)
+        gc, gn = M.assign_to_centroids(Xb, cb, r, thr)
+        assert np.array_equal(on, gn) and np.array_equal(oc, gc)
+
+
+def test_merge_topk(M):
+    """collection/snapshot.rs:60-61,105-106 + utils.rs:95-114 (NaN last, doc-id tie-break on the full 128 bits)."""
+    rng = np.random.default_rng(4)
+    S, B, k = 5, 33, 7
+    docs = np.zeros((S, B, k, 2), dtype=np.uint64)
+    docs[..., 0] = rng.integers(0, 50, (S, B, k))
+    docs[..., 1] = rng.integers(0, 2, (S, B, k))
+    scores = rng.integers(0, 6, (S, B, k)).astype(np.float32)  # many ties
+    scores[0, 0, 0] = np.nan
+    counts = rng.integers(0, k + 1, (S, B)).astype(np.uint32)
+    r = M.merge_topk(docs, scores, counts, k)
+    for b in range(B):
+        dl, sl = [], []
+        for s in range(S):
+            n = counts[s, b]
+            dl += [int(lo) | (int(hi) << 64) for lo, hi in docs[s, b, :n]]
+            sl += scores[s, b, :n].tolist()
+        ed, es = O.merge_topk(dl, sl, k) if dl else ([], np.zeros(0, np.float32))
+        assert int(r.counts[b]) == len(ed)
+        got = [int(lo) | (int(hi) << 64) for lo, hi in r.doc_ids[b, :len(ed)]]
+        assert got == ed
+        assert np.array_equal(np.isnan(es), np.isnan(r.scores[b, :len(ed)]))
+        assert np.array_equal(es[~np.isnan(es)], r.scores[b, :len(ed)][~np.isnan(es)])
+
+
+# ---- HNSW / SPANN ---------------------------------------------------------------------------------------------------------
+def _graph(X, M_=16, layers=5, efc=60, seed=9):
+    g = O.hnsw_build(X, M_, layers, efc, seed=seed)
+    return g
+
+
+@pytest.mark.parametrize("dim,n,ef,k", [(16, 3000, 64, 10), (128, 2000, 128, 10), (768, 800, 32, 5), (20, 1500, 100, 32), (4, 500, 1, 1)])
+def test_hnsw_flat_parity(M, dim, n, ef, k):
+    """hnsw/block_based/index.rs:159-298: identical ids, scores and traversal counts (#distance evals, #expansions)."""
+    X = synth.clustered(n, dim, n_blobs=10, seed=dim)
+    g = _graph(X, seed=dim)
+    docs = synth.doc_ids_for(n, seed=1)
+    oh = O.Hnsw(g["num_layers"], g["edges"], g["points"], g["edge_offsets"], g["level_offsets"], X, doc_ids=docs)
+    gh = M.BlockBasedHnsw(g["num_layers"], g["edges"], g["points"], g["edge_offsets"], g["level_offsets"], X,
+                          M.NoQuantizer(dim), doc_ids=docs)
+    rng = np.random.default_rng(3)
+    Q = np.vstack([X[:20] + 0.02 * rng.standard_normal((20, dim)).astype(np.float32), rng.random((20, dim), dtype=np.float32)])
+    od, os_, oc, ost = oh.search_batch(Q, k, ef)
+    r, st = gh.ann_search_batch(Q, k, ef, with_stats=True)
+    assert np.array_equal(np.asarray(r.counts, dtype=np.int64), oc.astype(np.int64))
+    for b in range(len(Q)):
+        assert np.array_equal(r.doc_ids[b, :oc[b]], od[b, :oc[b]]), b
+        assert _same_f32(r.scores[b, :oc[b]], os_[b, :oc[b]]), b
+    assert np.array_equal(st, ost)
+
+
+def test_hnsw_pq_parity(M):
+    """BlockBasedHnsw<ProductQuantizer<L2>>: quantized query (index.rs:168), squared SDC scores, many exact ties."""
+    dim, n = 64, 2500
+    X = synth.clustered(n, dim, n_blobs=8, seed=31)
+    g = _graph(X, seed=31)
+    cb = O.train_pq_codebook(X[:1500], 8, 4, iters=4, seed=2)  # 4 bits -> coarse codes -> lots of ties
+    opq, gpq = O.ProductQuantizer(dim, 8, 4, cb), M.ProductQuantizer(dim, 8, 4, cb)
+    codes = opq.quantize(X)
+    oh = O.Hnsw(g["num_layers"], g["edges"], g["points"], g["edge_offsets"], g["level_offsets"], codes, pq=opq)
+    gh = M.BlockBasedHnsw(g["num_layers"], g["edges"], g["points"], g["edge_offsets"], g["level_offsets"], codes, gpq)
+    Q = X[50:90] + 0.01
+    od, os_, oc, ost = oh.search_batch(Q, 10, 48)
+    r, st = gh.ann_search_batch(Q, 10, 48, with_stats=True)
+    assert np.array_equal(r.doc_ids, od) and _same_f32(r.scores, os_) and np.array_equal(st, ost)
+
+
+def test_hnsw_hand_built_graph(M):
+    """graph_storage.rs:459-554 on a hand-built 2-layer file image (same case as tests/test_oracle_golden.py)."""
+    X = np.array([[0.0], [1.0], [2.0], [3.0], [4.0]], dtype=np.float32)
+    gh = M.BlockBasedHnsw(2, [0, 4, 1, 0, 2, 1, 3, 2, 4, 3], [4, 0], [0, 1, 2, 3, 5, 7, 9, 10], [0, 2, 7], X, M.NoQuantizer(1))
+    res = gh.ann_search([0.9], 2, 4)
+    assert [x.doc_id for x in res.id_with_scores] == [1, 0]
+
+
+def _spann_pair(M, X, docs, nlist, pq_params=None, seed=7):
+    cents = O.kmeans(X, nlist, iters=25, seed=seed)
+    offsets, ids = O.build_posting_lists(X, cents, 1, 0.1)
+    g = O.hnsw_build(cents, 10, 2, 100, seed=3)
+    dim = X.shape[1]
+    if pq_params:
+        dsub, nbits, ntrain = pq_params
+        cb = O.train_pq_codebook(X[np.random.default_rng(0).choice(len(X), ntrain, replace=False)], dsub, nbits, iters=20, seed=5)
+        opq, gpq = O.ProductQuantizer(dim, dsub, nbits, cb), M.ProductQuantizer(dim, dsub, nbits, cb)
+        rows = opq.quantize(X)
+        oivf = O.Ivf(cents, offsets, ids, rows, doc_ids=docs, pq=opq)
+        givf = M.BlockBasedIvf(cents, offsets, ids, rows, gpq, doc_ids=docs)
+    else:
+        oivf = O.Ivf(cents, offsets, ids, X, doc_ids=docs)
+        givf = M.BlockBasedIvf(cents, offsets, ids, X, M.NoQuantizer(dim), doc_ids=docs)
+    ohn = O.Hnsw(g["num_layers"], g["edges"], g["points"], g["edge_offsets"], g["level_offsets"], cents)
+    ghn = M.BlockBasedHnsw(g["num_layers"], g["edges"], g["points"], g["edge_offsets"], g["level_offsets"], cents, M.NoQuantizer(dim))
+    return O.Spann(ohn, oivf), M.Spann(ghn, givf), oivf, givf
+
+
+def test_spann_reference_golden_cases(M):
+    """spann/index.rs:293-366 ([4,3]), :369-445 (after invalidating 4 -> [3,5]), :448-525 (PQ: five exact zeros),
+    multi_spann/index.rs:358-412 ([1000,3,2]) -- the reference's own known answers, on the GPU."""
+    n = 1000
+    X = np.repeat(np.arange(n, dtype=np.float32)[:, None], 4, axis=1)
+    _, gs, _, givf = _spann_pair(M, X, list(range(n)), 10)
+    res = gs.search([2.4, 3.4, 4.4, 5.4], M.SearchParams(2, 2))
+    assert [x.doc_id for x in res.id_with_scores] == [4, 3]
+    givf.invalidate(4)
+    res = gs.search([2.4, 3.4, 4.4, 5.4], M.SearchParams(2, 2))
+    assert [x.doc_id for x in res.id_with_scores] == [3, 5]
+    _, gs, _, _ = _spann_pair(M, X, list(range(n)), 10, pq_params=(2, 2, 200))
+    res = gs.search([2.4, 3.4, 4.4, 5.4], M.SearchParams(5, 2))
+    assert len(res.id_with_scores) == 5 and all(x.score == 0.0 for x in res.id_with_scores)
+    X2 = np.vstack([X, np.array([[1.2, 2.2, 3.2, 4.2]], dtype=np.float32)])
+    _, gs, _, _ = _spann_pair(M, X2, list(range(n + 1)), 10)
+    res = gs.search([1.4, 2.4, 3.4, 4.4], M.SearchParams(3, 2))
+    assert [x.doc_id for x in res.id_with_scores] == [1000, 3, 2]
+
+
+@pytest.mark.parametrize("pq", [None, (8, 8, 1500)])
+def test_spann_parity(M, pq):
+    """spann/index.rs:211-266: centroid HNSW -> ratio prune -> list scan -> remap, vs the oracle, default and loose ratio."""
+    X = synth.clustered(4000, 256, n_blobs=24, seed=41)
+    docs = synth.doc_ids_for(len(X), seed=4)
+    osp, gsp, _, _ = _spann_pair(M, X, docs, 48, pq_params=pq)
+    Q = X[200:260] + 0.01
+    for ne, ratio in ((10, 0.1), (16, 10.0), (1, 0.0)):
+        od, os_, oc = osp.search_batch(Q, 10, 50, ne, ratio)
+        r = gsp.search_batch(Q, M.SearchParams(10, 50, False, ne, ratio))
+        assert np.array_equal(np.asarray(r.counts).astype(np.int32), oc)  # UINT32_MAX == -1 encodes None
+        for b in range(len(Q)):
+            n = max(int(oc[b]), 0)
+            assert np.array_equal(r.doc_ids[b, :n], od[b, :n]), (ne, ratio, b)
+            assert _same_f32(r.scores[b, :n], os_[b, :n])
