@@ -4,9 +4,12 @@
 #include "pq_device.cuh"
 
 // table[s][a][b] = score contribution of subspace s when the query code is a and the row code is b.
-//   L2 : ||cb[s][a] - cb[s][b]||^2   (calculate_squared on the dsub-long centroids)
-//   dot: -<cb[s][a], cb[s][b]>
-// Used by the scan to build the per-query LUT as a 1 KB row gather instead of re-reading the whole codebook.
+//   L2 : ||cb[s][a] - cb[s][b]||^2,  dot: -<cb[s][a], cb[s][b]>
+// restricted to what ProductQuantizer::distance(StreamingSIMD) actually accumulates (pq/mod.rs:231-266): the 16/8/4-lane
+// phases of every subspace, but the scalar tail (dsub % 4 dims) of the LAST subspace only -- `sum_1 = ...` is an
+// assignment, so earlier tails are overwritten (pq/mod.rs:259-261).
+// Used by the scan to build the per-query LUT as a 1 KB row gather instead of re-reading the whole codebook; the scan
+// only ranks with it (fixed point), exact scores come from pq_distance_streaming.
 // One block per (s, a); also reduces rowmin/rowmax for the fixed-point LUT scaling.
 template <int METRIC>
 __global__ void k_pq_build_table(const float *__restrict__ cb, uint32_t dsub, uint32_t K, float *__restrict__ table,
@@ -16,7 +19,14 @@ __global__ void k_pq_build_table(const float *__restrict__ cb, uint32_t dsub, ui
   float mn = 3.4e38f, mx = -3.4e38f;
   for (uint32_t b = threadIdx.x; b < K; b += blockDim.x) {
     const float *cbv = cb + ((size_t)s * K + b) * dsub;
-    float v = ref_distance<METRIC>(PtrAcc{ca}, PtrAcc{cbv}, (int)dsub);
+    const uint32_t lanes_end = dsub - (dsub % 4);
+    const uint32_t end = (s + 1 == gridDim.y) ? dsub : lanes_end;
+    float v = 0.0f;
+    for (uint32_t d = 0; d < end; d++) {
+      float x = ca[d], y = cbv[d];
+      if (METRIC == MGPU_L2) { float df = __fsub_rn(x, y); v = __fadd_rn(v, __fmul_rn(df, df)); }
+      else v = __fsub_rn(v, __fmul_rn(x, y));
+    }
     table[((size_t)s * K + a) * K + b] = v;
     mn = fminf(mn, v); mx = fmaxf(mx, v);
   }
