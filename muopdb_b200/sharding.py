@@ -1,0 +1,56 @@
+"""Doc-sharded multi-GPU search: one process per GPU, each rank holds one shard (its own coarse centroids, posting
+lists and doc-id table); queries are replicated; every rank returns the merged top-k.
+
+Semantic model: rs/aggregator/src/aggregator.rs:81-132 (independent shards "{index}--{shard_id}", results unioned) with the
+leaf ordering of rs/index/src/collection/snapshot.rs:49-63 (sort by (score, doc_id), truncate to k) -- the aggregator's
+descending, untruncated sort (aggregator.rs:135) is NOT followed.
+
+Exchange step: one NCCL all-gather of the per-shard (doc_id, score, count) blocks over NVLink followed by the merge kernel
+(mgpu_shard_allgather_merge).  torch.distributed is only the rendezvous (it ships the NCCL unique id).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_of(doc_ids_lo: np.ndarray, world: int) -> np.ndarray:
+    """Shard assignment: doc_id mod world (on the low 64 bits; ids are u128 (lo, hi) pairs)."""
+    return (np.asarray(doc_ids_lo, dtype=np.uint64) % np.uint64(world)).astype(np.int64)
+
+
+def split_probes(nprobe: int, nlist: int, world: int):
+    """Per-shard (nlist, nprobe) keeping the probed fraction of the collection constant."""
+    return max(nlist // world, 1), max(nprobe // world, 1)
+
+
+def init_comm(ctx, dist=None):
+    """Create the NCCL communicator of `ctx` across the torch.distributed world (any backend is fine for the
+    rendezvous)."""
+    import torch
+    import torch.distributed as dist_mod
+    dist = dist or dist_mod
+    world, rank = dist.get_world_size(), dist.get_rank()
+    from . import Context
+    obj = [Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    ctx.comm_init(world, rank, obj[0])
+    return world, rank
+
+
+class ShardedSearcher:
+    """Wraps a rank-local index with the all-gather + merge exchange."""
+
+    def __init__(self, local_index, ctx):
+        self.local, self.ctx = local_index, ctx
+
+    def search_batch(self, Q_dev, k: int, local_search, out=None):
+        """local_search(Q_dev) -> BatchResult of device tensors for this shard; returns merged device tensors."""
+        import torch
+        r = local_search(Q_dev)
+        B = Q_dev.shape[0]
+        if out is None:
+            out = (torch.zeros((B, k, 2), dtype=torch.int64, device=Q_dev.device),
+                   torch.zeros((B, k), dtype=torch.float32, device=Q_dev.device),
+                   torch.zeros((B,), dtype=torch.int32, device=Q_dev.device))
+        self.ctx.shard_allgather_merge(r.doc_ids, r.scores, r.counts, B, k, *out)
+        return out

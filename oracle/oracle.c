@@ -66,7 +66,14 @@ static inline void dot_accumulate_lanes(const float *a, const float *b, size_t n
 }
 
 /* L2DistanceCalculator::calculate_squared (l2.rs:30-68) */
-ORC_API float orc_l2_squared(const float *a, const float *b, uint64_t n) {
+static inline __attribute__((always_inline)) float l2_squared_inl(const float *a, const float *b, uint64_t n) {
+  if (n == 8) { /* same arithmetic as the general cascade (one 8-lane chunk: 0 + d*d per lane, ordered reduce, 0 + s) */
+    float sq[8];
+    for (int l = 0; l < 8; l++) { float d = a[l] - b[l]; sq[l] = 0.0f + d * d; }
+    float s = -0.0f;
+    for (int l = 0; l < 8; l++) s = s + sq[l];
+    return 0.0f + s;
+  }
   float ret = 0.0f;
   size_t rem = (size_t)n;
   static const int LANES[3] = {16, 8, 4};
@@ -86,6 +93,8 @@ ORC_API float orc_l2_squared(const float *a, const float *b, uint64_t n) {
   }
   return ret;
 }
+
+ORC_API float orc_l2_squared(const float *a, const float *b, uint64_t n) { return l2_squared_inl(a, b, n); }
 
 /* L2DistanceCalculator::calculate (l2.rs:72-74) */
 ORC_API float orc_l2(const float *a, const float *b, uint64_t n) { return sqrtf(orc_l2_squared(a, b, n)); }
@@ -176,7 +185,7 @@ ORC_API void orc_pq_quantize(const float *cb, uint32_t dim, uint32_t dsub, uint3
     uint32_t best = 0;
     float best_d = 3.40282347e+38f; /* f32::MAX */
     for (uint32_t i = 0; i < K; i++) {
-      float d = orc_l2_squared(sub, base + (size_t)i * dsub, dsub);
+      float d = l2_squared_inl(sub, base + (size_t)i * dsub, dsub);
       if (d < best_d) { best_d = d; best = i; }
     }
     out[s] = (uint8_t)best;
