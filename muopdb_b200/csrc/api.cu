@@ -313,8 +313,8 @@ int mgpu_ivf_create(mgpu_ctx *ctx, uint32_t dim, uint32_t nlist, const float *ce
     if (s == MGPU_OK && cudaMemsetAsync(ivf->d_invalid, 0, ((n + 31) / 32 + 1) * 4, ctx->stream) != cudaSuccess) s = MGPU_ERR_CUDA;
   }
   if (s == MGPU_OK) {
-    s = dev_alloc_copy<unsigned long long>(ctx, &ivf->d_scan_rows, nullptr, 1);
-    if (s == MGPU_OK) cudaMemsetAsync(ivf->d_scan_rows, 0, 8, ctx->stream);
+    s = dev_alloc_copy<unsigned long long>(ctx, &ivf->d_scan_rows, nullptr, 2);
+    if (s == MGPU_OK) cudaMemsetAsync(ivf->d_scan_rows, 0, 16, ctx->stream);
   }
   // rows -> chunked layout
   void *d_src = nullptr;
@@ -453,7 +453,8 @@ static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32
   a.invalid = ivf->n_invalid ? ivf->d_invalid : nullptr;
   a.codes = ivf->d_codes; a.rows = ivf->d_rows; a.dim = ivf->dim; a.dim4 = ivf->dim4; a.ng = ivf->ng;
   a.Q = dQ; a.B = B; a.probes = d_probes; a.max_probes = max_probes; a.probe_counts = d_counts;
-  a.cand_key = d_ckey; a.cand_slot = d_cslot; a.rows_scanned = ivf->d_scan_rows; a.metric = ivf->metric;
+  a.cand_key = d_ckey; a.cand_slot = d_cslot; a.rows_scanned = ivf->d_scan_rows; a.next_query = (unsigned int *)(ivf->d_scan_rows + 1);
+  a.metric = ivf->metric;
   if (ivf->quant == MGPU_QUANT_PQ) {
     mgpu_pq *pq = ivf->pq;
     a.m = pq->m; a.K = pq->K; a.table = pq->d_table; a.rowmin = pq->d_rowmin; a.rowmax = pq->d_rowmax;

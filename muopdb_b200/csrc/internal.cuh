@@ -41,7 +41,7 @@ struct mgpu_ivf {
   mgpu_u128 *d_doc_ids = nullptr;     // null => identity
   uint32_t *d_invalid = nullptr;      // bitmap over point ids
   uint64_t n_invalid = 0;
-  unsigned long long *d_scan_rows = nullptr;  // rows scanned by the last scan
+  unsigned long long *d_scan_rows = nullptr;  // [0] rows scanned by the last scan, [1] query scheduler counter
   uint64_t bytes_per_row = 0;
   std::vector<uint32_t> h_list_len;
 };
@@ -87,6 +87,7 @@ struct ScanArgs {
   // out
   uint64_t *cand_key; uint32_t *cand_slot;  // B x 32
   unsigned long long *rows_scanned;
+  unsigned int *next_query;  // zeroed before every launch: dynamic query scheduler
   int metric;
 };
 

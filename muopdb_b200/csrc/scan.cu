@@ -16,8 +16,10 @@
 // in finalize.cu, which also applies the reference's (distance, point_id) ordering.
 #include "internal.cuh"
 
-#define SCAN_THREADS 512
-#define SCAN_WARPS 16
+#define SCAN_MAX_WARPS 32
+#ifndef SCAN_FAST_NT
+#define SCAN_FAST_NT 768
+#endif
 enum { SCAN_PQ_FAST = 0, SCAN_PQ_GENERIC = 1, SCAN_FLAT_L2 = 2, SCAN_FLAT_DOT = 3 };
 
 __device__ __forceinline__ uint4 ldg_stream16(const void *p) {
@@ -31,6 +33,14 @@ __device__ __forceinline__ float4 ldg_stream16f(const void *p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
+}
+
+// prmt.b32 with the full selector semantics (bit 3 of a selector nibble replicates the sign bit of the chosen byte);
+// the __byte_perm intrinsic only honours 3 bits per nibble.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
 }
 
 struct ScanSmemLayout {
@@ -49,14 +59,15 @@ __host__ __device__ inline ScanSmemLayout scan_layout(int mode, uint32_t dim, ui
   L.off_pref = L.off_tmp + L.tmp_bytes;
   L.off_pcs = L.off_pref + (max_probes + 1) * 4u;
   L.off_mkey = (L.off_pcs + max_probes * 4u + 15u) & ~15u;
-  L.off_mpay = L.off_mkey + SCAN_WARPS * 32u * 8u;
-  L.off_misc = L.off_mpay + SCAN_WARPS * 32u * 4u;
-  L.total = L.off_misc + 64u + 1024u * 4u + 1024u * 4u;  // flags | soff[1024] | scode[1024]
+  L.off_mpay = L.off_mkey + SCAN_MAX_WARPS * 32u * 8u;
+  L.off_misc = L.off_mpay + SCAN_MAX_WARPS * 32u * 4u;
+  L.total = L.off_misc + 384u + 1024u * 4u + 1024u * 4u;  // flags, reduction scratch, b2[32] | soff[1024] | scode[1024]
   return L;
 }
 
-template <int MODE, int NG>
-__global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(ScanArgs a, ScanSmemLayout L) {
+template <int MODE, int NG, int NT>
+__global__ void __launch_bounds__(NT, 1) k_scan(ScanArgs a, ScanSmemLayout L) {
+  constexpr int SCAN_THREADS = NT, SCAN_WARPS = NT / 32;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *pol = smem;
   float *tmp = (float *)(smem + L.off_tmp);
@@ -64,22 +75,32 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(ScanArgs a, ScanSmemLa
   uint32_t *pcs = (uint32_t *)(smem + L.off_pcs);
   uint64_t *mkey = (uint64_t *)(smem + L.off_mkey);
   uint32_t *mpay = (uint32_t *)(smem + L.off_mpay);
-  uint32_t *sh = (uint32_t *)(smem + L.off_misc);  // [0] threshold key, [1] total chunks, [2..3] scratch
-  float *shf = (float *)(sh + 4);                  // 12 floats of reduction scratch... (64 B block)
-  float *soff = (float *)(smem + L.off_misc + 64);
-  uint32_t *scode = (uint32_t *)(smem + L.off_misc + 64 + 4096);
+  uint32_t *sh = (uint32_t *)(smem + L.off_misc);  // [0] threshold key, [1] total chunks, [2] next query
+  float *shf = (float *)(sh + 32);                 // 32 floats of reduction scratch
+  uint32_t *b2 = sh + 64;                          // per-warp 2nd-best key (threshold tightening)
+  float *soff = (float *)(smem + L.off_misc + 384);
+  uint32_t *scode = (uint32_t *)(smem + L.off_misc + 384 + 4096);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t m = a.m, K = a.K;
 
-  // lane-dependent LUT column offsets for the conflict-free scan: x_t = ((lane ^ t) * 4), two per register
-  uint32_t xr[16];
+  // lane-dependent LUT column offsets for the conflict-free scan: x_t = ((lane ^ t) * 4) <= 124, four per register.
+  // PRMT builds the LUT byte offset (code << 8) | x_t in ONE instruction: byte0 = x_t, byte1 = code, bytes 2/3 = the
+  // sign replication of x_t (msb is 0) = 0.
+  uint32_t xr[8];
   if (MODE == SCAN_PQ_FAST) {
 #pragma unroll
-    for (int j = 0; j < 16; j++) xr[j] = (uint32_t)((lane ^ (2 * j)) << 2) | ((uint32_t)((lane ^ (2 * j + 1)) << 2) << 8);
+    for (int j = 0; j < 8; j++)
+      xr[j] = (uint32_t)((lane ^ (4 * j)) << 2) | ((uint32_t)((lane ^ (4 * j + 1)) << 2) << 8) |
+              ((uint32_t)((lane ^ (4 * j + 2)) << 2) << 16) | ((uint32_t)((lane ^ (4 * j + 3)) << 2) << 24);
   }
 
-  for (uint32_t q = blockIdx.x; q < a.B; q += gridDim.x) {
+  for (;;) {
+    // dynamic query scheduling: one atomic per query keeps the 148 persistent CTAs balanced on ragged probe lists
+    if (tid == 0) sh[2] = atomicAdd(a.next_query, 1u);
+    __syncthreads();
+    const uint32_t q = sh[2];
+    if (q >= a.B) break;
     uint32_t np = a.probe_counts ? min(a.probe_counts[q], a.max_probes) : a.max_probes;
     // ---- 1. prefix of chunk counts over this query's probe list -------------------------------------------------
     if (warp == 0) {
@@ -109,6 +130,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(ScanArgs a, ScanSmemLa
         pref[np] = run;
         sh[0] = 0xFFFFFFFFu;
         sh[1] = run;
+      }
+      if (lane < SCAN_WARPS) b2[lane] = 0xFFFFFFFFu;
+      if (lane == 0) {
         if (a.rows_scanned) atomicAdd(a.rows_scanned, rows);
       }
     }
@@ -167,6 +191,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(ScanArgs a, ScanSmemLa
     const uint32_t total = sh[1];
     WarpTop32 top;
     top.init();
+    bool first = true;
     uint32_t p = 0;
     for (uint32_t it = warp; it < total; it += SCAN_WARPS) {
       while (it >= pref[p + 1]) p++;
@@ -193,7 +218,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(ScanArgs a, ScanSmemLa
 #pragma unroll
             for (int k = 0; k < 4; k++) {
               const int t = wi * 4 + k;
-              uint32_t idx = __byte_perm(w, xr[t >> 1], 0x7600 | (k << 4) | (4 + (t & 1)));
+              uint32_t idx = prmt(w, xr[t >> 2], ((12 + (t & 3)) << 12) | ((12 + (t & 3)) << 8) | (k << 4) | (4 + (t & 3)));
               uint32_t v = *(const uint32_t *)(lut_g + idx);
               if (t & 1) acc1 += v; else acc0 += v;
             }
@@ -281,18 +306,38 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(ScanArgs a, ScanSmemLa
       const uint32_t thr = *(volatile uint32_t *)&sh[0];
       const bool pass = valid && key <= thr;
       if (__any_sync(0xffffffffu, pass)) {
-        uint32_t worst = top.offer(pass, ((uint64_t)key << 32) | pid, slot);
-        if (lane == 0 && worst < thr) atomicMin(&sh[0], worst);
+        uint32_t worst;
+        if (first) {
+          // empty list: one bitonic sort instead of up to 32 sequential insertions
+          top.key = pass ? (((uint64_t)key << 32) | pid) : MGPU_EMPTY_KEY;
+          top.pay = pass ? slot : MGPU_EMPTY_SLOT;
+          top.sort();
+          worst = (uint32_t)(shfl64(top.key, 31) >> 32);
+          first = false;
+        } else {
+          worst = top.offer(pass, ((uint64_t)key << 32) | pid, slot);
+        }
+        // Threshold tightening.  (a) this warp's 32nd best bounds the global 32nd best; (b) so does the maximum over
+        // warps of their 2nd best (the union of every warp's two best already holds >= 32 rows).  (b) converges ~5x
+        // faster because each warp only sees 1/NW of the rows.
+        uint32_t second = (uint32_t)(shfl64(top.key, 1) >> 32);
+        if (lane == 0) b2[warp] = second;
+        __syncwarp();
+        uint32_t v = lane < SCAN_WARPS ? *(volatile uint32_t *)&b2[lane] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+        v = min(v, worst);
+        if (lane == 0 && v < thr) atomicMin(&sh[0], v);
       }
     }
 
-    // ---- 4. merge the 16 warp lists -----------------------------------------------------------------------------
+    // ---- 4. merge the warp lists -----------------------------------------------------------------------------
     mkey[warp * 32 + lane] = top.key;
     mpay[warp * 32 + lane] = top.pay;
     __syncthreads();
 #pragma unroll
-    for (int half = SCAN_WARPS / 2; half >= 1; half >>= 1) {
-      if (warp < half) {
+    for (int half = 16; half >= 1; half >>= 1) {
+      if (warp < half && warp + half < SCAN_WARPS) {
         top.merge(mkey[(warp + half) * 32 + lane], mpay[(warp + half) * 32 + lane]);
         mkey[warp * 32 + lane] = top.key;
         mpay[warp * 32 + lane] = top.pay;
@@ -320,13 +365,14 @@ size_t scan_max_probes_supported(mgpu_ivf *ivf) {
   return (ivf->ctx->smem_optin - L0.total) / 8;
 }
 
-template <int MODE, int NG>
+template <int MODE, int NG, int NT = 512>
 static int launch_scan_t(mgpu_ivf *ivf, const ScanArgs &a, const ScanSmemLayout &L) {
   mgpu_ctx *ctx = ivf->ctx;
-  CUDA_TRY(ctx, cudaFuncSetAttribute(k_scan<MODE, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k_scan<MODE, NG, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   unsigned grid = a.B < (uint32_t)ctx->sm_count ? a.B : (unsigned)ctx->sm_count;
+  CUDA_TRY(ctx, cudaMemsetAsync(a.next_query, 0, 4, ctx->stream));
   LaunchScope ls(ctx, MGPU_K_SCAN);
-  k_scan<MODE, NG><<<grid, SCAN_THREADS, L.total, ctx->stream>>>(a, L);
+  k_scan<MODE, NG, NT><<<grid, NT, L.total, ctx->stream>>>(a, L);
   CUDA_TRY(ctx, cudaGetLastError());
   return MGPU_OK;
 }
@@ -344,7 +390,7 @@ int launch_scan(mgpu_ivf *ivf, const ScanArgs &a) {
       switch (a.ng) {
         case 1: return launch_scan_t<SCAN_PQ_FAST, 1>(ivf, a, L);
         case 2: return launch_scan_t<SCAN_PQ_FAST, 2>(ivf, a, L);
-        case 3: return launch_scan_t<SCAN_PQ_FAST, 3>(ivf, a, L);
+        case 3: return launch_scan_t<SCAN_PQ_FAST, 3, SCAN_FAST_NT>(ivf, a, L);
         case 4: return launch_scan_t<SCAN_PQ_FAST, 4>(ivf, a, L);
         default: return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "fast PQ scan supports m in {32,64,96,128}");
       }
