@@ -96,6 +96,7 @@ int launch_pq_quantize(mgpu_pq *pq, const float *dX, uint64_t n, uint8_t *dcodes
 int launch_pq_distance_pairs(mgpu_pq *pq, const uint8_t *da, const uint8_t *db, uint64_t n, float *dout);
 int launch_build_layout(mgpu_ivf *ivf, const void *d_rows_by_pid);
 int launch_scan(mgpu_ivf *ivf, const ScanArgs &a);
+int launch_scan_pq_db(mgpu_ivf *ivf, const ScanArgs &a);  // MGPU_ERR_UNSUPPORTED => use launch_scan's generic kernels
 size_t scan_max_probes_supported(mgpu_ivf *ivf);
 
 struct FinalizeArgs {

@@ -15,33 +15,11 @@
 // words always get equal keys, like the reference's exact ties); the 32 survivors per query are re-scored bit-exactly
 // in finalize.cu, which also applies the reference's (distance, point_id) ordering.
 #include "internal.cuh"
+#include "scan_common.cuh"
 
-#define SCAN_MAX_WARPS 32
 #ifndef SCAN_FAST_NT
 #define SCAN_FAST_NT 768
 #endif
-enum { SCAN_PQ_FAST = 0, SCAN_PQ_GENERIC = 1, SCAN_FLAT_L2 = 2, SCAN_FLAT_DOT = 3 };
-
-__device__ __forceinline__ uint4 ldg_stream16(const void *p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ float4 ldg_stream16f(const void *p) {
-  float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-}
-
-// prmt.b32 with the full selector semantics (bit 3 of a selector nibble replicates the sign bit of the chosen byte);
-// the __byte_perm intrinsic only honours 3 bits per nibble.
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-  uint32_t d;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-  return d;
-}
 
 struct ScanSmemLayout {
   uint32_t pol_bytes, tmp_bytes, total;
@@ -386,7 +364,14 @@ int launch_scan(mgpu_ivf *ivf, const ScanArgs &a) {
     return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "scan needs %u bytes of shared memory (max %zu): m*K or max_probes too large", L.total, ctx->smem_optin);
   if (a.m > 1024) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "scan supports at most 1024 PQ subspaces");
   switch (mode) {
-    case SCAN_PQ_FAST:
+    case SCAN_PQ_FAST: {
+      // headline path: warp-specialised, double-buffered LUT (scan_pq.cu); single-buffer kernel for m = 128
+      static const bool use_db = !(getenv("MGPU_SCAN_DB") && getenv("MGPU_SCAN_DB")[0] == '0');
+      if (use_db) {
+        int s = launch_scan_pq_db(ivf, a);
+        if (s != MGPU_ERR_UNSUPPORTED) return s;
+      }
+    }
       switch (a.ng) {
         case 1: return launch_scan_t<SCAN_PQ_FAST, 1>(ivf, a, L);
         case 2: return launch_scan_t<SCAN_PQ_FAST, 2>(ivf, a, L);

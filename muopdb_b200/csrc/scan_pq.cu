@@ -1,0 +1,343 @@
+// scan_pq.cu -- warp-specialised, double-buffered PQ posting-list scan (the headline kernel).
+//
+// Reference work replaced: BlockBasedIvf::scan_posting_list + search_with_centroids with a ProductQuantizer
+// (rs/index/src/ivf/block_based/index.rs:175-285; distance = pq/mod.rs:231-266), for a batch of queries.
+//
+// One persistent CTA per SM, two roles:
+//   * NPW producer warps build the NEXT query's fixed-point LUT (gather of m table rows of 1 KB, scale, transpose into the
+//     conflict-free [code][column] image) and its probe-list prefix into the idle half of a double buffer;
+//   * NCW consumer warps scan the CURRENT query's probed lists, one 32-row chunk per warp iteration, one row per lane:
+//     PRMT (code byte -> LUT byte offset) + LDS + IADD3 per lookup, zero bank conflicts by construction (lane l reads column
+//     l ^ t at step t; the HBM code layout is pre-permuted to match, see internal.cuh).
+// full[2]/empty[2] mbarriers hand the buffers over, so the latency-bound LUT build never stalls the shared-memory
+// pipe the scan is bound by.
+//
+// Shared memory (NG = m/32 groups, 32 KB of LUT per group): the two LUTs are interleaved at 128 B granularity inside
+// 64 KB blocks with a 256 B pitch per code, because PRMT can only place the code byte at a byte boundary (code << 8):
+//   slot s = parity * NG + g  ->  block s/2, half s%2;  address = block*64K + code*256 + half*128 + column*4.
+// NG = 3 (m = 96): 3 blocks = 192 KB for both LUTs.
+#include "internal.cuh"
+#include "scan_common.cuh"
+
+struct DbLayout {
+  uint32_t lut_bytes, off_tmp, off_pref, off_pcs, off_mkey, off_mpay, off_misc, total, maxp;
+};
+
+#define DB_TMP_PITCH 258
+#define DB_TMP_ROWS 16
+
+__host__ __device__ inline DbLayout db_layout(uint32_t ng, uint32_t ncw, uint32_t max_probes) {
+  DbLayout L;
+  L.maxp = max_probes;
+  L.lut_bytes = ((2 * ng + 1) / 2) * 65536u;
+  L.off_tmp = L.lut_bytes;
+  L.off_pref = L.off_tmp + DB_TMP_ROWS * DB_TMP_PITCH * 4u;
+  L.off_pcs = L.off_pref + 2u * (max_probes + 1) * 4u;
+  L.off_mkey = (L.off_pcs + 2u * max_probes * 4u + 15u) & ~15u;
+  L.off_mpay = L.off_mkey + ncw * 32u * 8u;
+  L.off_misc = L.off_mpay + ncw * 32u * 4u;
+  // misc: bars[4] (32 B) | qinfo[2][4] (32 B) | thr (4) pad | b2[32] | shf[32] | pq[4] | soff[128] | scode[128]
+  L.total = L.off_misc + 64u + 64u + 128u + 128u + 16u + 512u + 512u;
+  return L;
+}
+
+// Consumer side of k_scan_pq_db for one query; P = buffer parity (compile time => LUT offsets are LDS immediates).
+template <int NG, int NCW>
+struct DbConsumerCtx {
+  const ScanArgs &a; const DbLayout &L;
+  uint8_t *lut; uint32_t *pref, *pcs; uint64_t *mkey; uint32_t *mpay; uint64_t *bars; uint32_t *qinfo, *thr_p, *b2;
+  const uint32_t *xr; int lane, warp;
+
+  template <int P>
+  __device__ __forceinline__ bool query(uint32_t phase) {
+    constexpr int NCT = NCW * 32;
+    warp_mbar_wait(&bars[P], phase);  // buffer P is full
+    const uint32_t q = qinfo[P * 4 + 0];
+    if (q == 0xFFFFFFFFu) return false;
+    const uint32_t total = qinfo[P * 4 + 1];
+    const uint32_t *prefp = pref + P * (L.maxp + 1), *pcsp = pcs + P * L.maxp;
+    if (warp == 0) {
+      if (lane == 0) *thr_p = 0xFFFFFFFFu;
+      b2[lane] = 0xFFFFFFFFu;
+    }
+    named_bar_sync(1, NCT);
+
+    WarpTop32 top;
+    top.init();
+    bool first = true;
+    uint32_t pi = 0;
+    // software pipeline with NO extra registers: the 2 x 16 B of group g are re-loaded for the NEXT chunk right after group
+    // g of the current chunk has been scored, so every load has ~a full chunk of lookups (2 groups + top-k) to land.
+    uint4 u[NG * 2];
+    uint32_t pid_n = MGPU_EMPTY_SLOT, slot_n = 0;
+    uint32_t it = warp;
+    if (it < total) {
+      while (it >= prefp[pi + 1]) pi++;
+      const uint32_t chunk = pcsp[pi] + (it - prefp[pi]);
+      slot_n = chunk * 32 + lane;
+      const uint4 *base = (const uint4 *)a.codes + (size_t)chunk * (NG * 2 * 32) + lane;
+#pragma unroll
+      for (int i = 0; i < NG * 2; i++) u[i] = ldg_stream16(base + i * 32);
+      pid_n = a.slot_pid[slot_n];
+    }
+#pragma unroll 1
+    while (it < total) {
+      const uint32_t pid = pid_n, slot = slot_n;
+      it += NCW;
+      const bool more = it < total;
+      const uint4 *nbase = (const uint4 *)a.codes;
+      if (more) {
+        while (it >= prefp[pi + 1]) pi++;
+        const uint32_t chunk = pcsp[pi] + (it - prefp[pi]);
+        slot_n = chunk * 32 + lane;
+        nbase = (const uint4 *)a.codes + (size_t)chunk * (NG * 2 * 32) + lane;
+        pid_n = a.slot_pid[slot_n];
+      }
+      bool valid = pid != MGPU_EMPTY_SLOT;
+      if (a.invalid && valid) valid = !((a.invalid[pid >> 5] >> (pid & 31)) & 1u);  // index.rs:198-200
+
+      uint32_t acc0 = 0, acc1 = 0;
+#pragma unroll
+      for (int g = 0; g < NG; g++) {
+        const uint32_t slotg = P * NG + g;
+        const uint8_t *lut_g = lut + (slotg >> 1) * 65536u + (slotg & 1) * 128u;
+#pragma unroll
+        for (int wi = 0; wi < 8; wi++) {
+          const uint4 &uu = u[g * 2 + (wi >> 2)];
+          const uint32_t w = (wi & 3) == 0 ? uu.x : ((wi & 3) == 1 ? uu.y : ((wi & 3) == 2 ? uu.z : uu.w));
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int t = wi * 4 + k;
+            const uint32_t idx = prmt(w, xr[t >> 2], ((12 + (t & 3)) << 12) | ((12 + (t & 3)) << 8) | (k << 4) | (4 + (t & 3)));
+            const uint32_t v = *(const uint32_t *)(lut_g + idx);
+            if (t & 1) acc1 += v; else acc0 += v;
+          }
+        }
+        if (more) {
+          u[g * 2] = ldg_stream16(nbase + (g * 2) * 32);
+          u[g * 2 + 1] = ldg_stream16(nbase + (g * 2 + 1) * 32);
+        }
+      }
+      const uint32_t key = acc0 + acc1;
+
+      const uint32_t thr = *(volatile uint32_t *)thr_p;
+      const bool pass = valid && key <= thr;
+      if (__any_sync(0xffffffffu, pass)) {
+        uint32_t worst;
+        if (first) {
+          top.key = pass ? (((uint64_t)key << 32) | pid) : MGPU_EMPTY_KEY;
+          top.pay = pass ? slot : MGPU_EMPTY_SLOT;
+          top.sort();
+          worst = (uint32_t)(shfl64(top.key, 31) >> 32);
+          first = false;
+        } else {
+          worst = top.offer(pass, ((uint64_t)key << 32) | pid, slot);
+        }
+        // threshold: min(this warp's 32nd best, max over warps of their 2nd best) -- both bound the global 32nd best
+        uint32_t second = (uint32_t)(shfl64(top.key, 1) >> 32);
+        if (lane == 0) b2[warp] = second;
+        __syncwarp();
+        uint32_t v = lane < NCW ? *(volatile uint32_t *)&b2[lane] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+        v = min(v, worst);
+        if (lane == 0 && v < thr) atomicMin(thr_p, v);
+      }
+    }
+    // this warp no longer needs LUT[P] / pref[P]: hand the buffer back to the producers before the merge
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars[2 + P]);
+
+    // ---- merge the warp lists (shuffle bitonic merges, log2 rounds) -------------------------------------------------
+    mkey[warp * 32 + lane] = top.key;
+    mpay[warp * 32 + lane] = top.pay;
+    named_bar_sync(1, NCT);
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+      if (warp < half && warp + half < NCW) {
+        top.merge(mkey[(warp + half) * 32 + lane], mpay[(warp + half) * 32 + lane]);
+        mkey[warp * 32 + lane] = top.key;
+        mpay[warp * 32 + lane] = top.pay;
+      }
+      named_bar_sync(1, NCT);
+    }
+    if (warp == 0) {
+      a.cand_key[(size_t)q * MGPU_NCAND + lane] = top.key;
+      a.cand_slot[(size_t)q * MGPU_NCAND + lane] = top.pay;
+    }
+    return true;
+  }
+};
+
+template <int NG, int NCW, int NPW>
+__global__ void __launch_bounds__((NCW + NPW) * 32, 1) k_scan_pq_db(ScanArgs a, DbLayout L) {
+  constexpr int NCT = NCW * 32, NPT = NPW * 32;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *lut = smem;
+  float *tmp = (float *)(smem + L.off_tmp);
+  uint32_t *pref = (uint32_t *)(smem + L.off_pref);  // [2][maxp + 1]
+  uint32_t *pcs = (uint32_t *)(smem + L.off_pcs);    // [2][maxp]
+  uint64_t *mkey = (uint64_t *)(smem + L.off_mkey);
+  uint32_t *mpay = (uint32_t *)(smem + L.off_mpay);
+  uint64_t *bars = (uint64_t *)(smem + L.off_misc);        // full[0], full[1], empty[0], empty[1]
+  uint32_t *qinfo = (uint32_t *)(smem + L.off_misc + 32);  // [2][4]: query, total chunks, nprobe
+  uint32_t *thr_p = (uint32_t *)(smem + L.off_misc + 64);
+  uint32_t *b2 = (uint32_t *)(smem + L.off_misc + 128);
+  float *shf = (float *)(smem + L.off_misc + 256);
+  uint32_t *pq = (uint32_t *)(smem + L.off_misc + 384);
+  float *soff = (float *)(smem + L.off_misc + 400);
+  uint32_t *scode = (uint32_t *)(smem + L.off_misc + 400 + 512);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr uint32_t K = 256;
+  const uint32_t m = NG * 32;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], NPT); mbar_init(&bars[1], NPT);
+    mbar_init(&bars[2], NCW); mbar_init(&bars[3], NCW);
+  }
+  __syncthreads();
+
+  if (warp >= NCW) {
+    // =========================================== PRODUCER ===========================================================
+    const int ptid = tid - NCT, pwarp = warp - NCW;
+#pragma unroll 1
+    for (uint32_t n = 0;; n++) {
+      const uint32_t p = n & 1;
+      warp_mbar_wait(&bars[2 + p], ((n >> 1) & 1) ^ 1, 2000);  // buffer p is free
+      if (ptid == 0) pq[0] = atomicAdd(a.next_query, 1u);  // dynamic query scheduling over the persistent CTAs
+      named_bar_sync(2, NPT);
+      const uint32_t q = pq[0];
+      if (q >= a.B) {
+        if (ptid == 0) qinfo[p * 4] = 0xFFFFFFFFu;
+        mbar_arrive(&bars[p]);
+        break;
+      }
+      uint32_t *prefp = pref + p * (L.maxp + 1), *pcsp = pcs + p * L.maxp;
+      const uint32_t np = a.probe_counts ? min(a.probe_counts[q], a.max_probes) : a.max_probes;
+      // ---- probe-list prefix (chunk counts) --------------------------------------------------------------------------
+      if (pwarp == 0) {
+        uint32_t run = 0;
+        unsigned long long rows = 0;
+        for (uint32_t base = 0; base < np; base += 32) {
+          uint32_t i = base + lane, cnt = 0, cs = 0, len = 0;
+          if (i < np) {
+            uint32_t c = a.probes[(size_t)q * a.max_probes + i];
+            cs = a.chunk_start[c];
+            cnt = a.chunk_start[c + 1] - cs;
+            len = a.list_len[c];
+          }
+          uint32_t incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+          }
+          if (i < np) { prefp[i] = run + incl - cnt; pcsp[i] = cs; }
+          run += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) len += __shfl_xor_sync(0xffffffffu, len, o);
+          rows += len;
+        }
+        if (lane == 0) {
+          prefp[np] = run;
+          qinfo[p * 4 + 0] = q; qinfo[p * 4 + 1] = run; qinfo[p * 4 + 2] = np;
+          if (a.rows_scanned) atomicAdd(a.rows_scanned, rows);
+        }
+      }
+      // ---- fixed-point scale: the sum over subspaces of the LUT row ranges must fit 32 bits ---------------------------
+      float part = 0.0f;
+      for (uint32_t s = ptid; s < m; s += NPT) {
+        uint32_t code = a.qcodes[(size_t)q * m + s];
+        float mn = a.rowmin[(size_t)s * K + code], mx = a.rowmax[(size_t)s * K + code];
+        soff[s] = mn; scode[s] = code;
+        part += mx - mn;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (lane == 0) shf[pwarp] = part;
+      named_bar_sync(2, NPT);
+      float R = 0.0f;
+#pragma unroll
+      for (int w = 0; w < NPW; w++) R += shf[w];
+      const float scale = R > 0.0f ? 4.0e9f / R : 0.0f;
+      // ---- LUT image: 16 table rows at a time through a padded tile -----------------------------------------------------
+#pragma unroll 1
+      for (int g = 0; g < NG; g++) {
+        const uint32_t slot = p * NG + g;
+        uint8_t *dstg = lut + (slot >> 1) * 65536u + (slot & 1) * 128u;
+#pragma unroll 1
+        for (int hs = 0; hs < 2; hs++) {
+          for (int i = ptid; i < DB_TMP_ROWS * 64; i += NPT) {
+            const int r = i >> 6, j4 = i & 63;
+            const uint32_t s = g * 32 + hs * 16 + r;
+            const float4 v = *(const float4 *)(a.table + ((size_t)s * K + scode[s]) * K + j4 * 4);
+            float *d = tmp + r * DB_TMP_PITCH + j4 * 4;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+          }
+          named_bar_sync(2, NPT);
+          // transpose + convert: lane -> (column = lane/2, code parity = lane%2); pitch 258 keeps the reads conflict free
+          const int col = lane >> 1, jsub = lane & 1;
+          const float off = soff[g * 32 + hs * 16 + col];
+          for (int jj = pwarp; jj < 128; jj += NPW) {
+            const int j = 2 * jj + jsub;
+            const float v = tmp[col * DB_TMP_PITCH + j];
+            *(uint32_t *)(dstg + j * 256 + (hs * 16 + col) * 4) = __float2uint_rn(__fmul_rn(__fsub_rn(v, off), scale));
+          }
+          named_bar_sync(2, NPT);
+        }
+      }
+      mbar_arrive(&bars[p]);  // buffer p is full (release: every producer thread's writes precede its arrive)
+    }
+    return;
+  }
+
+  // ============================================= CONSUMER ===========================================================
+  // lane-dependent LUT column offsets: x_t = ((lane ^ t) * 4) <= 124, four per register.  PRMT builds (code << 8) | x_t in
+  // ONE instruction: byte0 = x_t, byte1 = code, bytes 2/3 = sign replication of x_t (msb 0) = 0.
+  uint32_t xr[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+    xr[j] = (uint32_t)((lane ^ (4 * j)) << 2) | ((uint32_t)((lane ^ (4 * j + 1)) << 2) << 8) |
+            ((uint32_t)((lane ^ (4 * j + 2)) << 2) << 16) | ((uint32_t)((lane ^ (4 * j + 3)) << 2) << 24);
+
+  DbConsumerCtx<NG, NCW> cc{a, L, lut, pref, pcs, mkey, mpay, bars, qinfo, thr_p, b2, xr, lane, warp};
+#pragma unroll 1
+  for (uint32_t n2 = 0;; n2++) {
+    // the two buffer parities are unrolled so that every LUT offset is an immediate of the LDS
+    if (!cc.template query<0>(n2 & 1)) break;
+    if (!cc.template query<1>(n2 & 1)) break;
+  }
+}
+
+template <int NG, int NCW, int NPW>
+static int launch_db_t(mgpu_ivf *ivf, const ScanArgs &a) {
+  mgpu_ctx *ctx = ivf->ctx;
+  DbLayout L = db_layout(NG, NCW, a.max_probes);
+  if (L.total > ctx->smem_optin) return MGPU_ERR_UNSUPPORTED;
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k_scan_pq_db<NG, NCW, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  unsigned grid = a.B < (uint32_t)ctx->sm_count ? a.B : (unsigned)ctx->sm_count;
+  CUDA_TRY(ctx, cudaMemsetAsync(a.next_query, 0, 4, ctx->stream));
+  LaunchScope ls(ctx, MGPU_K_SCAN);
+  k_scan_pq_db<NG, NCW, NPW><<<grid, (NCW + NPW) * 32, L.total, ctx->stream>>>(a, L);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return MGPU_OK;
+}
+
+// Returns MGPU_ERR_UNSUPPORTED when the double-buffered kernel does not apply (caller falls back to k_scan).
+int launch_scan_pq_db(mgpu_ivf *ivf, const ScanArgs &a) {
+  if (!ivf->pq_fast || a.m > 128) return MGPU_ERR_UNSUPPORTED;
+  static const int cfg = getenv("MGPU_DB_CFG") ? atoi(getenv("MGPU_DB_CFG")) : 0;
+  switch (a.ng) {
+    case 1: return launch_db_t<1, 16, 4>(ivf, a);
+    case 2: return launch_db_t<2, 16, 4>(ivf, a);
+    case 3:
+      // measured on B200 (profiles/): 16 consumer + 4 producer warps (96 registers, no spills) is the best split
+      switch (cfg) {
+        case 1: return launch_db_t<3, 20, 4>(ivf, a);
+        case 2: return launch_db_t<3, 12, 4>(ivf, a);
+        default: return launch_db_t<3, 16, 4>(ivf, a);
+      }
+    default: return MGPU_ERR_UNSUPPORTED;
+  }
+}
