@@ -304,6 +304,19 @@ int mgpu_ivf_create(mgpu_ctx *ctx, uint32_t dim, uint32_t nlist, const float *ce
   }
   ivf->h_list_len = list_len;
   int s = dev_alloc_copy(ctx, &ivf->d_centroids, centroids, (size_t)nlist * dim);
+  if (s == MGPU_OK && dim >= 16 && nlist % 4 == 0) {
+    // tensor-core coarse scoring operands: bf16 (hi, lo) split of the centroids + their squared norms
+    double mx = 0.0;
+    for (uint32_t c = 0; c < nlist; c++) {
+      double a = 0.0;
+      for (uint32_t d = 0; d < dim; d++) a += (double)centroids[(size_t)c * dim + d] * centroids[(size_t)c * dim + d];
+      mx = std::max(mx, a);
+    }
+    ivf->cn_max = (float)(mx * 1.000001);
+    s = dev_alloc_copy<uint16_t>(ctx, (uint16_t **)&ivf->d_csplit, nullptr, (size_t)nlist * coarse_tc_kp(dim));
+    if (s == MGPU_OK) s = dev_alloc_copy<float>(ctx, &ivf->d_cn, nullptr, nlist);
+    if (s == MGPU_OK) s = launch_split_bf16(ctx, ivf->d_centroids, nlist, dim, 1, ivf->d_csplit, ivf->d_cn);
+  }
   if (s == MGPU_OK) s = dev_alloc_copy(ctx, &ivf->d_chunk_start, chunk_start.data(), nlist + 1);
   if (s == MGPU_OK) s = dev_alloc_copy(ctx, &ivf->d_list_len, list_len.data(), nlist);
   if (s == MGPU_OK) s = dev_alloc_copy(ctx, &ivf->d_slot_pid, slot_pid.data(), slot_pid.size());
@@ -352,7 +365,7 @@ void mgpu_ivf_destroy(mgpu_ivf *ivf) {
   if (!ivf) return;
   cudaSetDevice(ivf->ctx->device);
   cudaStreamSynchronize(ivf->ctx->stream);
-  cudaFree(ivf->d_centroids); cudaFree(ivf->d_chunk_start); cudaFree(ivf->d_list_len); cudaFree(ivf->d_slot_pid);
+  cudaFree(ivf->d_centroids); cudaFree(ivf->d_csplit); cudaFree(ivf->d_cn); cudaFree(ivf->d_chunk_start); cudaFree(ivf->d_list_len); cudaFree(ivf->d_slot_pid);
   cudaFree(ivf->d_codes); cudaFree(ivf->d_rows); cudaFree(ivf->d_doc_ids); cudaFree(ivf->d_invalid); cudaFree(ivf->d_scan_rows);
   delete ivf;
 }
@@ -408,8 +421,22 @@ uint64_t mgpu_ivf_last_scan_rows(mgpu_ivf *ivf) {
 uint64_t mgpu_ivf_last_scan_bytes(mgpu_ivf *ivf) { return ivf ? mgpu_ivf_last_scan_rows(ivf) * ivf->bytes_per_row : 0; }
 
 // coarse scoring on device buffers: dQ (B x dim) -> d_ids (B x nprobe), d_dist (optional)
-static int ivf_coarse_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, uint32_t nprobe, float *dD, uint32_t *d_ids, float *d_dist) {
+static size_t ivf_coarse_extra_ws(mgpu_ivf *ivf, uint32_t B) {  // query split + norms + overflow counter
+  return ws_need(ws_need(ws_need(0, (size_t)B * coarse_tc_kp(ivf->dim) * 2), (size_t)B * 4), 16) + 256;
+}
+
+static int ivf_coarse_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, uint32_t nprobe, float *dD, uint32_t *d_ids, float *d_dist,
+                          void *extra_ws) {
   mgpu_ctx *ctx = ivf->ctx;
+  if (ivf->d_csplit && extra_ws && coarse_tc_applicable(ctx, ivf->dim, ivf->nlist, nprobe)) {
+    // tensor-core pass + exact re-score of a provably sufficient candidate set: identical probes to the exact path
+    WsAlloc w(extra_ws, ivf_coarse_extra_ws(ivf, B));
+    void *qsplit = w.get<uint16_t>((size_t)B * coarse_tc_kp(ivf->dim));
+    float *qn = w.get<float>(B);
+    uint32_t *ovf = w.get<uint32_t>(4);
+    return launch_coarse_tc(ctx, dQ, B, ivf->d_centroids, ivf->d_csplit, ivf->d_cn, ivf->cn_max, ivf->nlist, ivf->dim, nprobe, qsplit,
+                            qn, dD, ovf, d_ids, d_dist);
+  }
   // always the L2 calculator with sqrt (index.rs:155), whatever the quantizer's metric
   MGPU_TRY(launch_distance_matrix(ctx, dQ, B, ivf->d_centroids, ivf->nlist, ivf->dim, MGPU_L2, 1, dD, MGPU_K_COARSE));
   return launch_select_smallest(ctx, dD, B, ivf->nlist, nprobe, d_ids, d_dist);
@@ -423,18 +450,19 @@ int mgpu_ivf_coarse(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t nprobe, 
   cudaSetDevice(ctx->device);
   if (B == 0) return MGPU_OK;
   size_t bQ = (size_t)B * ivf->dim * 4, bD = (size_t)B * ivf->nlist * 4, bI = (size_t)B * nprobe * 4;
-  size_t need = ws_need(ws_need(ws_need(ws_need(0, bQ), bD), bI), bI);
+  size_t need = ws_need(ws_need(ws_need(ws_need(ws_need(0, bQ), bD), bI), bI), ivf_coarse_extra_ws(ivf, B));
   MGPU_TRY(mgpu_ws_reserve(ctx, need));
   WsAlloc w(ctx->ws, ctx->ws_bytes);
   float *sQ = w.get<float>((size_t)B * ivf->dim);
   float *dD = w.get<float>((size_t)B * ivf->nlist);
   uint32_t *sI = w.get<uint32_t>((size_t)B * nprobe);
   float *sV = w.get<float>((size_t)B * nprobe);
+  uint8_t *xws = w.get<uint8_t>(ivf_coarse_extra_ws(ivf, B));
   const void *dQ;
   MGPU_TRY(stage_in(ctx, Q, bQ, mem, sQ, &dQ));
   uint32_t *dI = mem == MGPU_DEVICE ? out_ids : sI;
   float *dV = mem == MGPU_DEVICE ? out_dist : (out_dist ? sV : nullptr);
-  MGPU_TRY(ivf_coarse_dev(ivf, (const float *)dQ, B, nprobe, dD, dI, dV));
+  MGPU_TRY(ivf_coarse_dev(ivf, (const float *)dQ, B, nprobe, dD, dI, dV, xws));
   MGPU_TRY(stage_out(ctx, out_ids, dI, bI, mem));
   MGPU_TRY(stage_out(ctx, out_dist, dV, bI, mem));
   if (mem == MGPU_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -511,6 +539,7 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
   need = ws_need(need, (size_t)B * k * 4);                    // out pids
   need = ws_need(need, (size_t)B * k * 4);                    // out scores
   need = ws_need(need, (size_t)B * 4);                        // out counts
+  need = ws_need(need, do_coarse ? ivf_coarse_extra_ws(ivf, B) : 0);
   MGPU_TRY(mgpu_ws_reserve(ctx, need));
   WsAlloc w(ctx->ws, ctx->ws_bytes);
   float *sQ = w.get<float>((size_t)B * ivf->dim);
@@ -524,12 +553,13 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
   uint32_t *sPids = w.get<uint32_t>((size_t)B * k);
   float *sScores = w.get<float>((size_t)B * k);
   uint32_t *sCounts = w.get<uint32_t>(B);
+  uint8_t *xws = w.get<uint8_t>(do_coarse ? ivf_coarse_extra_ws(ivf, B) : 0);
 
   const void *dQ;
   MGPU_TRY(stage_in(ctx, Q, bQ, mem, sQ, &dQ));
   const uint32_t *dP, *dPC = nullptr;
   if (do_coarse) {
-    MGPU_TRY(ivf_coarse_dev(ivf, (const float *)dQ, B, nprobe_coarse, dD, sP, nullptr));
+    MGPU_TRY(ivf_coarse_dev(ivf, (const float *)dQ, B, nprobe_coarse, dD, sP, nullptr, xws));
     dP = sP;
   } else {
     const void *t;

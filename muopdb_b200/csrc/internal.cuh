@@ -29,6 +29,9 @@ struct mgpu_ivf {
   int quant, metric;
   mgpu_pq *pq = nullptr;
   float *d_centroids = nullptr;
+  void *d_csplit = nullptr;           // centroids as [hi | lo | hi] bf16 rows (tensor-core coarse scoring), may be null
+  float *d_cn = nullptr;              // |c|^2 per centroid
+  float cn_max = 0.f;
   uint32_t *d_chunk_start = nullptr;  // nlist+1, in chunks
   uint32_t *d_list_len = nullptr;     // nlist
   uint64_t total_chunks = 0;
@@ -118,6 +121,14 @@ int launch_assign_filter(mgpu_ctx *ctx, const uint32_t *sel_ids, const float *se
                          float threshold, uint32_t *out_cids, uint32_t *out_counts);
 int launch_merge_topk(mgpu_ctx *ctx, const mgpu_u128 *docs, const float *scores, const uint32_t *counts, uint32_t S,
                       uint32_t B, uint32_t k, mgpu_u128 *out_docs, float *out_scores, uint32_t *out_counts);
+
+// tensor-core coarse scoring (coarse_tc.cu)
+uint32_t coarse_tc_kp(uint32_t dim);
+bool coarse_tc_applicable(mgpu_ctx *ctx, uint32_t dim, uint32_t C, uint32_t nprobe);
+int launch_split_bf16(mgpu_ctx *ctx, const float *dX, uint64_t n, uint32_t dim, int is_centroid, void *d_out, float *d_norms);
+int launch_coarse_tc(mgpu_ctx *ctx, const float *dQ, uint32_t B, const float *d_centroids, const void *d_csplit, const float *d_cn,
+                     float cn_max, uint32_t C, uint32_t dim, uint32_t nprobe, void *d_qsplit, float *d_qn, float *d_Dt,
+                     uint32_t *d_overflow, uint32_t *out_ids, float *out_dist);
 
 struct HnswSearchArgs {
   const float *Q; uint32_t B, k, ef;

@@ -378,3 +378,26 @@ def test_spann_parity(M, pq):
             n = max(int(oc[b]), 0)
             assert np.array_equal(r.doc_ids[b, :n], od[b, :n]), (ne, ratio, b)
             assert _same_f32(r.scores[b, :n], os_[b, :n])
+
+
+# ---- tensor-core coarse scoring --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,nlist,nprobe", [(64, 1024, 16), (128, 2048, 64), (768, 1280, 32), (80, 1028, 7)])
+def test_coarse_tensor_core_path_matches_exact(M, dim, nlist, nprobe):
+    """find_nearest_centroids (index.rs:147-163) through the tcgen05 GEMM + margin + exact re-score: the probe lists and
+    distances must be IDENTICAL to the oracle's (the tensor-core pass only proposes candidates).  Includes duplicated
+    centroids (exact ties -> index order) and near-ties far below bf16/tf32 resolution."""
+    rng = np.random.default_rng(dim + nlist)
+    cents = synth.clustered(nlist, dim, n_blobs=9, sigma=0.3, seed=dim).astype(np.float32)
+    cents[1::97] = cents[0::97][: len(cents[1::97])]                    # exact duplicates
+    cents[2::101] = cents[3::101][: len(cents[2::101])] * np.float32(1.0 + 1e-6)  # near-ties ~1e-6 apart
+    X = cents[rng.integers(0, nlist, 3000)] + 0.05 * rng.standard_normal((3000, dim)).astype(np.float32)
+    offsets, ids = O.build_posting_lists(X, cents)
+    givf = M.BlockBasedIvf(cents, offsets, ids, X, M.NoQuantizer(dim))
+    oivf = O.Ivf(cents, offsets, ids, X)
+    Q = np.vstack([X[:100] + 0.01, cents[:28], rng.random((100, dim), dtype=np.float32) * 3 - 1]).astype(np.float32)
+    gp, gd = givf.find_nearest_centroids_batch(Q, nprobe, with_distances=True)
+    for b in range(len(Q)):
+        op, od = oivf.find_nearest_centroids(Q[b], nprobe, with_dist=True)
+        assert np.array_equal(op, gp[b]), (b, op[:8], gp[b][:8])
+        assert _same_f32(od, gd[b])
+    assert givf.ctx.profile_get(0)[1] > 0
