@@ -191,7 +191,7 @@ k_coarse_gemm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 
 // ---- selection with a provable margin + exact re-score -------------------------------------------------------------------
 // One CTA per query.  smem: keys[C] (ordered keys of D~), hist[256], cand[<= C] indices, exact key64 list.
-#define SEL_THREADS 256
+#define SEL_THREADS 512
 __global__ void __launch_bounds__(SEL_THREADS)
 k_coarse_select(const float *__restrict__ Dt, const float *__restrict__ Q, const float *__restrict__ centroids,
                 const float *__restrict__ qn, float cn_max, uint32_t C, uint32_t dim, uint32_t nprobe, uint32_t cand_cap,
@@ -210,23 +210,46 @@ k_coarse_select(const float *__restrict__ Dt, const float *__restrict__ Q, const
   for (uint32_t d = tid; d < dim; d += SEL_THREADS) sq[d] = Q[(size_t)q * dim + d];
   if (tid == 0) { misc[0] = 0; misc[1] = nprobe - 1; misc[2] = 0; }
   __syncthreads();
-  // radix select (MSB first, 8 bits per pass) of the key with rank nprobe-1
+  // radix select (MSB first, 8 bits per pass) of the key with rank nprobe-1.  Keys cluster in a few bins, so increments are
+  // aggregated per warp with match_any (one shared-memory atomic per distinct bin per warp instruction) and the bin scan is
+  // a warp-parallel prefix sum.
   for (int pass = 0; pass < 4; pass++) {
     const int shift = 24 - 8 * pass;
     for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
     __syncthreads();
     const uint32_t prefix = misc[0];
     const uint32_t mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
-    for (uint32_t i = tid; i < C; i += SEL_THREADS) {
-      uint32_t k = keys[i];
-      if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+    for (uint32_t i0 = 0; i0 < C; i0 += SEL_THREADS) {
+      const uint32_t i = i0 + tid;
+      uint32_t bin = 0xFFFFu;  // "not a candidate of this pass"
+      if (i < C) {
+        uint32_t k = keys[i];
+        if ((k & mask) == prefix) bin = (k >> shift) & 255u;
+      }
+      const unsigned grp = __match_any_sync(0xffffffffu, bin);
+      if (bin != 0xFFFFu && lane == __ffs(grp) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(grp));
     }
     __syncthreads();
-    if (tid == 0) {
-      uint32_t rank = misc[1], b = 0;
-      for (; b < 256; b++) { if (rank < hist[b]) break; rank -= hist[b]; }
-      misc[0] = prefix | (b << shift);
-      misc[1] = rank;
+    if (warp == 0) {
+      uint32_t loc[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) { loc[j] = hist[lane * 8 + j]; sum += loc[j]; }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const uint32_t rank = misc[1];
+      const uint32_t excl = incl - sum;
+      const bool mine = rank >= excl && rank < incl;  // exactly one lane
+      if (mine) {
+        uint32_t r = rank - excl, b = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { if (r >= loc[j] && b == (uint32_t)j) { r -= loc[j]; b = j + 1; } }
+        misc[0] = prefix | ((uint32_t)(lane * 8 + b) << shift);
+        misc[1] = r;
+      }
     }
     __syncthreads();
   }
@@ -259,8 +282,8 @@ k_coarse_select(const float *__restrict__ Dt, const float *__restrict__ Q, const
     if (n / 16 > 0) {
       const int chunks = n / 16;
       float acc = 0.0f;
-#pragma unroll 8
-      for (int c = 0; c < chunks; c++) {
+#pragma unroll 16
+      for (int c = 0; c < chunks; c++) {  // 16 independent 64-byte row segments in flight per half-warp
         float d = __fsub_rn(sq[c * 16 + h], __ldg(crow + c * 16 + h));
         acc = __fadd_rn(acc, __fmul_rn(d, d));
       }

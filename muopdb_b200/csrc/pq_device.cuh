@@ -14,6 +14,26 @@ __device__ __forceinline__ float pq_distance_streaming(const float *__restrict__
   for (int i = 0; i < 8; i++) s8[i] = 0.0f;
 #pragma unroll
   for (int i = 0; i < 4; i++) s4[i] = 0.0f;
+  if (dsub == 8) {
+    // common case (reference default pq_subvector_dimension = 8): one 8-lane chunk per subspace, two 16-byte loads per
+    // centroid; identical arithmetic to the general cascade below
+    for (uint32_t s = 0; s < m; s++) {
+      const float4 *av = (const float4 *)(cb + ((size_t)s * K + ca(s)) * 8);
+      const float4 *bv = (const float4 *)(cb + ((size_t)s * K + cbk(s)) * 8);
+      const float4 a0 = __ldg(av), a1 = __ldg(av + 1), b0 = __ldg(bv), b1 = __ldg(bv + 1);
+      const float x[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float y[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int l = 0; l < 8; l++) {
+        if (METRIC == MGPU_L2) { float d = __fsub_rn(x[l], y[l]); s8[l] = __fadd_rn(s8[l], __fmul_rn(d, d)); }
+        else s8[l] = __fadd_rn(s8[l], __fmul_rn(x[l], y[l]));
+      }
+    }
+    float r8 = __fadd_rn(ordered_reduce(s16, 16), ordered_reduce(s8, 8));
+    r8 = __fadd_rn(r8, ordered_reduce(s4, 4));
+    r8 = __fadd_rn(r8, s1);
+    return METRIC == MGPU_L2 ? r8 : -r8;
+  }
   for (uint32_t s = 0; s < m; s++) {
     const float *av = cb + ((size_t)s * K + ca(s)) * dsub;
     const float *bv = cb + ((size_t)s * K + cbk(s)) * dsub;
