@@ -224,6 +224,7 @@ def cpu_leg(O, oivf, Qh, k, nprobe, seconds, nthreads, per_call):
     """Times the oracle on successive slices of Qh until `seconds` of CPU wall time are used."""
     done, t_used, i = 0, 0.0, 0
     res = []
+    oivf.search_batch(Qh[:min(per_call, Qh.shape[0])], k, nprobe, nthreads)  # warm-up (page faults, thread pool)
     while t_used < seconds and i < Qh.shape[0]:
         q = Qh[i:i + per_call]
         t0 = time.perf_counter()

@@ -472,7 +472,7 @@ int mgpu_ivf_coarse(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t nprobe, 
 // scan + finalize on device buffers
 static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32_t *d_probes, uint32_t max_probes,
                         const uint32_t *d_counts, uint32_t k, uint8_t *d_qcodes, uint64_t *d_ckey, uint32_t *d_cslot,
-                        uint32_t *d_out_pids, mgpu_u128 *d_out_docs, float *d_out_scores, uint32_t *d_out_counts) {
+                        uint32_t *d_order, uint32_t *d_out_pids, mgpu_u128 *d_out_docs, float *d_out_scores, uint32_t *d_out_counts) {
   mgpu_ctx *ctx = ivf->ctx;
   CUDA_TRY(ctx, cudaMemsetAsync(ivf->d_scan_rows, 0, 8, ctx->stream));
   ScanArgs a;
@@ -489,6 +489,12 @@ static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32
     // the query is quantized with the same codebook (index.rs:193) -- once per query here, not once per list
     MGPU_TRY(launch_pq_quantize(pq, dQ, B, d_qcodes));
     a.qcodes = d_qcodes;
+  }
+  // longest-first query schedule: the single-CTA planner costs more than the tail it removes at B = 1024, so it is opt-in
+  static const bool use_plan = getenv("MGPU_PLAN") && getenv("MGPU_PLAN")[0] == '1';
+  if (use_plan && d_order && B <= 4096 && B > (uint32_t)ctx->sm_count) {
+    MGPU_TRY(launch_plan_queries(ivf, d_probes, max_probes, d_counts, B, d_order));
+    a.order = d_order;
   }
   MGPU_TRY(launch_scan(ivf, a));
   FinalizeArgs f;
@@ -535,6 +541,7 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
   need = ws_need(need, (size_t)B * m);                        // query codes
   need = ws_need(need, (size_t)B * MGPU_NCAND * 8);           // cand keys
   need = ws_need(need, (size_t)B * MGPU_NCAND * 4);           // cand slots
+  need = ws_need(need, (size_t)B * 4);                        // query schedule
   need = ws_need(need, (size_t)B * k * 16);                   // out docs
   need = ws_need(need, (size_t)B * k * 4);                    // out pids
   need = ws_need(need, (size_t)B * k * 4);                    // out scores
@@ -549,6 +556,7 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
   uint8_t *dQC = w.get<uint8_t>((size_t)B * m);
   uint64_t *dCK = w.get<uint64_t>((size_t)B * MGPU_NCAND);
   uint32_t *dCS = w.get<uint32_t>((size_t)B * MGPU_NCAND);
+  uint32_t *dOrd = w.get<uint32_t>(B);
   mgpu_u128 *sDocs = w.get<mgpu_u128>((size_t)B * k);
   uint32_t *sPids = w.get<uint32_t>((size_t)B * k);
   float *sScores = w.get<float>((size_t)B * k);
@@ -571,7 +579,7 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
   mgpu_u128 *oD = out_docs ? (mem == MGPU_DEVICE ? out_docs : sDocs) : nullptr;
   float *oS = mem == MGPU_DEVICE ? out_scores : sScores;
   uint32_t *oC = mem == MGPU_DEVICE ? out_counts : sCounts;
-  MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, dP, max_probes, dPC, k, dQC, dCK, dCS, oP, oD, oS, oC));
+  MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, dP, max_probes, dPC, k, dQC, dCK, dCS, dOrd, oP, oD, oS, oC));
   if (mem == MGPU_HOST) {
     MGPU_TRY(stage_out(ctx, out_pids, oP, (size_t)B * k * 4, mem));
     MGPU_TRY(stage_out(ctx, out_docs, oD, (size_t)B * k * 16, mem));
@@ -972,7 +980,7 @@ int mgpu_spann_search(mgpu_spann *sp, const float *Q, uint32_t B, uint32_t top_k
   float *oS = mem == MGPU_DEVICE ? out_scores : sS;
   uint32_t *oC = mem == MGPU_DEVICE ? out_counts : sC;
   if (top_k == 0) CUDA_TRY(ctx, cudaMemsetAsync(oC, 0, (size_t)B * 4, ctx->stream));
-  else MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, pr, ne, pc, top_k, dQC, dCK, dCS, nullptr, oD, oS, oC));
+  else MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, pr, ne, pc, top_k, dQC, dCK, dCS, nullptr, nullptr, oD, oS, oC));
   {
     LaunchScope ls(ctx, MGPU_K_OTHER);
     k_spann_mark_none<<<(B + 127) / 128, 128, 0, ctx->stream>>>(cC, B, oC);

@@ -91,6 +91,7 @@ struct ScanArgs {
   uint64_t *cand_key; uint32_t *cand_slot;  // B x 32
   unsigned long long *rows_scanned;
   unsigned int *next_query;  // zeroed before every launch: dynamic query scheduler
+  const uint32_t *order;     // optional: queries in descending-work order (k_plan_queries)
   int metric;
 };
 
@@ -99,6 +100,8 @@ int launch_pq_quantize(mgpu_pq *pq, const float *dX, uint64_t n, uint8_t *dcodes
 int launch_pq_distance_pairs(mgpu_pq *pq, const uint8_t *da, const uint8_t *db, uint64_t n, float *dout);
 int launch_build_layout(mgpu_ivf *ivf, const void *d_rows_by_pid);
 int launch_scan(mgpu_ivf *ivf, const ScanArgs &a);
+int launch_plan_queries(mgpu_ivf *ivf, const uint32_t *d_probes, uint32_t max_probes, const uint32_t *d_counts, uint32_t B,
+                        uint32_t *d_order);
 int launch_scan_pq_db(mgpu_ivf *ivf, const ScanArgs &a);  // MGPU_ERR_UNSUPPORTED => use launch_scan's generic kernels
 size_t scan_max_probes_supported(mgpu_ivf *ivf);
 

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(NT, 1) k_scan(ScanArgs a, ScanSmemLayout L) {
 
   for (;;) {
     // dynamic query scheduling: one atomic per query keeps the 148 persistent CTAs balanced on ragged probe lists
-    if (tid == 0) sh[2] = atomicAdd(a.next_query, 1u);
+    if (tid == 0) { uint32_t t = atomicAdd(a.next_query, 1u); sh[2] = t < a.B ? (a.order ? a.order[t] : t) : 0xFFFFFFFFu; }
     __syncthreads();
     const uint32_t q = sh[2];
     if (q >= a.B) break;
@@ -328,6 +328,49 @@ __global__ void __launch_bounds__(NT, 1) k_scan(ScanArgs a, ScanSmemLayout L) {
     }
     __syncthreads();
   }
+}
+
+// Longest-processing-time-first order for the persistent CTAs' dynamic scheduler: work(q) = chunks of q's probed lists.
+// One CTA, bitonic sort of (work, query) in shared memory; B <= 4096 (larger batches keep the natural order).
+__global__ void __launch_bounds__(1024) k_plan_queries(const uint32_t *__restrict__ probes, uint32_t max_probes,
+                                                       const uint32_t *__restrict__ probe_counts,
+                                                       const uint32_t *__restrict__ chunk_start, uint32_t B, uint32_t P2,
+                                                       uint32_t *__restrict__ order) {
+  extern __shared__ uint64_t pk[];
+  for (uint32_t q = threadIdx.x; q < P2; q += blockDim.x) {
+    uint64_t key = 0;  // padding sorts last (descending order)
+    if (q < B) {
+      uint32_t np = probe_counts ? min(probe_counts[q], max_probes) : max_probes, w = 0;
+      for (uint32_t i = 0; i < np; i++) { uint32_t c = probes[(size_t)q * max_probes + i]; w += chunk_start[c + 1] - chunk_start[c]; }
+      key = ((uint64_t)(w + 1) << 32) | (0xFFFFFFFFu - q);
+    }
+    pk[q] = key;
+  }
+  __syncthreads();
+  for (uint32_t k = 2; k <= P2; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < P2; i += blockDim.x) {
+        uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          uint64_t x = pk[i], y = pk[ixj];
+          bool up = (i & k) == 0;
+          if ((x < y) == up) { pk[i] = y; pk[ixj] = x; }  // descending
+        }
+      }
+      __syncthreads();
+    }
+  for (uint32_t q = threadIdx.x; q < B; q += blockDim.x) order[q] = 0xFFFFFFFFu - (uint32_t)pk[q];
+}
+
+int launch_plan_queries(mgpu_ivf *ivf, const uint32_t *d_probes, uint32_t max_probes, const uint32_t *d_counts, uint32_t B,
+                        uint32_t *d_order) {
+  mgpu_ctx *ctx = ivf->ctx;
+  uint32_t P2 = 1;
+  while (P2 < B) P2 <<= 1;
+  LaunchScope ls(ctx, MGPU_K_OTHER);
+  k_plan_queries<<<1, 1024, (size_t)P2 * 8, ctx->stream>>>(d_probes, max_probes, d_counts, ivf->d_chunk_start, B, P2, d_order);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return MGPU_OK;
 }
 
 static int scan_mode(const mgpu_ivf *ivf) {

@@ -66,6 +66,7 @@ struct DbConsumerCtx {
     top.init();
     bool first = true;
     uint32_t pi = 0;
+    uint32_t hi_it = 0, base_off = 0;  // current probed list covers chunk iterations [.., hi_it); chunk = base_off + it
     // software pipeline with NO extra registers: the 2 x 16 B of group g are re-loaded for the NEXT chunk right after group
     // g of the current chunk has been scored, so every load has ~a full chunk of lookups (2 groups + top-k) to land.
     uint4 u[NG * 2];
@@ -73,7 +74,8 @@ struct DbConsumerCtx {
     uint32_t it = warp;
     if (it < total) {
       while (it >= prefp[pi + 1]) pi++;
-      const uint32_t chunk = pcsp[pi] + (it - prefp[pi]);
+      hi_it = prefp[pi + 1]; base_off = pcsp[pi] - prefp[pi];
+      const uint32_t chunk = base_off + it;
       slot_n = chunk * 32 + lane;
       const uint4 *base = (const uint4 *)a.codes + (size_t)chunk * (NG * 2 * 32) + lane;
 #pragma unroll
@@ -87,8 +89,11 @@ struct DbConsumerCtx {
       const bool more = it < total;
       const uint4 *nbase = (const uint4 *)a.codes;
       if (more) {
-        while (it >= prefp[pi + 1]) pi++;
-        const uint32_t chunk = pcsp[pi] + (it - prefp[pi]);
+        if (it >= hi_it) {  // crossed into another probed list: refresh the cached bounds (rare)
+          while (it >= prefp[pi + 1]) pi++;
+          hi_it = prefp[pi + 1]; base_off = pcsp[pi] - prefp[pi];
+        }
+        const uint32_t chunk = base_off + it;
         slot_n = chunk * 32 + lane;
         nbase = (const uint4 *)a.codes + (size_t)chunk * (NG * 2 * 32) + lane;
         pid_n = a.slot_pid[slot_n];
@@ -205,7 +210,10 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) k_scan_pq_db(ScanArgs a, 
     for (uint32_t n = 0;; n++) {
       const uint32_t p = n & 1;
       warp_mbar_wait(&bars[2 + p], ((n >> 1) & 1) ^ 1, 2000);  // buffer p is free
-      if (ptid == 0) pq[0] = atomicAdd(a.next_query, 1u);  // dynamic query scheduling over the persistent CTAs
+      if (ptid == 0) {  // dynamic query scheduling over the persistent CTAs, longest queries first (a.order)
+        uint32_t t = atomicAdd(a.next_query, 1u);
+        pq[0] = t < a.B ? (a.order ? a.order[t] : t) : 0xFFFFFFFFu;
+      }
       named_bar_sync(2, NPT);
       const uint32_t q = pq[0];
       if (q >= a.B) {
