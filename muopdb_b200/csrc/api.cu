@@ -490,10 +490,10 @@ static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32
     MGPU_TRY(launch_pq_quantize(pq, dQ, B, d_qcodes));
     a.qcodes = d_qcodes;
   }
-  // longest-first query schedule: the single-CTA planner costs more than the tail it removes at B = 1024, so it is opt-in
-  static const bool use_plan = getenv("MGPU_PLAN") && getenv("MGPU_PLAN")[0] == '1';
-  if (use_plan && d_order && B <= 4096 && B > (uint32_t)ctx->sm_count) {
-    MGPU_TRY(launch_plan_queries(ivf, d_probes, max_probes, d_counts, B, d_order));
+  // longest-first query schedule for the persistent scan CTAs (MGPU_PLAN=0 disables it)
+  static const bool use_plan = !(getenv("MGPU_PLAN") && getenv("MGPU_PLAN")[0] == '0');
+  if (use_plan && d_order && B > 2 * (uint32_t)ctx->sm_count) {
+    MGPU_TRY(launch_plan_queries(ivf, d_probes, max_probes, d_counts, B, d_order, d_order + B));
     a.order = d_order;
   }
   MGPU_TRY(launch_scan(ivf, a));
@@ -541,7 +541,7 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
   need = ws_need(need, (size_t)B * m);                        // query codes
   need = ws_need(need, (size_t)B * MGPU_NCAND * 8);           // cand keys
   need = ws_need(need, (size_t)B * MGPU_NCAND * 4);           // cand slots
-  need = ws_need(need, (size_t)B * 4);                        // query schedule
+  need = ws_need(need, (size_t)B * 8);                        // query schedule + work
   need = ws_need(need, (size_t)B * k * 16);                   // out docs
   need = ws_need(need, (size_t)B * k * 4);                    // out pids
   need = ws_need(need, (size_t)B * k * 4);                    // out scores
@@ -556,7 +556,7 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
   uint8_t *dQC = w.get<uint8_t>((size_t)B * m);
   uint64_t *dCK = w.get<uint64_t>((size_t)B * MGPU_NCAND);
   uint32_t *dCS = w.get<uint32_t>((size_t)B * MGPU_NCAND);
-  uint32_t *dOrd = w.get<uint32_t>(B);
+  uint32_t *dOrd = w.get<uint32_t>((size_t)B * 2);
   mgpu_u128 *sDocs = w.get<mgpu_u128>((size_t)B * k);
   uint32_t *sPids = w.get<uint32_t>((size_t)B * k);
   float *sScores = w.get<float>((size_t)B * k);

@@ -101,7 +101,7 @@ int launch_pq_distance_pairs(mgpu_pq *pq, const uint8_t *da, const uint8_t *db, 
 int launch_build_layout(mgpu_ivf *ivf, const void *d_rows_by_pid);
 int launch_scan(mgpu_ivf *ivf, const ScanArgs &a);
 int launch_plan_queries(mgpu_ivf *ivf, const uint32_t *d_probes, uint32_t max_probes, const uint32_t *d_counts, uint32_t B,
-                        uint32_t *d_order);
+                        uint32_t *d_order, uint32_t *d_work);
 int launch_scan_pq_db(mgpu_ivf *ivf, const ScanArgs &a);  // MGPU_ERR_UNSUPPORTED => use launch_scan's generic kernels
 size_t scan_max_probes_supported(mgpu_ivf *ivf);
 

@@ -330,46 +330,63 @@ __global__ void __launch_bounds__(NT, 1) k_scan(ScanArgs a, ScanSmemLayout L) {
   }
 }
 
-// Longest-processing-time-first order for the persistent CTAs' dynamic scheduler: work(q) = chunks of q's probed lists.
-// One CTA, bitonic sort of (work, query) in shared memory; B <= 4096 (larger batches keep the natural order).
-__global__ void __launch_bounds__(1024) k_plan_queries(const uint32_t *__restrict__ probes, uint32_t max_probes,
-                                                       const uint32_t *__restrict__ probe_counts,
-                                                       const uint32_t *__restrict__ chunk_start, uint32_t B, uint32_t P2,
-                                                       uint32_t *__restrict__ order) {
-  extern __shared__ uint64_t pk[];
-  for (uint32_t q = threadIdx.x; q < P2; q += blockDim.x) {
-    uint64_t key = 0;  // padding sorts last (descending order)
-    if (q < B) {
-      uint32_t np = probe_counts ? min(probe_counts[q], max_probes) : max_probes, w = 0;
-      for (uint32_t i = 0; i < np; i++) { uint32_t c = probes[(size_t)q * max_probes + i]; w += chunk_start[c + 1] - chunk_start[c]; }
-      key = ((uint64_t)(w + 1) << 32) | (0xFFFFFFFFu - q);
-    }
-    pk[q] = key;
+// Longest-processing-time-first order for the persistent CTAs' dynamic scheduler (removes the ragged tail of the last
+// wave: ~3 % of the scan).  work(q) = chunks of q's probed lists (one warp per query), then a 64-bucket counting sort
+// by descending work in one CTA -- an exact sort is not needed, only "big queries first".
+__global__ void __launch_bounds__(256) k_query_work(const uint32_t *__restrict__ probes, uint32_t max_probes,
+                                                    const uint32_t *__restrict__ probe_counts,
+                                                    const uint32_t *__restrict__ chunk_start, uint32_t B,
+                                                    uint32_t *__restrict__ work) {
+  const uint32_t q = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (q >= B) return;
+  const uint32_t np = probe_counts ? min(probe_counts[q], max_probes) : max_probes;
+  uint32_t w = 0;
+  for (uint32_t i = threadIdx.x & 31; i < np; i += 32) {
+    uint32_t c = probes[(size_t)q * max_probes + i];
+    w += chunk_start[c + 1] - chunk_start[c];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+  if ((threadIdx.x & 31) == 0) work[q] = w;
+}
+
+__global__ void __launch_bounds__(1024) k_plan_bucket(const uint32_t *__restrict__ work, uint32_t B, uint32_t *__restrict__ order) {
+  __shared__ uint32_t hist[64], base[64], wmax_s;
+  if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) wmax_s = 0;
+  __syncthreads();
+  uint32_t mx = 0;
+  for (uint32_t q = threadIdx.x; q < B; q += blockDim.x) mx = max(mx, work[q]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&wmax_s, mx);
+  __syncthreads();
+  const uint64_t wmax = (uint64_t)wmax_s + 1;
+  // pass 1: histogram; pass 2 (after the prefix): scatter -- positions inside a bucket come from a second atomic counter
+  for (uint32_t q = threadIdx.x; q < B; q += blockDim.x) atomicAdd(&hist[63 - (uint32_t)(((uint64_t)work[q] * 64) / wmax)], 1u);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t a0 = hist[2 * threadIdx.x], a1 = hist[2 * threadIdx.x + 1], sum = a0 + a1, incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += v; }
+    base[2 * threadIdx.x] = incl - sum;
+    base[2 * threadIdx.x + 1] = incl - sum + a0;
   }
   __syncthreads();
-  for (uint32_t k = 2; k <= P2; k <<= 1)
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t i = threadIdx.x; i < P2; i += blockDim.x) {
-        uint32_t ixj = i ^ j;
-        if (ixj > i) {
-          uint64_t x = pk[i], y = pk[ixj];
-          bool up = (i & k) == 0;
-          if ((x < y) == up) { pk[i] = y; pk[ixj] = x; }  // descending
-        }
-      }
-      __syncthreads();
-    }
-  for (uint32_t q = threadIdx.x; q < B; q += blockDim.x) order[q] = 0xFFFFFFFFu - (uint32_t)pk[q];
+  for (uint32_t q = threadIdx.x; q < B; q += blockDim.x) {
+    uint32_t b = 63 - (uint32_t)(((uint64_t)work[q] * 64) / wmax);
+    order[atomicAdd(&base[b], 1u)] = q;
+  }
 }
 
 int launch_plan_queries(mgpu_ivf *ivf, const uint32_t *d_probes, uint32_t max_probes, const uint32_t *d_counts, uint32_t B,
-                        uint32_t *d_order) {
+                        uint32_t *d_order, uint32_t *d_work) {
   mgpu_ctx *ctx = ivf->ctx;
-  uint32_t P2 = 1;
-  while (P2 < B) P2 <<= 1;
   LaunchScope ls(ctx, MGPU_K_OTHER);
-  k_plan_queries<<<1, 1024, (size_t)P2 * 8, ctx->stream>>>(d_probes, max_probes, d_counts, ivf->d_chunk_start, B, P2, d_order);
+  k_query_work<<<(B + 7) / 8, 256, 0, ctx->stream>>>(d_probes, max_probes, d_counts, ivf->d_chunk_start, B, d_work);
+  k_plan_bucket<<<1, 1024, 0, ctx->stream>>>(d_work, B, d_order);
   CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
   return MGPU_OK;
 }
 

@@ -269,30 +269,32 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) k_scan_pq_db(ScanArgs a, 
 #pragma unroll
       for (int w = 0; w < NPW; w++) R += shf[w];
       const float scale = R > 0.0f ? 4.0e9f / R : 0.0f;
-      // ---- LUT image: 16 table rows at a time through a padded tile -----------------------------------------------------
+      // ---- LUT image, no staging: lane <-> LUT column (subspace), each lane streams its own 1 KB table row with 16-byte
+      // loads and stores four codes' entries; every store is one conflict-free 128-byte wavefront (32 lanes = 32
+      // consecutive columns of one code row).  The producer warps split the 256 codes.
+      {
+        constexpr int CODES_PER_WARP = 256 / NPW;
 #pragma unroll 1
-      for (int g = 0; g < NG; g++) {
-        const uint32_t slot = p * NG + g;
-        uint8_t *dstg = lut + (slot >> 1) * 65536u + (slot & 1) * 128u;
+        for (int g = 0; g < NG; g++) {
+          const uint32_t slot = p * NG + g;
+          uint8_t *dstg = lut + (slot >> 1) * 65536u + (slot & 1) * 128u + lane * 4;
+          const uint32_t s = g * 32 + lane;
+          const float off = soff[s];
+          const float4 *src = (const float4 *)(a.table + ((size_t)s * K + scode[s]) * K) + pwarp * (CODES_PER_WARP / 4);
 #pragma unroll 1
-        for (int hs = 0; hs < 2; hs++) {
-          for (int i = ptid; i < DB_TMP_ROWS * 64; i += NPT) {
-            const int r = i >> 6, j4 = i & 63;
-            const uint32_t s = g * 32 + hs * 16 + r;
-            const float4 v = *(const float4 *)(a.table + ((size_t)s * K + scode[s]) * K + j4 * 4);
-            float *d = tmp + r * DB_TMP_PITCH + j4 * 4;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+          for (int j4 = 0; j4 < CODES_PER_WARP / 4; j4 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = __ldg(src + j4 + i);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const int j = pwarp * CODES_PER_WARP + (j4 + i) * 4;
+              *(uint32_t *)(dstg + (j + 0) * 256) = __float2uint_rn(__fmul_rn(__fsub_rn(v[i].x, off), scale));
+              *(uint32_t *)(dstg + (j + 1) * 256) = __float2uint_rn(__fmul_rn(__fsub_rn(v[i].y, off), scale));
+              *(uint32_t *)(dstg + (j + 2) * 256) = __float2uint_rn(__fmul_rn(__fsub_rn(v[i].z, off), scale));
+              *(uint32_t *)(dstg + (j + 3) * 256) = __float2uint_rn(__fmul_rn(__fsub_rn(v[i].w, off), scale));
+            }
           }
-          named_bar_sync(2, NPT);
-          // transpose + convert: lane -> (column = lane/2, code parity = lane%2); pitch 258 keeps the reads conflict free
-          const int col = lane >> 1, jsub = lane & 1;
-          const float off = soff[g * 32 + hs * 16 + col];
-          for (int jj = pwarp; jj < 128; jj += NPW) {
-            const int j = 2 * jj + jsub;
-            const float v = tmp[col * DB_TMP_PITCH + j];
-            *(uint32_t *)(dstg + j * 256 + (hs * 16 + col) * 4) = __float2uint_rn(__fmul_rn(__fsub_rn(v, off), scale));
-          }
-          named_bar_sync(2, NPT);
         }
       }
       mbar_arrive(&bars[p]);  // buffer p is full (release: every producer thread's writes precede its arrive)
