@@ -835,7 +835,21 @@ int mgpu_hnsw_create(mgpu_ctx *ctx, uint32_t dim, uint32_t num_layers, const uin
     for (uint64_t i = s; i < e; i++) { spid[i] = v[i - s].first; spos[i] = v[i - s].second; }
   }
   size_t row_bytes = quant == MGPU_QUANT_PQ ? pq->m : (size_t)dim * 4;
+  // dense (layer, point) -> first position map: one load instead of a binary search per expansion on the upper layers,
+  // which matter because the reference runs the full `ef` beam on every layer (index.rs:172-183)
+  std::vector<int32_t> dense;
+  if (num_layers > 1 && (uint64_t)(num_layers - 1) * n * 4 <= (1ull << 30)) {
+    dense.assign((size_t)(num_layers - 1) * n, -1);
+    for (uint32_t li = 0; li + 1 < num_layers; li++) {
+      uint32_t layer = num_layers - 1 - li;
+      for (uint64_t i = level_offsets[li]; i < level_offsets[li + 1]; i++) {
+        uint32_t pid = points[i];
+        if (pid < n && dense[(size_t)(layer - 1) * n + pid] < 0) dense[(size_t)(layer - 1) * n + pid] = (int32_t)i;
+      }
+    }
+  }
   int s = dev_alloc_copy(ctx, &h->d_edges, edges, n_edges);
+  if (s == MGPU_OK && !dense.empty()) s = dev_alloc_copy(ctx, &h->d_upper_dense, dense.data(), dense.size());
   if (s == MGPU_OK) s = dev_alloc_copy(ctx, &h->d_points, points, n_points);
   if (s == MGPU_OK) s = dev_alloc_copy(ctx, &h->d_edge_offsets, edge_offsets, n_edge_offsets);
   if (s == MGPU_OK) s = dev_alloc_copy(ctx, &h->d_level_offsets, level_offsets, num_layers + 1);
@@ -854,7 +868,7 @@ void mgpu_hnsw_destroy(mgpu_hnsw *h) {
   cudaSetDevice(h->ctx->device);
   cudaStreamSynchronize(h->ctx->stream);
   cudaFree(h->d_edges); cudaFree(h->d_points); cudaFree(h->d_edge_offsets); cudaFree(h->d_level_offsets);
-  cudaFree(h->d_upper_sorted_pid); cudaFree(h->d_upper_sorted_pos); cudaFree(h->d_rows); cudaFree(h->d_doc_ids);
+  cudaFree(h->d_upper_sorted_pid); cudaFree(h->d_upper_sorted_pos); cudaFree(h->d_upper_dense); cudaFree(h->d_rows); cudaFree(h->d_doc_ids);
   delete h;
 }
 

@@ -21,6 +21,7 @@
 
 struct HnswDev {
   const uint32_t *edges, *points, *upper_pid, *upper_pos;
+  const int32_t *upper_dense;  // [(layer-1) * n + point] -> position in `points`, -1 if absent; may be null
   const uint64_t *edge_offsets, *level_offsets;
   const void *rows;
   const mgpu_u128 *doc_ids;
@@ -89,11 +90,19 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswDev g, HnswSearc
     if (go16) {
       const int chunks = n / 16;
       float acc = 0.0f;
-#pragma unroll 8
-      for (int c = 0; c < chunks; c++) {
-        float x = sq[c * 16 + h], y = __ldg(row + c * 16 + h);
-        if (METRIC == MGPU_L2) { float d = __fsub_rn(x, y); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
-        else acc = __fadd_rn(acc, __fmul_rn(x, y));
+      // 48 independent 64-byte row segments in flight per half-warp (one round trip for a 768-d row), consumed in order
+      for (int c0 = 0; c0 < chunks; c0 += 48) {
+        float y[48];
+#pragma unroll
+        for (int i = 0; i < 48; i++) y[i] = (c0 + i < chunks) ? __ldg(row + (c0 + i) * 16 + h) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 48; i++) {
+          if (c0 + i < chunks) {
+            float x = sq[(c0 + i) * 16 + h];
+            if (METRIC == MGPU_L2) { float d = __fsub_rn(x, y[i]); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
+            else acc = __fadd_rn(acc, __fmul_rn(x, y[i]));
+          }
+        }
       }
       float s = -0.0f;
       const int basel = lane & 16;
@@ -109,6 +118,24 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswDev g, HnswSearc
   auto pq_distance_thread = [&](uint32_t pid) -> float {
     return pq_distance_streaming<METRIC>(g.cb, g.m, g.K, g.dsub, RowMajorCode{qc},
                                          RowMajorCode{(const uint8_t *)g.rows + (size_t)pid * g.m});
+  };
+
+  // pop the nearest candidate (thread 0 only): `continue` while the working list is empty, `break` when the candidate is
+  // strictly farther than the furthest of the working list (index.rs:235-247)
+  auto pop_next = [&]() {
+    int head = st[1], nC = st[2], nW = st[0];
+    int stop = 0;
+    uint32_t cur = 0;
+    for (;;) {
+      if (head >= nC) { stop = 1; break; }
+      uint64_t c = C[head++];
+      if (nW == 0) continue;
+      uint32_t ck = (uint32_t)(c >> 32), fk = (uint32_t)(W[nW - 1] >> 32);
+      if (ck > fk) { stop = 1; break; }
+      cur = ~(uint32_t)c;
+      break;
+    }
+    st[1] = head; st[3] = (int)cur; st[4] = stop;
   };
 
   uint32_t ep = g.entry_point;
@@ -127,25 +154,10 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswDev g, HnswSearc
       C[0] = ((uint64_t)kd << 32) | (uint32_t)~ep;
       st[0] = 1; st[1] = 0; st[2] = 1; st[4] = 0;
       n_dist++;
+      pop_next();
     }
-    __syncthreads();
     for (;;) {
-      // ---- pop the nearest candidate (index.rs:235-247)
-      if (tid == 0) {
-        int head = st[1], nC = st[2], nW = st[0];
-        int stop = 0;
-        uint32_t cur = 0;
-        for (;;) {
-          if (head >= nC) { stop = 1; break; }
-          uint64_t c = C[head++];
-          if (nW == 0) continue;                                       // peek() == None => continue
-          uint32_t ck = (uint32_t)(c >> 32), fk = (uint32_t)(W[nW - 1] >> 32);
-          if (ck > fk) { stop = 1; break; }                            // strictly farther than the furthest => break
-          cur = ~(uint32_t)c;
-          break;
-        }
-        st[1] = head; st[3] = (int)cur; st[4] = stop;
-      }
+      // the nearest candidate was popped by thread 0 at the end of the previous admission phase (index.rs:235-247)
       __syncthreads();
       if (st[4]) break;
       const uint32_t cur = (uint32_t)st[3];
@@ -153,21 +165,31 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswDev g, HnswSearc
       long long idx = -1;
       if (layer == 0) idx = cur;
       else {
-        // first position of `cur` inside points[lvl_s, lvl_e): binary search in the per-layer sorted copy
-        long long lo = (long long)lvl_s, hi = (long long)lvl_e - 1;
-        while (lo <= hi) {
-          long long mid = (lo + hi) >> 1;
-          uint32_t v = g.upper_pid[mid];
-          if (v < cur) lo = mid + 1; else hi = mid - 1;
+        // first position of `cur` inside points[lvl_s, lvl_e): one load from the dense per-layer map when the index has one
+        // (create builds it while (num_layers-1) * n * 4 bytes stays small), else a binary search in the sorted copy
+        if (g.upper_dense) {
+          int32_t pos = cur < g.n ? g.upper_dense[(size_t)(layer - 1) * g.n + cur] : -1;
+          if (pos >= 0) idx = (long long)pos - (long long)lvl_s;
+        } else {
+          long long lo = (long long)lvl_s, hi = (long long)lvl_e - 1;
+          while (lo <= hi) {
+            long long mid = (lo + hi) >> 1;
+            uint32_t v = g.upper_pid[mid];
+            if (v < cur) lo = mid + 1; else hi = mid - 1;
+          }
+          if (lo < (long long)lvl_e && g.upper_pid[lo] == cur) idx = (long long)g.upper_pos[lo] - (long long)lvl_s;
         }
-        if (lo < (long long)lvl_e && g.upper_pid[lo] == cur) idx = (long long)g.upper_pos[lo] - (long long)lvl_s;
       }
       uint64_t e_begin = 0, e_end = 0;
       if (idx >= 0 && lvl_s + (uint64_t)idx + 1 < g.n_edge_offsets) {
         e_begin = g.edge_offsets[lvl_s + idx];
         e_end = g.edge_offsets[lvl_s + idx + 1];
       }
-      if (e_begin == e_end) { __syncthreads(); continue; }  // None => continue (uniform across the CTA)
+      if (e_begin == e_end) {  // None => continue (uniform across the CTA)
+        __syncthreads();
+        if (tid == 0) pop_next();
+        continue;
+      }
       if (tid == 0) n_expand++;
       for (uint64_t eb = e_begin; eb < e_end; eb += 32) {
         // ---- visited filter, edge order preserved (index.rs:255-259)
@@ -236,10 +258,13 @@ __global__ void __launch_bounds__(HN_THREADS) k_hnsw_search(HnswDev g, HnswSearc
               }
             }
           }
-          if (lane == 0) { st[0] = nW; st[1] = head; st[2] = nC; }
+          if (lane == 0) {
+            st[0] = nW; st[1] = head; st[2] = nC;
+            n_dist += nu;
+            if (eb + 32 >= e_end) pop_next();  // last edge batch: pop the next candidate right away (saves a barrier)
+          }
         }
-        if (tid == 0) n_dist += nu;
-        __syncthreads();
+        // no barrier here: warps 1..3 only touch nb/nbk again after the next filter barrier, which warp 0 reaches last
       }
     }
     // ---- next layer's entry: min_by distance over the sorted working list == W[0] (index.rs:176-181)
@@ -293,6 +318,8 @@ int launch_hnsw_search(mgpu_hnsw *h, const HnswSearchArgs &a) {
   CUDA_TRY(ctx, cudaMemsetAsync(err, 0, (size_t)a.B * 4, ctx->stream));
   HnswDev g;
   g.edges = h->d_edges; g.points = h->d_points; g.upper_pid = h->d_upper_sorted_pid; g.upper_pos = h->d_upper_sorted_pos;
+  static const bool use_dense = !(getenv("MGPU_HNSW_DENSE") && getenv("MGPU_HNSW_DENSE")[0] == '0');
+  g.upper_dense = use_dense ? h->d_upper_dense : nullptr;
   g.edge_offsets = h->d_edge_offsets; g.level_offsets = h->d_level_offsets; g.rows = h->d_rows; g.doc_ids = h->d_doc_ids;
   g.cb = h->pq ? h->pq->d_cb : nullptr; g.dim = h->dim; g.qdim = h->qdim; g.num_layers = h->num_layers;
   g.entry_point = h->entry_point; g.m = h->pq ? h->pq->m : 0; g.K = h->pq ? h->pq->K : 0; g.dsub = h->pq ? h->pq->dsub : 0;

@@ -65,6 +65,7 @@ struct mgpu_hnsw {
   std::vector<uint64_t> h_level_offsets;
   // upper-layer point -> position lookup: sorted (point, pos) pairs per layer
   uint32_t *d_upper_sorted_pid = nullptr, *d_upper_sorted_pos = nullptr;
+  int32_t *d_upper_dense = nullptr;  // dense (layer, point) -> position map for the upper layers (optional)
 };
 
 struct mgpu_spann {
