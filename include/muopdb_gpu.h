@@ -189,6 +189,26 @@ int mgpu_shard_allgather_merge(mgpu_ctx *ctx, const mgpu_u128 *local_doc_ids, co
                                const uint32_t *local_counts, uint32_t B, uint32_t k, mgpu_u128 *out_doc_ids,
                                float *out_scores, uint32_t *out_counts);
 
+/* ---- Readers of the reference's on-disk formats -------------- */
+/* One Elias-Fano posting-list payload (rs/compression/src/elias_fano/ef.rs:197-215; decode rule
+ * block_based_decoder.rs:162-179,257-266) -> ascending values.  Host-only (no device needed).
+ * Returns the element count or -1 on malformed input / insufficient capacity. */
+int64_t mgpu_ef_decode(const uint8_t *payload, uint64_t len, uint64_t *out, uint64_t cap);
+/* ProductQuantizerReader::read (rs/quantization/src/pq/mod.rs:52-136): `product_quantizer_config.yaml` + `codebook`. */
+int mgpu_pq_load(mgpu_ctx *ctx, const char *quantizer_dir, int metric, mgpu_pq **out);
+/* BlockBasedIvf::new_with_offset (rs/index/src/ivf/block_based/index.rs:95-138): `{base}/index` + `{base}/vectors`
+ * (layouts: ivf/writer.rs:300-353, ivf/block_based/storage.rs:52-151); byte offsets address a user's section inside
+ * the shared multi-user files (multi_spann/user_index_info.rs:4-14), 0 for single-index directories. */
+int mgpu_ivf_load(mgpu_ctx *ctx, const char *base_dir, uint64_t index_offset, uint64_t vector_offset, int quant, int metric,
+                  mgpu_pq *pq, mgpu_ivf **out);
+/* BlockBasedHnsw::new_with_offsets (rs/index/src/hnsw/block_based/index.rs:94-140): `{base}/hnsw/index` +
+ * `{base}/hnsw/vector_storage` (hnsw/writer.rs:206-265, graph_storage.rs:122-193).  dim = original dimension. */
+int mgpu_hnsw_load(mgpu_ctx *ctx, const char *base_dir, uint64_t index_offset, uint64_t vector_offset, uint32_t dim, int quant,
+                   int metric, mgpu_pq *pq, mgpu_hnsw **out);
+/* sizes = {num_layers, n_edges, n_points, n_edge_offsets, n, entry_point}; copy_graph reads the resident arrays back. */
+int mgpu_hnsw_info(mgpu_hnsw *h, uint64_t sizes[6]);
+int mgpu_hnsw_copy_graph(mgpu_hnsw *h, uint32_t *edges, uint32_t *points, uint64_t *edge_offsets, uint64_t *level_offsets);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,7 +31,7 @@ from ._lib import (DEVICE, DOT, HOST, L2, QUANT_NONE, QUANT_PQ, InvalidArgument,
 
 __all__ = ["Context", "default_context", "L2DistanceCalculator", "DotProductDistanceCalculator", "NoQuantizer",
            "ProductQuantizer", "BlockBasedIvf", "BlockBasedHnsw", "Spann", "SearchParams", "IdWithScore", "SearchResult",
-           "merge_topk", "assign_to_centroids", "L2", "DOT", "MuopdbGpuError", "OutOfRange", "InvalidArgument", "Unsupported",
+           "merge_topk", "assign_to_centroids", "elias_fano_decode", "L2", "DOT", "MuopdbGpuError", "OutOfRange", "InvalidArgument", "Unsupported",
            "NoDevice"]
 
 
@@ -274,6 +274,25 @@ class ProductQuantizer:
                                                self.metric, C.byref(h)), self.ctx.h)
         self.handle = h
 
+    @classmethod
+    def read(cls, dir: str, distance=L2DistanceCalculator, ctx: Optional[Context] = None):
+        """Quantizer::read / ProductQuantizerReader::read (pq/mod.rs:52-136): yaml config + raw f32 codebook."""
+        import os
+        self = cls.__new__(cls)
+        self.ctx = ctx or default_context()
+        self.metric = distance.METRIC
+        h = C.c_void_p()
+        _lib.check(self.ctx.lib.mgpu_pq_load(self.ctx.h, dir.encode(), self.metric, C.byref(h)), self.ctx.h)
+        self.handle = h
+        cfg = {}
+        for line in open(os.path.join(dir, "product_quantizer_config.yaml")):
+            if ":" in line:
+                k, v = line.split(":", 1)
+                cfg[k.strip()] = int(v)
+        self.dimension, self.subvector_dimension, self.num_bits = cfg["dimension"], cfg["subvector_dimension"], cfg["num_bits"]
+        self.codebook = np.fromfile(os.path.join(dir, "codebook"), dtype="<f4")
+        return self
+
     def __del__(self):
         try:
             if self.handle:
@@ -413,6 +432,21 @@ class BlockBasedIvf:
         except Exception:
             pass
 
+    @classmethod
+    def new(cls, base_directory: str, quantizer, index_offset: int = 0, vector_offset: int = 0, ctx: Optional[Context] = None):
+        """BlockBasedIvf::new / new_with_offset (index.rs:50-138): open `{base}/index` + `{base}/vectors` written by the
+        reference's IvfWriter (ivf/writer.rs:46-353); Elias-Fano posting lists are decoded on the host."""
+        self = cls.__new__(cls)
+        self.ctx = ctx or getattr(quantizer, "ctx", None) or default_context()
+        self.quantizer = quantizer
+        h = C.c_void_p()
+        _lib.check(self.ctx.lib.mgpu_ivf_load(self.ctx.h, base_directory.encode(), index_offset, vector_offset, quantizer.QUANT,
+                                              quantizer.metric, quantizer.handle, C.byref(h)), self.ctx.h)
+        self.handle = h
+        self.nlist = int(self.ctx.lib.mgpu_ivf_num_clusters(h))
+        self.dim = quantizer.dimension
+        return self
+
     def num_clusters(self) -> int:
         return int(self.ctx.lib.mgpu_ivf_num_clusters(self.handle))
 
@@ -533,6 +567,33 @@ class BlockBasedHnsw:
         except Exception:
             pass
 
+    @classmethod
+    def new(cls, base_directory: str, quantizer, index_offset: int = 0, vector_offset: int = 0, ctx: Optional[Context] = None):
+        """BlockBasedHnsw::new / new_with_offsets (hnsw/block_based/index.rs:69-140): `{base}/hnsw/index` +
+        `{base}/hnsw/vector_storage` written by the reference's HnswWriter (hnsw/writer.rs:43-265)."""
+        self = cls.__new__(cls)
+        self.ctx = ctx or getattr(quantizer, "ctx", None) or default_context()
+        self.quantizer = quantizer
+        self.dim = quantizer.dimension
+        h = C.c_void_p()
+        _lib.check(self.ctx.lib.mgpu_hnsw_load(self.ctx.h, base_directory.encode(), index_offset, vector_offset, self.dim,
+                                               quantizer.QUANT, quantizer.metric, quantizer.handle, C.byref(h)), self.ctx.h)
+        self.handle = h
+        return self
+
+    def graph_arrays(self):
+        """The resident graph sections (edges, points, edge_offsets, level_offsets) + entry point, read back from HBM."""
+        sz = np.zeros(6, dtype=np.uint64)
+        _lib.check(self.ctx.lib.mgpu_hnsw_info(self.handle, sz.ctypes.data), self.ctx.h)
+        nl, ne, npnt, neo, n, ep = (int(v) for v in sz)
+        edges = np.zeros(max(ne, 1), dtype=np.uint32)
+        points = np.zeros(max(npnt, 1), dtype=np.uint32)
+        eo = np.zeros(neo, dtype=np.uint64)
+        lo = np.zeros(nl + 1, dtype=np.uint64)
+        _lib.check(self.ctx.lib.mgpu_hnsw_copy_graph(self.handle, edges.ctypes.data, points.ctypes.data, eo.ctypes.data,
+                                                     lo.ctypes.data), self.ctx.h)
+        return dict(num_layers=nl, edges=edges[:ne], points=points[:npnt], edge_offsets=eo, level_offsets=lo, n=n, entry_point=ep)
+
     def ann_search_batch(self, Q, k: int, ef: int, with_stats=False):
         q = _Buf(Q, np.float32, (None, self.dim))
         B = q.shape[0]
@@ -571,6 +632,16 @@ class Spann:
         except Exception:
             pass
 
+    @classmethod
+    def read(cls, base_directory: str, quantizer, ctx: Optional[Context] = None):
+        """SpannReader::read (spann/reader.rs:75-76): `{base}/centroids` is an HNSW over the centroids with a NoQuantizer,
+        `{base}/ivf` the posting lists with quantizer Q."""
+        import os
+        ctx = ctx or getattr(quantizer, "ctx", None) or default_context()
+        centroids = BlockBasedHnsw.new(os.path.join(base_directory, "centroids"), NoQuantizer(quantizer.dimension), ctx=ctx)
+        lists = BlockBasedIvf.new(os.path.join(base_directory, "ivf"), quantizer, ctx=ctx)
+        return cls(centroids, lists)
+
     def search_batch(self, Q, params: SearchParams) -> BatchResult:
         q = _Buf(Q, np.float32, (None, self.posting_lists.dim))
         B = q.shape[0]
@@ -586,6 +657,19 @@ class Spann:
 
 
 # ---- merge / assignment ---------------------------------------------------------------------------------------------------
+def elias_fano_decode(payload: bytes) -> np.ndarray:
+    """Decode one Elias-Fano posting list as written by EliasFano::write (rs/compression/src/elias_fano/ef.rs:197-215)."""
+    buf = np.frombuffer(payload, dtype=np.uint8)
+    if buf.size < 32:
+        raise InvalidArgument(_lib.ERR_INVALID_ARG, "payload shorter than the Elias-Fano header")
+    n = int(np.frombuffer(payload[:8], dtype="<u8")[0])
+    out = np.zeros(max(n, 1), dtype=np.uint64)
+    r = _lib.load().mgpu_ef_decode(buf.ctypes.data, buf.size, out.ctypes.data, n)
+    if r < 0:
+        raise InvalidArgument(_lib.ERR_INVALID_ARG, "malformed Elias-Fano payload")
+    return out[:n]
+
+
 def merge_topk(doc_ids, scores, counts, k: int, ctx: Optional[Context] = None) -> BatchResult:
     """Snapshot merge (collection/snapshot.rs:49-63,79-108): doc_ids (S,B,k,2), scores (S,B,k), counts (S,B)."""
     ctx = ctx or default_context()

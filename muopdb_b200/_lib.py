@@ -90,6 +90,13 @@ SIGNATURES = {
     "mgpu_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mgpu_comm_destroy": (C.c_int, [C.c_void_p]),
     "mgpu_shard_allgather_merge": (C.c_int, [C.c_void_p, _vp, _f32p, _u32p, C.c_uint32, C.c_uint32, _vp, _f32p, _u32p]),
+    "mgpu_ef_decode": (C.c_int64, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
+    "mgpu_pq_load": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "mgpu_ivf_load": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mgpu_hnsw_load": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_void_p,
+                                 C.POINTER(C.c_void_p)]),
+    "mgpu_hnsw_info": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mgpu_hnsw_copy_graph": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

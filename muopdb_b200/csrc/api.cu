@@ -808,7 +808,9 @@ int mgpu_hnsw_create(mgpu_ctx *ctx, uint32_t dim, uint32_t num_layers, const uin
     return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "hnsw_create: null/zero argument");
   if (quant == MGPU_QUANT_PQ && (!pq || pq->dim != dim)) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "hnsw_create: PQ quantizer missing or of the wrong dimension");
   if (n_edges && !edges) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "hnsw_create: null edges");
-  if (level_offsets[num_layers] + 1 > n_edge_offsets || level_offsets[num_layers - 1] > n_points)
+  // edge_offsets = one entry per upper-layer node, then n layer-0 entries, then one terminal entry (hnsw/writer.rs:100-140);
+  // level_offsets[num_layers] is n_upper + n in our builders and n_upper + n + 1 in files written by the reference
+  if (level_offsets[num_layers - 1] + n + 1 > n_edge_offsets || level_offsets[num_layers - 1] > n_points)
     return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "hnsw_create: level_offsets inconsistent with points/edge_offsets");
   std::lock_guard<std::mutex> g(ctx->mu);
   cudaSetDevice(ctx->device);
