@@ -68,6 +68,7 @@ typedef struct mgpu_pq mgpu_pq;
 typedef struct mgpu_ivf mgpu_ivf;
 typedef struct mgpu_hnsw mgpu_hnsw;
 typedef struct mgpu_spann mgpu_spann;
+typedef struct mgpu_batcher mgpu_batcher;
 
 /* ---- context ------------------------------------------------------------------------------ */
 int mgpu_init(int device, mgpu_ctx **out);
@@ -140,6 +141,18 @@ int mgpu_ivf_scan_remap(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint32_
 /* BlockBasedIvf::search (index.rs:396-412): coarse + scan + remap. */
 int mgpu_ivf_search(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, mgpu_u128 *out_doc_ids,
                     float *out_scores, uint32_t *out_counts, int mem);
+/* Planner filter hook (index.rs:212-226; Planner::plan_with_ids rs/index/src/query/planner.rs:43-60): the caller evaluates
+ * the request's DocumentFilter to a point-id set and passes it as a bitmap (bit p of word p/32 = point id p allowed).  A
+ * scanned row is kept only if its bit is set; distances are still computed for every non-invalidated row, as in the
+ * reference.  filter_bits: ceil(N/32) words per query, query b at filter_bits + b * filter_stride_words; stride 0 = one
+ * bitmap shared by the batch; NULL = no filter.  Same memory space (`mem`) as Q. */
+int mgpu_ivf_search_filtered(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, const uint32_t *filter_bits,
+                             uint64_t filter_stride_words, mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts,
+                             int mem);
+int mgpu_ivf_scan_remap_filtered(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint32_t *probe_ids, uint32_t max_probes,
+                                 const uint32_t *probe_counts, uint32_t k, const uint32_t *filter_bits,
+                                 uint64_t filter_stride_words, mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts,
+                                 int mem);
 /* Algorithmic bytes of the last scan on this index (sum over queries of L(q) x bytes/row + 4). */
 uint64_t mgpu_ivf_last_scan_bytes(mgpu_ivf *ivf);
 uint64_t mgpu_ivf_last_scan_rows(mgpu_ivf *ivf);
@@ -171,6 +184,29 @@ void mgpu_spann_destroy(mgpu_spann *s);
 int mgpu_spann_search(mgpu_spann *s, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef,
                       uint32_t num_explored_centroids, float centroid_distance_ratio, mgpu_u128 *out_doc_ids,
                       float *out_scores, uint32_t *out_counts, int mem);
+
+/* Spann::search with Some(planner) (spann/index.rs:253-263): filter semantics as mgpu_ivf_search_filtered. */
+int mgpu_spann_search_filtered(mgpu_spann *s, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef,
+                               uint32_t num_explored_centroids, float centroid_distance_ratio, const uint32_t *filter_bits,
+                               uint64_t filter_stride_words, mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts,
+                               int mem);
+
+/* ---- Micro-batcher (SURVEY.md 8b "Threading", 8f row 4) ------------------------------------- */
+/* The reference serves one query per call from many tokio tasks (IndexServer::search, rs/index_server/src/index_server.rs:
+ * 171-271 -> Snapshot::search_for_users -> ... -> BlockBasedIvf::search index.rs:396-412 / Spann::search spann/index.rs:211).
+ * A batcher keeps that call shape: mgpu_batcher_search blocks with ONE query (thread-safe, call it from spawn_blocking); a
+ * worker thread closes a batch at max_batch queries or when its oldest query has waited max_wait_us, runs one batched
+ * search and scatters the results into the callers' buffers (out_doc_ids/out_scores: k entries; *out_count as in the
+ * batched call, UINT32_MAX = None for SPANN).  filter_bits: the request's planner filter (ceil(N/32) words) or NULL. */
+int mgpu_batcher_create(mgpu_ivf *ivf, uint32_t max_batch, uint32_t max_wait_us, uint32_t k, uint32_t nprobe, mgpu_batcher **out);
+int mgpu_batcher_create_spann(mgpu_spann *s, uint32_t max_batch, uint32_t max_wait_us, uint32_t top_k, uint32_t ef,
+                              uint32_t num_explored_centroids, float centroid_distance_ratio, mgpu_batcher **out);
+void mgpu_batcher_destroy(mgpu_batcher *b);  /* drains the queries already submitted, then stops the worker */
+int mgpu_batcher_search(mgpu_batcher *b, const float *query, mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_count);
+int mgpu_batcher_search_filtered(mgpu_batcher *b, const float *query, const uint32_t *filter_bits, mgpu_u128 *out_doc_ids,
+                                 float *out_scores, uint32_t *out_count);
+/* stats = {queries served, batches launched, largest batch, batches closed because they were full} */
+int mgpu_batcher_stats(mgpu_batcher *b, uint64_t stats[4]);
 
 /* ---- Cross-segment / cross-shard merge (rs/index/src/collection/snapshot.rs:49-63,79-108) -- */
 /* Concatenate S partial results per query, sort by (score, doc_id) (utils.rs:95-114), truncate to k.

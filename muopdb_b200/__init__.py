@@ -31,7 +31,7 @@ from ._lib import (DEVICE, DOT, HOST, L2, QUANT_NONE, QUANT_PQ, InvalidArgument,
 
 __all__ = ["Context", "default_context", "L2DistanceCalculator", "DotProductDistanceCalculator", "NoQuantizer",
            "ProductQuantizer", "BlockBasedIvf", "BlockBasedHnsw", "Spann", "SearchParams", "IdWithScore", "SearchResult",
-           "merge_topk", "assign_to_centroids", "elias_fano_decode", "L2", "DOT", "MuopdbGpuError", "OutOfRange", "InvalidArgument", "Unsupported",
+           "Planner", "MicroBatcher", "merge_topk", "assign_to_centroids", "elias_fano_decode", "L2", "DOT", "MuopdbGpuError", "OutOfRange", "InvalidArgument", "Unsupported",
            "NoDevice"]
 
 
@@ -363,6 +363,53 @@ class SearchParams:
         return self.top_k if self.num_explored_centroids is None else self.num_explored_centroids
 
 
+class Planner:
+    """Host mirror of rs/index/src/query/planner.rs as the search path sees it: `planner.plan_with_ids(scanned_ids)`
+    (planner.rs:43-60) yields the scanned point ids that satisfy the request's DocumentFilter, and scan_posting_list keeps only
+    those (ivf/block_based/index.rs:212-226).  Here the filter is already evaluated to its point-id set; the GPU scan tests
+    one bit per row.  Pass one Planner for a whole batch, or a list with one Planner (or None = no filter) per query."""
+
+    def __init__(self, allowed_point_ids=None, bitmap=None):
+        if (allowed_point_ids is None) == (bitmap is None):
+            raise InvalidArgument(_lib.ERR_INVALID_ARG, "give either the allowed point ids or a ready bitmap")
+        self._ids = None if allowed_point_ids is None else np.unique(np.asarray(allowed_point_ids, dtype=np.uint64))
+        self._bitmap = None if bitmap is None else np.ascontiguousarray(bitmap, dtype=np.uint32)
+
+    def bitmap(self, num_vectors: int) -> np.ndarray:
+        words = (num_vectors + 31) // 32
+        if self._bitmap is not None:
+            if self._bitmap.size < words:
+                raise InvalidArgument(_lib.ERR_INVALID_ARG, "filter bitmap shorter than the index")
+            return self._bitmap[:words]
+        bits = np.zeros(words, dtype=np.uint32)
+        ids = self._ids[self._ids < num_vectors].astype(np.int64)
+        np.bitwise_or.at(bits, ids >> 5, (np.uint32(1) << (ids & 31).astype(np.uint32)))
+        return bits
+
+
+def _filter_arg(planner, B: int, num_vectors: int, device_like):
+    """-> (pointer, stride_words, keepalive) for the *_filtered entry points; (None, 0, None) when there is no filter."""
+    if planner is None:
+        return None, 0, None
+    words = (num_vectors + 31) // 32
+    if isinstance(planner, Planner):
+        bits, stride = planner.bitmap(num_vectors), 0
+    else:
+        if len(planner) != B:
+            raise InvalidArgument(_lib.ERR_INVALID_ARG, "one planner per query expected")
+        bits = np.full((B, words), 0xFFFFFFFF, dtype=np.uint32)
+        for b, p in enumerate(planner):
+            if p is not None:
+                bits[b] = p.bitmap(num_vectors)
+        stride = words
+    bits = np.ascontiguousarray(bits)
+    if device_like is not None:
+        import torch
+        t = torch.from_numpy(bits.view(np.int32)).to(device_like.device)
+        return t.data_ptr(), stride, t
+    return bits.ctypes.data, stride, bits
+
+
 class BatchResult(NamedTuple):
     doc_ids: object   # (B, k, 2) uint64 (numpy) / int64 (torch): (lo, hi) of each u128 doc id
     scores: object    # (B, k) float32
@@ -482,7 +529,7 @@ class BlockBasedIvf:
         _lib.check(self.ctx.lib.mgpu_ivf_coarse(self.handle, q.ptr, B, num_probes, ip, dp, q.mem), self.ctx.h)
         return (ids, ds) if with_distances else ids
 
-    def search_with_centroids_batch(self, Q, centroid_ids, k: int, counts=None, remap=True):
+    def search_with_centroids_batch(self, Q, centroid_ids, k: int, counts=None, remap=True, planner=None):
         """search_with_centroids(_and_remap) for a batch; centroid_ids (B, P), counts (B,) optional."""
         q = _Buf(Q, np.float32, (None, self.dim))
         B = q.shape[0]
@@ -492,12 +539,22 @@ class BlockBasedIvf:
             raise InvalidArgument(_lib.ERR_INVALID_ARG, "queries and probe lists must live in the same memory space")
         P = pr.shape[1]
         ids, scores, cnt, ip, sp, cp = _alloc_out(B, k, Q if q.mem == DEVICE else None, u128=remap)
+        if planner is not None:
+            if not remap:
+                raise Unsupported(_lib.ERR_UNSUPPORTED, "the planner filter is only wired into the remapping search (index.rs:298-332)")
+            fp, fstride, _keep = _filter_arg(planner, B, self.num_vectors(), Q if q.mem == DEVICE else None)
+            _lib.check(self.ctx.lib.mgpu_ivf_scan_remap_filtered(self.handle, q.ptr, B, pr.ptr, P, pc.ptr, k, fp, fstride, ip, sp, cp,
+                                                                 q.mem), self.ctx.h)
+            if _keep is not None and q.mem == DEVICE:
+                self.ctx.sync()  # the bitmap tensor must outlive the asynchronous scan
+            return BatchResult(ids, scores, cnt)
         f = self.ctx.lib.mgpu_ivf_scan_remap if remap else self.ctx.lib.mgpu_ivf_scan
         _lib.check(f(self.handle, q.ptr, B, pr.ptr, P, pc.ptr, k, ip, sp, cp, q.mem), self.ctx.h)
         return BatchResult(ids, scores, cnt)
 
-    def search_batch(self, Q, k: int, num_probes: int, out=None) -> BatchResult:
-        """BlockBasedIvf::search for a batch of queries: coarse scoring + list scan + remap, all on the GPU."""
+    def search_batch(self, Q, k: int, num_probes: int, out=None, planner=None) -> BatchResult:
+        """BlockBasedIvf::search for a batch of queries: coarse scoring + list scan + remap, all on the GPU.
+        planner: Option<Arc<Planner>> of index.rs:396-403 (one for the batch or one per query)."""
         q = _Buf(Q, np.float32, (None, self.dim))
         B = q.shape[0]
         if out is None:
@@ -505,6 +562,13 @@ class BlockBasedIvf:
         else:
             ids, scores, cnt = out
             ip, sp, cp = (x.data_ptr() if _is_torch(x) else x.ctypes.data for x in out)
+        if planner is not None:
+            fp, fstride, _keep = _filter_arg(planner, B, self.num_vectors(), Q if q.mem == DEVICE else None)
+            _lib.check(self.ctx.lib.mgpu_ivf_search_filtered(self.handle, q.ptr, B, k, num_probes, fp, fstride, ip, sp, cp, q.mem),
+                       self.ctx.h)
+            if _keep is not None and q.mem == DEVICE:
+                self.ctx.sync()  # the bitmap tensor must outlive the asynchronous scan
+            return BatchResult(ids, scores, cnt)
         _lib.check(self.ctx.lib.mgpu_ivf_search(self.handle, q.ptr, B, k, num_probes, ip, sp, cp, q.mem), self.ctx.h)
         return BatchResult(ids, scores, cnt)
 
@@ -520,17 +584,17 @@ class BlockBasedIvf:
         ids = self.find_nearest_centroids_batch(np.asarray(vector, dtype=np.float32).reshape(1, -1), num_probes)
         return [int(x) for x in ids[0]]
 
-    def search_with_centroids_and_remap(self, query, nearest_centroid_ids, k: int) -> SearchResult:
+    def search_with_centroids_and_remap(self, query, nearest_centroid_ids, k: int, planner: Optional[Planner] = None) -> SearchResult:
         """index.rs:298-332"""
         c = np.asarray(nearest_centroid_ids, dtype=np.uint32).reshape(1, -1)
         if c.size == 0:
             return SearchResult([])
-        r = self.search_with_centroids_batch(np.asarray(query, dtype=np.float32).reshape(1, -1), c, k)
+        r = self.search_with_centroids_batch(np.asarray(query, dtype=np.float32).reshape(1, -1), c, k, planner=planner)
         return r.to_results()[0]
 
-    def search(self, query, k: int, num_probes: int) -> Optional[SearchResult]:
+    def search(self, query, k: int, num_probes: int, planner: Optional[Planner] = None) -> Optional[SearchResult]:
         """index.rs:396-412"""
-        return self.search_batch(np.asarray(query, dtype=np.float32).reshape(1, -1), k, num_probes).to_results()[0]
+        return self.search_batch(np.asarray(query, dtype=np.float32).reshape(1, -1), k, num_probes, planner=planner).to_results()[0]
 
 
 # ---- BlockBasedHnsw<Q> (rs/index/src/hnsw/block_based/index.rs) --------------------------------------------------------------
@@ -642,18 +706,81 @@ class Spann:
         lists = BlockBasedIvf.new(os.path.join(base_directory, "ivf"), quantizer, ctx=ctx)
         return cls(centroids, lists)
 
-    def search_batch(self, Q, params: SearchParams) -> BatchResult:
+    def search_batch(self, Q, params: SearchParams, planner=None) -> BatchResult:
         q = _Buf(Q, np.float32, (None, self.posting_lists.dim))
         B = q.shape[0]
         ids, scores, cnt, ip, sp, cp = _alloc_out(B, params.top_k, Q if q.mem == DEVICE else None)
+        if planner is not None:
+            fp, fstride, _keep = _filter_arg(planner, B, self.posting_lists.num_vectors(), Q if q.mem == DEVICE else None)
+            _lib.check(self.ctx.lib.mgpu_spann_search_filtered(self.handle, q.ptr, B, params.top_k, params.ef_construction,
+                                                               params.explored(), float(params.centroid_distance_ratio), fp,
+                                                               fstride, ip, sp, cp, q.mem), self.ctx.h)
+            if _keep is not None and q.mem == DEVICE:
+                self.ctx.sync()
+            return BatchResult(ids, scores, cnt)
         _lib.check(self.ctx.lib.mgpu_spann_search(self.handle, q.ptr, B, params.top_k, params.ef_construction,
                                                   params.explored(), float(params.centroid_distance_ratio), ip, sp, cp,
                                                   q.mem), self.ctx.h)
         return BatchResult(ids, scores, cnt)
 
-    def search(self, query, params: SearchParams) -> Optional[SearchResult]:
+    def search(self, query, params: SearchParams, planner: Optional[Planner] = None) -> Optional[SearchResult]:
         """spann/index.rs:211-266"""
-        return self.search_batch(np.asarray(query, dtype=np.float32).reshape(1, -1), params).to_results()[0]
+        return self.search_batch(np.asarray(query, dtype=np.float32).reshape(1, -1), params, planner=planner).to_results()[0]
+
+
+# ---- micro-batcher ------------------------------------------------------------------------------------------------------------
+class MicroBatcher:
+    """Per-request front door: `search(query)` has the reference's single-query shape
+    (BlockBasedIvf::search index.rs:396-412 / Spann::search spann/index.rs:211-266) and may be called from many threads;
+    a native worker thread groups concurrent calls into one batched GPU search (ctypes releases the GIL while a call waits)."""
+
+    def __init__(self, index, k: int, num_probes: int = 0, params: Optional[SearchParams] = None, max_batch: int = 1024,
+                 max_wait_us: int = 200):
+        self.index, self.ctx = index, index.ctx
+        h = C.c_void_p()
+        if isinstance(index, Spann):
+            p = params or SearchParams(k, 100)
+            self.k = p.top_k
+            self.dim = index.posting_lists.dim
+            self.num_vectors = index.posting_lists.num_vectors()
+            _lib.check(self.ctx.lib.mgpu_batcher_create_spann(index.handle, max_batch, max_wait_us, p.top_k, p.ef_construction,
+                                                              p.explored(), float(p.centroid_distance_ratio), C.byref(h)), self.ctx.h)
+        else:
+            self.k, self.dim, self.num_vectors = k, index.dim, index.num_vectors()
+            _lib.check(self.ctx.lib.mgpu_batcher_create(index.handle, max_batch, max_wait_us, k, num_probes, C.byref(h)), self.ctx.h)
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.mgpu_batcher_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def search(self, query, planner: Optional[Planner] = None) -> Optional[SearchResult]:
+        q = np.ascontiguousarray(query, dtype=np.float32).reshape(-1)
+        if q.size != self.dim:
+            raise InvalidArgument(_lib.ERR_INVALID_ARG, "query has the wrong dimension")
+        ids = np.zeros((1, self.k, 2), dtype=np.uint64)
+        scores = np.zeros((1, self.k), dtype=np.float32)
+        cnt = np.zeros(1, dtype=np.uint32)
+        if planner is None:
+            st = self.ctx.lib.mgpu_batcher_search(self.handle, q.ctypes.data, ids.ctypes.data, scores.ctypes.data, cnt.ctypes.data)
+        else:
+            bits = np.ascontiguousarray(planner.bitmap(self.num_vectors))
+            st = self.ctx.lib.mgpu_batcher_search_filtered(self.handle, q.ctypes.data, bits.ctypes.data, ids.ctypes.data,
+                                                           scores.ctypes.data, cnt.ctypes.data)
+        _lib.check(st, self.ctx.h)
+        return BatchResult(ids, scores, cnt).to_results()[0]
+
+    def stats(self) -> dict:
+        s = (C.c_uint64 * 4)()
+        _lib.check(self.ctx.lib.mgpu_batcher_stats(self.handle, C.addressof(s)), self.ctx.h)
+        return {"queries": s[0], "batches": s[1], "largest_batch": s[2], "full_batches": s[3]}
 
 
 # ---- merge / assignment ---------------------------------------------------------------------------------------------------

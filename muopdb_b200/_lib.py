@@ -75,6 +75,10 @@ SIGNATURES = {
     "mgpu_ivf_scan": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, _u32p, C.c_uint32, _u32p, C.c_uint32, _u32p, _f32p, _u32p, C.c_int]),
     "mgpu_ivf_scan_remap": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, _u32p, C.c_uint32, _u32p, C.c_uint32, _vp, _f32p, _u32p, C.c_int]),
     "mgpu_ivf_search": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _f32p, _u32p, C.c_int]),
+    "mgpu_ivf_search_filtered": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, C.c_uint64, _vp, _f32p, _u32p,
+                                           C.c_int]),
+    "mgpu_ivf_scan_remap_filtered": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, _u32p, C.c_uint32, _u32p, C.c_uint32, _u32p, C.c_uint64,
+                                               _vp, _f32p, _u32p, C.c_int]),
     "mgpu_ivf_last_scan_bytes": (C.c_uint64, [C.c_void_p]),
     "mgpu_ivf_last_scan_rows": (C.c_uint64, [C.c_void_p]),
     "mgpu_ivf_assign": (C.c_int, [C.c_void_p, _f32p, C.c_uint64, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, _u32p, _u32p, C.c_int]),
@@ -85,6 +89,15 @@ SIGNATURES = {
     "mgpu_spann_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "mgpu_spann_destroy": (None, [C.c_void_p]),
     "mgpu_spann_search": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, _vp, _f32p, _u32p, C.c_int]),
+    "mgpu_spann_search_filtered": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, _u32p,
+                                             C.c_uint64, _vp, _f32p, _u32p, C.c_int]),
+    "mgpu_batcher_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "mgpu_batcher_create_spann": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float,
+                                            C.POINTER(C.c_void_p)]),
+    "mgpu_batcher_destroy": (None, [C.c_void_p]),
+    "mgpu_batcher_search": (C.c_int, [C.c_void_p, _f32p, _vp, _f32p, _u32p]),
+    "mgpu_batcher_search_filtered": (C.c_int, [C.c_void_p, _f32p, _u32p, _vp, _f32p, _u32p]),
+    "mgpu_batcher_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mgpu_merge_topk": (C.c_int, [C.c_void_p, _vp, _f32p, _u32p, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _f32p, _u32p, C.c_int]),
     "mgpu_comm_unique_id": (C.c_int, [C.c_void_p]),
     "mgpu_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

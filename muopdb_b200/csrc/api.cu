@@ -64,6 +64,9 @@ int mgpu_init(int device, mgpu_ctx **out) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MGPU_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return MGPU_ERR_CUDA; }
+  cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   cudaEventCreate(&ctx->t0);
   cudaEventCreate(&ctx->t1);
   *out = ctx;
@@ -80,6 +83,10 @@ void mgpu_destroy(mgpu_ctx *ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   cudaEventDestroy(ctx->t0);
   cudaEventDestroy(ctx->t1);
+  cudaEventDestroy(ctx->ev_fork);
+  cudaEventDestroy(ctx->ev_join);
+  cudaStreamSynchronize(ctx->aux_stream);
+  cudaStreamDestroy(ctx->aux_stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -422,11 +429,12 @@ uint64_t mgpu_ivf_last_scan_bytes(mgpu_ivf *ivf) { return ivf ? mgpu_ivf_last_sc
 
 // coarse scoring on device buffers: dQ (B x dim) -> d_ids (B x nprobe), d_dist (optional)
 static size_t ivf_coarse_extra_ws(mgpu_ivf *ivf, uint32_t B) {  // query split + norms + overflow counter
-  return ws_need(ws_need(ws_need(0, (size_t)B * coarse_tc_kp(ivf->dim) * 2), (size_t)B * 4), 16) + 256;
+  return ws_need(ws_need(ws_need(ws_need(0, (size_t)B * coarse_tc_kp(ivf->dim) * 2), (size_t)B * 4), 16), (size_t)B * 4) + 256;
 }
 
+// need_order: the caller wants the probes nearest-first (mgpu_ivf_coarse); a search only needs the probe SET
 static int ivf_coarse_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, uint32_t nprobe, float *dD, uint32_t *d_ids, float *d_dist,
-                          void *extra_ws) {
+                          void *extra_ws, int need_order) {
   mgpu_ctx *ctx = ivf->ctx;
   if (ivf->d_csplit && extra_ws && coarse_tc_applicable(ctx, ivf->dim, ivf->nlist, nprobe)) {
     // tensor-core pass + exact re-score of a provably sufficient candidate set: identical probes to the exact path
@@ -434,8 +442,9 @@ static int ivf_coarse_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, uint32_t n
     void *qsplit = w.get<uint16_t>((size_t)B * coarse_tc_kp(ivf->dim));
     float *qn = w.get<float>(B);
     uint32_t *ovf = w.get<uint32_t>(4);
+    uint32_t *flags = w.get<uint32_t>(B);
     return launch_coarse_tc(ctx, dQ, B, ivf->d_centroids, ivf->d_csplit, ivf->d_cn, ivf->cn_max, ivf->nlist, ivf->dim, nprobe, qsplit,
-                            qn, dD, ovf, d_ids, d_dist);
+                            qn, dD, ovf, flags, need_order, d_ids, d_dist);
   }
   // always the L2 calculator with sqrt (index.rs:155), whatever the quantizer's metric
   MGPU_TRY(launch_distance_matrix(ctx, dQ, B, ivf->d_centroids, ivf->nlist, ivf->dim, MGPU_L2, 1, dD, MGPU_K_COARSE));
@@ -462,7 +471,7 @@ int mgpu_ivf_coarse(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t nprobe, 
   MGPU_TRY(stage_in(ctx, Q, bQ, mem, sQ, &dQ));
   uint32_t *dI = mem == MGPU_DEVICE ? out_ids : sI;
   float *dV = mem == MGPU_DEVICE ? out_dist : (out_dist ? sV : nullptr);
-  MGPU_TRY(ivf_coarse_dev(ivf, (const float *)dQ, B, nprobe, dD, dI, dV, xws));
+  MGPU_TRY(ivf_coarse_dev(ivf, (const float *)dQ, B, nprobe, dD, dI, dV, xws, 1));
   MGPU_TRY(stage_out(ctx, out_ids, dI, bI, mem));
   MGPU_TRY(stage_out(ctx, out_dist, dV, bI, mem));
   if (mem == MGPU_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -472,7 +481,8 @@ int mgpu_ivf_coarse(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t nprobe, 
 // scan + finalize on device buffers
 static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32_t *d_probes, uint32_t max_probes,
                         const uint32_t *d_counts, uint32_t k, uint8_t *d_qcodes, uint64_t *d_ckey, uint32_t *d_cslot,
-                        uint32_t *d_order, uint32_t *d_out_pids, mgpu_u128 *d_out_docs, float *d_out_scores, uint32_t *d_out_counts) {
+                        uint32_t *d_order, uint32_t *d_out_pids, mgpu_u128 *d_out_docs, float *d_out_scores, uint32_t *d_out_counts,
+                        bool qcodes_on_aux = false, const uint32_t *d_filter = nullptr, uint64_t filter_stride = 0) {
   mgpu_ctx *ctx = ivf->ctx;
   CUDA_TRY(ctx, cudaMemsetAsync(ivf->d_scan_rows, 0, 8, ctx->stream));
   ScanArgs a;
@@ -483,11 +493,13 @@ static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32
   a.Q = dQ; a.B = B; a.probes = d_probes; a.max_probes = max_probes; a.probe_counts = d_counts;
   a.cand_key = d_ckey; a.cand_slot = d_cslot; a.rows_scanned = ivf->d_scan_rows; a.next_query = (unsigned int *)(ivf->d_scan_rows + 1);
   a.metric = ivf->metric;
+  a.filter = d_filter; a.filter_stride = filter_stride;
   if (ivf->quant == MGPU_QUANT_PQ) {
     mgpu_pq *pq = ivf->pq;
     a.m = pq->m; a.K = pq->K; a.table = pq->d_table; a.rowmin = pq->d_rowmin; a.rowmax = pq->d_rowmax;
     // the query is quantized with the same codebook (index.rs:193) -- once per query here, not once per list
-    MGPU_TRY(launch_pq_quantize(pq, dQ, B, d_qcodes));
+    if (qcodes_on_aux) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // encoded on the side stream
+    else MGPU_TRY(launch_pq_quantize(pq, dQ, B, d_qcodes));
     a.qcodes = d_qcodes;
   }
   // longest-first query schedule for the persistent scan CTAs (MGPU_PLAN=0 disables it)
@@ -512,7 +524,8 @@ static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32
 // shared implementation of scan / scan_remap / search
 static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint32_t *probe_ids, uint32_t max_probes,
                            const uint32_t *probe_counts, uint32_t nprobe_coarse, uint32_t k, uint32_t *out_pids,
-                           mgpu_u128 *out_docs, float *out_scores, uint32_t *out_counts, int mem) {
+                           mgpu_u128 *out_docs, float *out_scores, uint32_t *out_counts, int mem,
+                           const uint32_t *filter_bits = nullptr, uint64_t filter_stride = 0) {
   mgpu_ctx *ctx = ivf->ctx;
   const bool do_coarse = probe_ids == nullptr;
   if (do_coarse) {
@@ -531,6 +544,10 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
     return MGPU_OK;
   }
   if (max_probes == 0) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "search: max_probes == 0");
+  const uint64_t fwords = (ivf->n + 31) / 32;
+  if (filter_bits && filter_stride != 0 && filter_stride < fwords)
+    return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "search: filter stride %llu < %llu words per bitmap", (unsigned long long)filter_stride, (unsigned long long)fwords);
+  const size_t bF = filter_bits && mem == MGPU_HOST ? (filter_stride ? (size_t)B * filter_stride : (size_t)fwords) * 4 : 0;
   const uint32_t m = ivf->pq ? ivf->pq->m : 0;
   size_t bQ = (size_t)B * ivf->dim * 4, bP = (size_t)B * max_probes * 4;
   size_t need = 0;
@@ -547,6 +564,7 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
   need = ws_need(need, (size_t)B * k * 4);                    // out scores
   need = ws_need(need, (size_t)B * 4);                        // out counts
   need = ws_need(need, do_coarse ? ivf_coarse_extra_ws(ivf, B) : 0);
+  need = ws_need(need, bF);                                   // planner filter bitmaps
   MGPU_TRY(mgpu_ws_reserve(ctx, need));
   WsAlloc w(ctx->ws, ctx->ws_bytes);
   float *sQ = w.get<float>((size_t)B * ivf->dim);
@@ -562,12 +580,25 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
   float *sScores = w.get<float>((size_t)B * k);
   uint32_t *sCounts = w.get<uint32_t>(B);
   uint8_t *xws = w.get<uint8_t>(do_coarse ? ivf_coarse_extra_ws(ivf, B) : 0);
+  uint32_t *sF = w.get<uint32_t>(bF / 4);
 
   const void *dQ;
   MGPU_TRY(stage_in(ctx, Q, bQ, mem, sQ, &dQ));
+  const uint32_t *dF = filter_bits;
+  if (bF) { const void *t; MGPU_TRY(stage_in(ctx, filter_bits, bF, mem, sF, &t)); dF = (const uint32_t *)t; }
   const uint32_t *dP, *dPC = nullptr;
+  bool qcodes_on_aux = false;
   if (do_coarse) {
-    MGPU_TRY(ivf_coarse_dev(ivf, (const float *)dQ, B, nprobe_coarse, dD, sP, nullptr, xws));
+    // the query encode (index.rs:193) does not depend on the coarse scoring: run it on the side stream meanwhile
+    static const bool use_aux = !(getenv("MGPU_AUX_STREAM") && getenv("MGPU_AUX_STREAM")[0] == '0');
+    if (use_aux && ivf->quant == MGPU_QUANT_PQ) {
+      CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+      MGPU_TRY(launch_pq_quantize(ivf->pq, (const float *)dQ, B, dQC, ctx->aux_stream));
+      CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+      qcodes_on_aux = true;
+    }
+    MGPU_TRY(ivf_coarse_dev(ivf, (const float *)dQ, B, nprobe_coarse, dD, sP, nullptr, xws, 0));
     dP = sP;
   } else {
     const void *t;
@@ -579,7 +610,7 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
   mgpu_u128 *oD = out_docs ? (mem == MGPU_DEVICE ? out_docs : sDocs) : nullptr;
   float *oS = mem == MGPU_DEVICE ? out_scores : sScores;
   uint32_t *oC = mem == MGPU_DEVICE ? out_counts : sCounts;
-  MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, dP, max_probes, dPC, k, dQC, dCK, dCS, dOrd, oP, oD, oS, oC));
+  MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, dP, max_probes, dPC, k, dQC, dCK, dCS, dOrd, oP, oD, oS, oC, qcodes_on_aux, dF, filter_stride));
   if (mem == MGPU_HOST) {
     MGPU_TRY(stage_out(ctx, out_pids, oP, (size_t)B * k * 4, mem));
     MGPU_TRY(stage_out(ctx, out_docs, oD, (size_t)B * k * 16, mem));
@@ -624,6 +655,24 @@ int mgpu_ivf_search(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint3
                     float *out_scores, uint32_t *out_counts, int mem) {
   if (!ivf) return MGPU_ERR_INVALID_ARG;
   return ivf_search_impl(ivf, Q, B, nullptr, 0, nullptr, nprobe, k, nullptr, out_doc_ids, out_scores, out_counts, mem);
+}
+
+/* Planner filter hook (index.rs:212-226): BlockBasedIvf::search with Some(planner). */
+int mgpu_ivf_search_filtered(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, const uint32_t *filter_bits,
+                             uint64_t filter_stride_words, mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, int mem) {
+  if (!ivf) return MGPU_ERR_INVALID_ARG;
+  return ivf_search_impl(ivf, Q, B, nullptr, 0, nullptr, nprobe, k, nullptr, out_doc_ids, out_scores, out_counts, mem, filter_bits,
+                         filter_stride_words);
+}
+
+int mgpu_ivf_scan_remap_filtered(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint32_t *probe_ids, uint32_t max_probes,
+                                 const uint32_t *probe_counts, uint32_t k, const uint32_t *filter_bits, uint64_t filter_stride_words,
+                                 mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, int mem) {
+  if (!ivf) return MGPU_ERR_INVALID_ARG;
+  if (B && !probe_ids) return mgpu_fail(ivf->ctx, MGPU_ERR_INVALID_ARG, "ivf_scan_remap_filtered: null probe list");
+  MGPU_TRY(check_probes_host(ivf, probe_ids, B, max_probes, probe_counts, mem));
+  return ivf_search_impl(ivf, Q, B, probe_ids, max_probes, probe_counts, 0, k, nullptr, out_doc_ids, out_scores, out_counts, mem,
+                         filter_bits, filter_stride_words);
 }
 
 // ---- build-time assignment -----------------------------------------------------------------------------------------------
@@ -949,9 +998,9 @@ __global__ void k_spann_mark_none(const uint32_t *__restrict__ ccounts, uint32_t
   if (b < B && ccounts[b] == 0) out_counts[b] = 0xFFFFFFFFu;
 }
 
-int mgpu_spann_search(mgpu_spann *sp, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef,
-                      uint32_t num_explored_centroids, float ratio, mgpu_u128 *out_doc_ids, float *out_scores,
-                      uint32_t *out_counts, int mem) {
+static int spann_search_impl(mgpu_spann *sp, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef,
+                             uint32_t num_explored_centroids, float ratio, const uint32_t *filter_bits, uint64_t filter_stride,
+                             mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, int mem) {
   if (!sp) return MGPU_ERR_INVALID_ARG;
   mgpu_ctx *ctx = sp->ctx;
   mgpu_ivf *ivf = sp->lists;
@@ -968,7 +1017,12 @@ int mgpu_spann_search(mgpu_spann *sp, const float *Q, uint32_t B, uint32_t top_k
   }
   const uint32_t k = std::max<uint32_t>(top_k, 1);
   const uint32_t m = ivf->pq ? ivf->pq->m : 0;
+  const uint64_t fwords = (ivf->n + 31) / 32;
+  if (filter_bits && filter_stride != 0 && filter_stride < fwords)
+    return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "spann_search: filter stride smaller than one bitmap");
+  const size_t bF = filter_bits && mem == MGPU_HOST ? (filter_stride ? (size_t)B * filter_stride : (size_t)fwords) * 4 : 0;
   size_t need = 0;
+  need = ws_need(need, bF);
   need = ws_need(need, (size_t)B * ivf->dim * 4);
   need = ws_need(need, (size_t)B * ne * 16); need = ws_need(need, (size_t)B * ne * 4); need = ws_need(need, (size_t)B * 4);
   need = ws_need(need, (size_t)B * ne * 4); need = ws_need(need, (size_t)B * 4);
@@ -976,6 +1030,9 @@ int mgpu_spann_search(mgpu_spann *sp, const float *Q, uint32_t B, uint32_t top_k
   need = ws_need(need, (size_t)B * k * 16); need = ws_need(need, (size_t)B * k * 4); need = ws_need(need, (size_t)B * 4);
   MGPU_TRY(mgpu_ws_reserve(ctx, need));
   WsAlloc w(ctx->ws, ctx->ws_bytes);
+  uint32_t *sF = w.get<uint32_t>(bF / 4);
+  const uint32_t *dF = filter_bits;
+  if (bF) { const void *t; MGPU_TRY(stage_in(ctx, filter_bits, bF, mem, sF, &t)); dF = (const uint32_t *)t; }
   float *sQ = w.get<float>((size_t)B * ivf->dim);
   mgpu_u128 *cD = w.get<mgpu_u128>((size_t)B * ne); float *cS = w.get<float>((size_t)B * ne); uint32_t *cC = w.get<uint32_t>(B);
   uint32_t *pr = w.get<uint32_t>((size_t)B * ne); uint32_t *pc = w.get<uint32_t>(B);
@@ -996,7 +1053,7 @@ int mgpu_spann_search(mgpu_spann *sp, const float *Q, uint32_t B, uint32_t top_k
   float *oS = mem == MGPU_DEVICE ? out_scores : sS;
   uint32_t *oC = mem == MGPU_DEVICE ? out_counts : sC;
   if (top_k == 0) CUDA_TRY(ctx, cudaMemsetAsync(oC, 0, (size_t)B * 4, ctx->stream));
-  else MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, pr, ne, pc, top_k, dQC, dCK, dCS, nullptr, nullptr, oD, oS, oC));
+  else MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, pr, ne, pc, top_k, dQC, dCK, dCS, nullptr, nullptr, oD, oS, oC, false, dF, filter_stride));
   {
     LaunchScope ls(ctx, MGPU_K_OTHER);
     k_spann_mark_none<<<(B + 127) / 128, 128, 0, ctx->stream>>>(cC, B, oC);
@@ -1009,6 +1066,21 @@ int mgpu_spann_search(mgpu_spann *sp, const float *Q, uint32_t B, uint32_t top_k
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return MGPU_OK;
+}
+
+int mgpu_spann_search(mgpu_spann *sp, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef,
+                      uint32_t num_explored_centroids, float ratio, mgpu_u128 *out_doc_ids, float *out_scores,
+                      uint32_t *out_counts, int mem) {
+  return spann_search_impl(sp, Q, B, top_k, ef, num_explored_centroids, ratio, nullptr, 0, out_doc_ids, out_scores, out_counts, mem);
+}
+
+/* Spann::search with Some(planner): the filter reaches the posting-list scan (spann/index.rs:253-263). */
+int mgpu_spann_search_filtered(mgpu_spann *sp, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef,
+                               uint32_t num_explored_centroids, float ratio, const uint32_t *filter_bits,
+                               uint64_t filter_stride_words, mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts,
+                               int mem) {
+  return spann_search_impl(sp, Q, B, top_k, ef, num_explored_centroids, ratio, filter_bits, filter_stride_words, out_doc_ids,
+                           out_scores, out_counts, mem);
 }
 
 }  // extern "C"

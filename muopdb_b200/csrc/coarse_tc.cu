@@ -190,50 +190,71 @@ k_coarse_gemm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 }
 
 // ---- selection with a provable margin + exact re-score -------------------------------------------------------------------
-// One CTA per query.  smem: keys[C] (ordered keys of D~), hist[256], cand[<= C] indices, exact key64 list.
+// One CTA per query.  Let d_c be the reference's fp32 squared distance, D~_c the tensor-core value, |D~_c - d_c| <= eps,
+// tau the nprobe-th smallest D~ and [lo, hi] a key interval known to contain tau (a 22-bit radix bin).  Then
+//   * D~_c < lo - 2 eps  =>  d_c < tau - eps <= d_(nprobe): c is in EVERY valid answer ("sure");
+//   * every member of the answer has D~_c <= tau + 2 eps <= hi + 2 eps ("band" = the rest of those).
+// need_order != 0 (mgpu_ivf_coarse: nearest-first ids + distances): every centroid with D~ <= hi + 2 eps is re-scored with
+// the bit-faithful sqrt-L2 and ordered by (distance, index) -- identical to the exact path.
+// need_order == 0 (search: the result of scanning a probe SET does not depend on its order, index.rs:265-274): sure
+// centroids are emitted directly, only the band is re-scored and its (nprobe - #sure) nearest complete the set.
+// smem: ckey[cap] (u64; its first C words double as the radix keys until the band is known), cand[cap], query, hist.
 #define SEL_THREADS 512
-__global__ void __launch_bounds__(SEL_THREADS)
+#define SEL_BINS 2048
+__device__ __forceinline__ float sel_key2f(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k); }
+
+__global__ void __launch_bounds__(SEL_THREADS, 3)
 k_coarse_select(const float *__restrict__ Dt, const float *__restrict__ Q, const float *__restrict__ centroids,
                 const float *__restrict__ qn, float cn_max, uint32_t C, uint32_t dim, uint32_t nprobe, uint32_t cand_cap,
-                uint32_t *__restrict__ out_ids, float *__restrict__ out_dist, uint32_t *__restrict__ overflow) {
+                int need_order, uint32_t *__restrict__ out_ids, float *__restrict__ out_dist, uint32_t *__restrict__ overflow,
+                const uint32_t *__restrict__ only_flagged) {
+  if (only_flagged && !only_flagged[blockIdx.x]) return;  // fallback launch: queries the warp kernel could not finish
   extern __shared__ __align__(16) uint8_t sm[];
-  uint32_t *keys = (uint32_t *)sm;                 // C
-  float *sq = (float *)(keys + C);                 // dim (16-byte aligned: C % 4 == 0 is required by the launcher)
-  uint64_t *ckey = (uint64_t *)(sq + ((dim + 3) & ~3u));  // cand_cap (power of two)
+  uint64_t *ckey = (uint64_t *)sm;                 // cand_cap (power of two >= C)
+  uint32_t *keys = (uint32_t *)sm;                 // C, aliases ckey: dead before the first ckey store
   uint32_t *cand = (uint32_t *)(ckey + cand_cap);  // cand_cap
-  uint32_t *hist = cand + cand_cap;                // 256
-  uint32_t *misc = hist + 256;                     // [0] prefix, [1] remaining rank, [2] candidate count
+  float *sq = (float *)(cand + cand_cap);          // dim
+  uint32_t *hist = (uint32_t *)(sq + ((dim + 3) & ~3u));  // SEL_BINS
+  uint32_t *misc = hist + SEL_BINS;                // [0] bin, [1] remaining rank, [2] band count, [3] sure count, [4] kmin, [5] kmax
   const uint32_t q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float *row = Dt + (size_t)q * C;
-  for (uint32_t i = tid; i < C; i += SEL_THREADS) keys[i] = f2key(row[i]);
+  uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+  for (uint32_t i = tid; i < C / 4; i += SEL_THREADS) {  // C % 4 == 0 (launcher)
+    const float4 v = __ldg((const float4 *)row + i);
+    uint4 k4 = make_uint4(f2key(v.x), f2key(v.y), f2key(v.z), f2key(v.w));
+    ((uint4 *)keys)[i] = k4;
+    kmin = min(min(kmin, k4.x), min(k4.y, min(k4.z, k4.w)));
+    kmax = max(max(kmax, k4.x), max(k4.y, max(k4.z, k4.w)));
+  }
   for (uint32_t d = tid; d < dim; d += SEL_THREADS) sq[d] = Q[(size_t)q * dim + d];
-  if (tid == 0) { misc[0] = 0; misc[1] = nprobe - 1; misc[2] = 0; }
+  for (int i = tid; i < SEL_BINS; i += SEL_THREADS) hist[i] = 0;
+  if (tid == 0) { misc[0] = 0; misc[1] = nprobe - 1; misc[2] = 0; misc[3] = 0; misc[4] = 0xFFFFFFFFu; misc[5] = 0u; }
   __syncthreads();
-  // radix select (MSB first, 8 bits per pass) of the key with rank nprobe-1.  Keys cluster in a few bins, so increments are
-  // aggregated per warp with match_any (one shared-memory atomic per distinct bin per warp instruction) and the bin scan is
-  // a warp-parallel prefix sum.
-  for (int pass = 0; pass < 4; pass++) {
-    const int shift = 24 - 8 * pass;
-    for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
-    __syncthreads();
-    const uint32_t prefix = misc[0];
-    const uint32_t mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
-    for (uint32_t i0 = 0; i0 < C; i0 += SEL_THREADS) {
-      const uint32_t i = i0 + tid;
-      uint32_t bin = 0xFFFFu;  // "not a candidate of this pass"
-      if (i < C) {
-        uint32_t k = keys[i];
-        if ((k & mask) == prefix) bin = (k >> shift) & 255u;
-      }
-      const unsigned grp = __match_any_sync(0xffffffffu, bin);
-      if (bin != 0xFFFFu && lane == __ffs(grp) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(grp));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+  }
+  if (lane == 0) { atomicMin(&misc[4], kmin); atomicMax(&misc[5], kmax); }
+  __syncthreads();
+  // two-level histogram over the query's OWN key range [kmin, kmax] (keys are monotone in the distance): level 1 splits
+  // the range into <= 2048 equal key intervals, level 2 splits the interval holding rank nprobe-1 again.  The result is a
+  // key interval [lo_key, hi_key] of width range / 2^22 (or a single key) that contains tau.
+  uint32_t base = misc[4];
+  uint32_t width_log = 32 - __clz((misc[5] - base) | 1u);          // bits needed for (k - base)
+  uint32_t lo_key = base, hi_key = misc[5];
+  for (int pass = 0; pass < 2; pass++) {
+    const uint32_t shift = width_log > 11 ? width_log - 11 : 0;      // bin = (k - base) >> shift  in [0, 2048)
+    for (uint32_t i = tid; i < C; i += SEL_THREADS) {
+      const uint32_t k = keys[i];
+      if (k >= lo_key && k <= hi_key) atomicAdd(&hist[(k - base) >> shift], 1u);
     }
     __syncthreads();
     if (warp == 0) {
-      uint32_t loc[8], sum = 0;
-#pragma unroll
-      for (int j = 0; j < 8; j++) { loc[j] = hist[lane * 8 + j]; sum += loc[j]; }
+      constexpr int PER = SEL_BINS / 32;
+      uint32_t sum = 0;
+      for (int j = 0; j < PER; j++) sum += hist[lane * PER + j];
       uint32_t incl = sum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -242,48 +263,125 @@ k_coarse_select(const float *__restrict__ Dt, const float *__restrict__ Q, const
       }
       const uint32_t rank = misc[1];
       const uint32_t excl = incl - sum;
-      const bool mine = rank >= excl && rank < incl;  // exactly one lane
-      if (mine) {
-        uint32_t r = rank - excl, b = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) { if (r >= loc[j] && b == (uint32_t)j) { r -= loc[j]; b = j + 1; } }
-        misc[0] = prefix | ((uint32_t)(lane * 8 + b) << shift);
+      if (rank >= excl && rank < incl) {  // exactly one lane
+        uint32_t r = rank - excl;
+        int bb = 0;
+        for (; bb < PER - 1; bb++) { uint32_t h = hist[lane * PER + bb]; if (r < h) break; r -= h; }
+        misc[0] = (uint32_t)(lane * PER + bb);
         misc[1] = r;
       }
     }
     __syncthreads();
-  }
-  const uint32_t tau_key = misc[0];
-  // candidates: D~ <= tau + 2 eps   (eps bounds |D~ - reference fp32 squared distance|)
-  const uint32_t tk = (tau_key & 0x80000000u) ? (tau_key ^ 0x80000000u) : ~tau_key;
-  const float tau = __uint_as_float(tk);
-  const float eps = TC_ERR_REL * (qn[q] + cn_max);
-  const uint32_t lim_key = f2key(tau + 2.0f * eps);
-  for (uint32_t i = tid; i < C; i += SEL_THREADS) {
-    if (keys[i] <= lim_key) {
-      uint32_t pos = atomicAdd(&misc[2], 1u);
-      if (pos < cand_cap) cand[pos] = i;
+    const uint32_t bsel = misc[0];
+    lo_key = base + (bsel << shift);
+    hi_key = shift ? lo_key + ((1u << shift) - 1u) : lo_key;
+    if (shift == 0) break;
+    base = lo_key;
+    width_log = shift;
+    if (pass == 0) {
+      for (int i = tid; i < SEL_BINS; i += SEL_THREADS) hist[i] = 0;
+      __syncthreads();
     }
+  }
+  const float eps = TC_ERR_REL * (qn[q] + cn_max);
+  const uint32_t lim_hi = f2key(sel_key2f(hi_key) + 2.0f * eps);
+  const uint32_t lim_lo = need_order ? 0u : f2key(sel_key2f(lo_key) - 2.0f * eps);
+  // classification: sure (emitted right away, set-only mode) / band (to be re-scored)
+  for (uint32_t i0 = 0; i0 < C; i0 += SEL_THREADS) {
+    const uint32_t i = i0 + tid;
+    const uint32_t k = i < C ? keys[i] : 0xFFFFFFFFu;
+    const bool sure = i < C && k < lim_lo;
+    const bool band = i < C && !sure && k <= lim_hi;
+    const unsigned ms = __ballot_sync(0xffffffffu, sure), mb = __ballot_sync(0xffffffffu, band);
+    uint32_t bs = 0, bb = 0;
+    if (lane == 0) {
+      if (ms) bs = atomicAdd(&misc[3], (uint32_t)__popc(ms));
+      if (mb) bb = atomicAdd(&misc[2], (uint32_t)__popc(mb));
+    }
+    bs = __shfl_sync(0xffffffffu, bs, 0);
+    bb = __shfl_sync(0xffffffffu, bb, 0);
+    const unsigned below = (1u << lane) - 1;
+    if (sure) { uint32_t pos = bs + __popc(ms & below); if (pos < nprobe) out_ids[(size_t)q * nprobe + pos] = i; }
+    if (band) { uint32_t pos = bb + __popc(mb & below); if (pos < cand_cap) cand[pos] = i; }
   }
   __syncthreads();
   uint32_t ncand = misc[2];
+  const uint32_t nsure = min(misc[3], nprobe);
+  const uint32_t need = nprobe - nsure;
   if (ncand > cand_cap) { if (tid == 0) atomicAdd(overflow, 1u); ncand = cand_cap; }
-  // exact sqrt-L2 (l2.rs:30-74) for every candidate: half-warp per pair, lane h owns lane-accumulator h
-  const int h = lane & 15, half = lane >> 4;
-  const uint32_t npairs_round = (SEL_THREADS / 32) * 2;
-  for (uint32_t base = 0; base < ncand; base += npairs_round) {
-    uint32_t j = base + warp * 2 + half;
-    uint32_t jj = j < ncand ? j : ncand - 1;
-    const uint32_t cidx = cand[jj];
-    const float *crow = centroids + (size_t)cidx * dim;
-    const int n = (int)dim;
-    float ret = 0.0f;
-    int p = 0;
-    if (n / 16 > 0) {
+  if (!need_order && ncand <= need) {
+    // the whole band belongs to the answer: nothing to decide, nothing to re-score
+    for (uint32_t i = tid; i < ncand; i += SEL_THREADS) out_ids[(size_t)q * nprobe + nsure + i] = cand[i];
+    return;
+  }
+  // exact sqrt-L2 (l2.rs:30-74) for every band centroid
+  const int n = (int)dim;
+  if ((dim & 3u) == 0) {
+    // 4 lanes per pair: lane r of a group owns lane-accumulators 4r..4r+3 of the reference's 16 (float4 loads)
+    const int r = lane & 3, grp = lane >> 2;
+    const uint32_t per_round = (SEL_THREADS / 32) * 8;
+    for (uint32_t base = 0; base < ncand; base += per_round) {
+      if (base + warp * 8 >= ncand) continue;  // warp-uniform: nothing for this warp in this round
+      const uint32_t j = base + warp * 8 + grp;
+      const uint32_t jj = j < ncand ? j : ncand - 1;
+      const uint32_t cidx = cand[jj];
+      const float *crow = centroids + (size_t)cidx * dim;
+      const int chunks = n / 16;
+      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+      const float4 *c4 = (const float4 *)crow + r;
+      const float4 *q4 = (const float4 *)sq + r;
+      int c = 0;
+      for (; c + 4 <= chunks; c += 4) {
+        float4 y[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) y[u] = __ldg(c4 + (c + u) * 4);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const float4 x = q4[(c + u) * 4];
+          float d;
+          d = __fsub_rn(x.x, y[u].x); a0 = __fadd_rn(a0, __fmul_rn(d, d));
+          d = __fsub_rn(x.y, y[u].y); a1 = __fadd_rn(a1, __fmul_rn(d, d));
+          d = __fsub_rn(x.z, y[u].z); a2 = __fadd_rn(a2, __fmul_rn(d, d));
+          d = __fsub_rn(x.w, y[u].w); a3 = __fadd_rn(a3, __fmul_rn(d, d));
+        }
+      }
+      for (; c < chunks; c++) {
+        const float4 y = __ldg(c4 + c * 4), x = q4[c * 4];
+        float d;
+        d = __fsub_rn(x.x, y.x); a0 = __fadd_rn(a0, __fmul_rn(d, d));
+        d = __fsub_rn(x.y, y.y); a1 = __fadd_rn(a1, __fmul_rn(d, d));
+        d = __fsub_rn(x.z, y.z); a2 = __fadd_rn(a2, __fmul_rn(d, d));
+        d = __fsub_rn(x.w, y.w); a3 = __fadd_rn(a3, __fmul_rn(d, d));
+      }
+      float s2 = -0.0f;  // ordered lane reduction 0..15
+      const int gl = lane & ~3;
+#pragma unroll
+      for (int l = 0; l < 4; l++) {
+        s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, a0, gl + l));
+        s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, a1, gl + l));
+        s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, a2, gl + l));
+        s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, a3, gl + l));
+      }
+      float ret = __fadd_rn(0.0f, s2);
+      const int p = chunks * 16;
+      if (p < n) ret = ref_tail<MGPU_L2>(PtrAcc{sq}, PtrAcc{crow}, p, n, ret);
+      const float dist = sqrtf(ret);
+      if (j < ncand && r == 0) ckey[j] = ((uint64_t)f2key(dist) << 32) | cidx;
+    }
+  } else {
+    // half-warp per pair, lane h owns lane-accumulator h
+    const int h = lane & 15, half = lane >> 4;
+    const uint32_t per_round = (SEL_THREADS / 32) * 2;
+    for (uint32_t base = 0; base < ncand; base += per_round) {
+      if (base + warp * 2 >= ncand) continue;
+      const uint32_t j = base + warp * 2 + half;
+      const uint32_t jj = j < ncand ? j : ncand - 1;
+      const uint32_t cidx = cand[jj];
+      const float *crow = centroids + (size_t)cidx * dim;
       const int chunks = n / 16;
       float acc = 0.0f;
-#pragma unroll 16
-      for (int c = 0; c < chunks; c++) {  // 16 independent 64-byte row segments in flight per half-warp
+#pragma unroll 8
+      for (int c = 0; c < chunks; c++) {
         float d = __fsub_rn(sq[c * 16 + h], __ldg(crow + c * 16 + h));
         acc = __fadd_rn(acc, __fmul_rn(d, d));
       }
@@ -291,16 +389,31 @@ k_coarse_select(const float *__restrict__ Dt, const float *__restrict__ Q, const
       const int basel = lane & 16;
 #pragma unroll
       for (int l = 0; l < 16; l++) s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, acc, basel + l));
-      ret = __fadd_rn(ret, s2);
-      p = chunks * 16;
+      float ret = __fadd_rn(0.0f, s2);
+      const int p = chunks * 16;
+      if (p < n) ret = ref_tail<MGPU_L2>(PtrAcc{sq}, PtrAcc{crow}, p, n, ret);
+      const float dist = sqrtf(ret);
+      if (j < ncand && h == 0) ckey[j] = ((uint64_t)f2key(dist) << 32) | cidx;
     }
-    if (p < n) ret = ref_tail<MGPU_L2>(PtrAcc{sq}, PtrAcc{crow}, p, n, ret);
-    const float dist = sqrtf(ret);
-    if (j < ncand && h == 0) ckey[j] = ((uint64_t)f2key(dist) << 32) | cidx;
+  }
+  __syncthreads();
+  uint32_t *oi = out_ids + (size_t)q * nprobe + nsure;
+  float *od = out_dist ? out_dist + (size_t)q * nprobe + nsure : nullptr;
+  if (ncand <= 2048) {
+    // order by (distance total order, centroid index): rank by counting (keys are distinct: the index is part of the key)
+    for (uint32_t i = tid; i < ncand; i += SEL_THREADS) {
+      const uint64_t kk = ckey[i];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < ncand; j++) rank += ckey[j] < kk ? 1u : 0u;
+      if (rank < need) {
+        oi[rank] = (uint32_t)kk;
+        if (od) od[rank] = sel_key2f((uint32_t)(kk >> 32));
+      }
+    }
+    return;
   }
   for (uint32_t i = ncand + tid; i < cand_cap; i += SEL_THREADS) ckey[i] = MGPU_EMPTY_KEY;
   __syncthreads();
-  // order by (distance total order, centroid index): bitonic sort over the smallest power of two >= ncand
   uint32_t P2 = 1;
   while (P2 < ncand) P2 <<= 1;
   for (uint32_t k = 2; k <= P2; k <<= 1) {
@@ -316,12 +429,202 @@ k_coarse_select(const float *__restrict__ Dt, const float *__restrict__ Q, const
       __syncthreads();
     }
   }
-  for (uint32_t i = tid; i < nprobe; i += SEL_THREADS) {
+  for (uint32_t i = tid; i < need; i += SEL_THREADS) {
     uint64_t kk = ckey[i];
-    out_ids[(size_t)q * nprobe + i] = (uint32_t)kk;
-    if (out_dist) {
-      uint32_t kd = (uint32_t)(kk >> 32);
-      out_dist[(size_t)q * nprobe + i] = __uint_as_float((kd & 0x80000000u) ? (kd ^ 0x80000000u) : ~kd);
+    oi[i] = (uint32_t)kk;
+    if (od) od[i] = sel_key2f((uint32_t)(kk >> 32));
+  }
+}
+
+// ---- warp-per-query selection (the fast path) --------------------------------------------------------------------------------
+// Same rule as k_coarse_select, but one WARP owns a query and there are no CTA barriers.  The D~ row (C <= 4096 values) is
+// pulled into a private slice of shared memory with ONE burst of cp.async (every 16-byte piece in flight at once),
+// converted to ordered keys in place, and all later passes (range, two histogram levels, classification) run at
+// shared-memory speed.  Sure centroids are emitted in ascending D~ order (the scan prunes best when the nearest lists come
+// first), the band is re-scored exactly and appended.  Queries whose band does not fit the private lists are flagged and
+// finished by k_coarse_select.
+#define SELW_WARPS 4
+#define SELW_CAP 256
+#define SELW_MAXC 4096
+#define SELW_BINS 1024
+#define SELW_BYTES (SELW_MAXC * 4 + SELW_BINS * 4 + SELW_CAP * 8 + SELW_CAP * 8 + SELW_CAP * 4 + 16)
+#define SELW_MLP 16
+__device__ __forceinline__ void selw_cp_async16(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void selw_cp_async_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(SELW_WARPS * 32)
+k_coarse_select_warp(const float *__restrict__ Dt, const float *__restrict__ Q, const float *__restrict__ centroids,
+                     const float *__restrict__ qn, float cn_max, uint32_t B, uint32_t C, uint32_t dim, uint32_t nprobe,
+                     int need_order, uint32_t *__restrict__ out_ids, float *__restrict__ out_dist, uint32_t *__restrict__ flags) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t q = blockIdx.x * SELW_WARPS + w;
+  if (q >= B) return;
+  uint8_t *my = sm + (size_t)w * SELW_BYTES;
+  uint32_t *keys = (uint32_t *)my;                       // C ordered keys (first the raw floats)
+  uint32_t *hist = keys + SELW_MAXC;                     // SELW_BINS
+  uint64_t *skey = (uint64_t *)(hist + SELW_BINS);       // SELW_CAP: (approximate key, index) of the sure centroids
+  uint64_t *ckey = skey + SELW_CAP;                      // SELW_CAP: (exact key, index) of the band
+  uint32_t *cand = (uint32_t *)(ckey + SELW_CAP);        // SELW_CAP: band indices
+  uint32_t *cnt = cand + SELW_CAP;                       // [0] sure, [1] band
+  const float4 *row4 = (const float4 *)(Dt + (size_t)q * C);
+  const uint32_t C4 = C / 4;
+  // ---- the row, one burst
+  for (uint32_t i = lane; i < C4; i += 32) selw_cp_async16((uint4 *)keys + i, row4 + i);
+  selw_cp_async_wait();
+  // ---- keys in place + key range
+  uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+#pragma unroll 4
+  for (uint32_t i = lane; i < C4; i += 32) {
+    const float4 v = ((const float4 *)keys)[i];
+    const uint4 k4 = make_uint4(f2key(v.x), f2key(v.y), f2key(v.z), f2key(v.w));
+    ((uint4 *)keys)[i] = k4;
+    kmin = min(min(kmin, k4.x), min(k4.y, min(k4.z, k4.w)));
+    kmax = max(max(kmax, k4.x), max(k4.y, max(k4.z, k4.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+  }
+  // ---- two histogram levels over [kmin, kmax]: the key interval [lo_key, hi_key] of width range / 2^20 holding tau
+  uint32_t base = kmin, width_log = 32 - __clz((kmax - kmin) | 1u);
+  uint32_t lo_key = kmin, hi_key = kmax, rank = nprobe - 1;
+  for (int pass = 0; pass < 2; pass++) {
+    const uint32_t shift = width_log > 10 ? width_log - 10 : 0;
+    for (int i = lane; i < SELW_BINS / 4; i += 32) ((uint4 *)hist)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+#pragma unroll 4
+    for (uint32_t i = lane; i < C4; i += 32) {
+      const uint4 k4 = ((const uint4 *)keys)[i];
+      if (k4.x >= lo_key && k4.x <= hi_key) atomicAdd(&hist[(k4.x - base) >> shift], 1u);
+      if (k4.y >= lo_key && k4.y <= hi_key) atomicAdd(&hist[(k4.y - base) >> shift], 1u);
+      if (k4.z >= lo_key && k4.z <= hi_key) atomicAdd(&hist[(k4.z - base) >> shift], 1u);
+      if (k4.w >= lo_key && k4.w <= hi_key) atomicAdd(&hist[(k4.w - base) >> shift], 1u);
+    }
+    __syncwarp();
+    // lane l owns bins [32 l, 32 l + 32); rotated read order keeps the 32 lanes on 32 different banks
+    constexpr int PER = SELW_BINS / 32;
+    uint32_t sum = 0;
+#pragma unroll 8
+    for (int j = 0; j < PER; j++) sum += hist[lane * PER + ((j + lane) & (PER - 1))];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t excl = incl - sum;
+    const bool mine = rank >= excl && rank < incl;  // exactly one lane
+    uint32_t bsel = 0, rr = 0;
+    if (mine) {
+      rr = rank - excl;
+      int bb = 0;
+      for (; bb < PER - 1; bb++) { uint32_t h = hist[lane * PER + bb]; if (rr < h) break; rr -= h; }
+      bsel = (uint32_t)(lane * PER + bb);
+    }
+    const int owner = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+    bsel = __shfl_sync(0xffffffffu, bsel, owner);
+    rank = __shfl_sync(0xffffffffu, rr, owner);
+    lo_key = base + (bsel << shift);
+    hi_key = shift ? lo_key + ((1u << shift) - 1u) : lo_key;
+    if (shift == 0) break;
+    base = lo_key;
+    width_log = shift;
+  }
+  if (lane == 0) { cnt[0] = 0; cnt[1] = 0; }
+  __syncwarp();
+  const float eps = TC_ERR_REL * (qn[q] + cn_max);
+  const uint32_t lim_hi = f2key(sel_key2f(hi_key) + 2.0f * eps);
+  const uint32_t lim_lo = need_order ? 0u : f2key(sel_key2f(lo_key) - 2.0f * eps);
+  // ---- classification (hits are rare: plain shared-memory counters)
+#pragma unroll 4
+  for (uint32_t i = lane; i < C4; i += 32) {
+    const uint4 k4 = ((const uint4 *)keys)[i];
+    const uint32_t kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      if (kk[c] < lim_lo) {
+        const uint32_t pos = atomicAdd(&cnt[0], 1u);
+        if (pos < SELW_CAP) skey[pos] = ((uint64_t)kk[c] << 32) | (4 * i + c);
+      } else if (kk[c] <= lim_hi) {
+        const uint32_t pos = atomicAdd(&cnt[1], 1u);
+        if (pos < SELW_CAP) cand[pos] = 4 * i + c;
+      }
+    }
+  }
+  __syncwarp();
+  const uint32_t nsure = min(cnt[0], nprobe);   // <= nprobe - 1 by construction
+  const uint32_t ncand = cnt[1];
+  if (ncand > SELW_CAP || nsure > SELW_CAP) {   // does not fit the private lists: k_coarse_select finishes this query
+    if (lane == 0) flags[q] = 1u;
+    return;
+  }
+  const uint32_t need = nprobe - nsure;
+  uint32_t *oi = out_ids + (size_t)q * nprobe;
+  // sure centroids, ascending approximate distance (rank by counting; keys are distinct)
+  for (uint32_t e = lane; e < nsure; e += 32) {
+    const uint64_t kk = skey[e];
+    uint32_t r = 0;
+    for (uint32_t j = 0; j < nsure; j++) r += skey[j] < kk ? 1u : 0u;
+    oi[r] = (uint32_t)kk;
+  }
+  if (!need_order && ncand <= need) {  // the whole band belongs to the answer
+    for (uint32_t e = lane; e < ncand; e += 32) oi[nsure + e] = cand[e];
+    return;
+  }
+  // ---- exact sqrt-L2 (l2.rs:30-74) of the band: 4 lanes per pair, lane r owns lane-accumulators 4r..4r+3.
+  // cp.async (no register destination) keeps SELW_MLP 16-byte centroid loads in flight per lane -- a plain load is
+  // scheduled next to its use, which turns the loop into a chain of L2 round trips.  The ring re-uses the key space.
+  const int n = (int)dim, chunks = n / 16;
+  const int r4 = lane & 3, grp = lane >> 2, gl = lane & ~3;
+  const float4 *q4 = (const float4 *)(Q + (size_t)q * dim) + r4;
+  float4 *ring = (float4 *)keys;
+  __syncwarp();
+  for (uint32_t b0 = 0; b0 < ncand; b0 += 8) {
+    const uint32_t j = b0 + grp;
+    const uint32_t cidx = cand[j < ncand ? j : ncand - 1];
+    const float *crow = centroids + (size_t)cidx * dim;
+    const float4 *c4 = (const float4 *)crow + r4;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    for (int c = 0; c < chunks; c += SELW_MLP) {
+      const int nb = min(SELW_MLP, chunks - c);
+      for (int u = 0; u < nb; u++) selw_cp_async16(&ring[u * 32 + lane], c4 + (c + u) * 4);
+      selw_cp_async_wait();
+      for (int u = 0; u < nb; u++) {
+        const float4 x = __ldg(q4 + (c + u) * 4), y = ring[u * 32 + lane];
+        float d;
+        d = __fsub_rn(x.x, y.x); a0 = __fadd_rn(a0, __fmul_rn(d, d));
+        d = __fsub_rn(x.y, y.y); a1 = __fadd_rn(a1, __fmul_rn(d, d));
+        d = __fsub_rn(x.z, y.z); a2 = __fadd_rn(a2, __fmul_rn(d, d));
+        d = __fsub_rn(x.w, y.w); a3 = __fadd_rn(a3, __fmul_rn(d, d));
+      }
+    }
+    float s2 = -0.0f;  // ordered lane reduction 0..15
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, a0, gl + l));
+      s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, a1, gl + l));
+      s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, a2, gl + l));
+      s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, a3, gl + l));
+    }
+    float ret = __fadd_rn(0.0f, s2);
+    const int p = chunks * 16;
+    if (p < n) ret = ref_tail<MGPU_L2>(PtrAcc{Q + (size_t)q * dim}, PtrAcc{crow}, p, n, ret);
+    const float dist = sqrtf(ret);
+    if (j < ncand && r4 == 0) ckey[j] = ((uint64_t)f2key(dist) << 32) | cidx;
+  }
+  __syncwarp();
+  float *od = out_dist ? out_dist + (size_t)q * nprobe + nsure : nullptr;
+  for (uint32_t e = lane; e < ncand; e += 32) {
+    const uint64_t kk = ckey[e];
+    uint32_t r = 0;
+    for (uint32_t j = 0; j < ncand; j++) r += ckey[j] < kk ? 1u : 0u;
+    if (r < need) {
+      oi[nsure + r] = (uint32_t)kk;
+      if (od) od[r] = sel_key2f((uint32_t)(kk >> 32));
     }
   }
 }
@@ -364,7 +667,7 @@ bool coarse_tc_applicable(mgpu_ctx *ctx, uint32_t dim, uint32_t C, uint32_t npro
   // the candidate buffers are sized for ALL centroids, so the margin rule can never overflow them
   size_t cap = 1;
   while (cap < (size_t)C) cap <<= 1;
-  size_t smem = (size_t)C * 4 + ((dim + 3) & ~3u) * 4 + cap * 12 + 1024 + 64;
+  size_t smem = ((dim + 3) & ~3u) * 4 + cap * 12 + SEL_BINS * 4 + 64;
   if (smem > ctx->smem_optin || nprobe > C) return false;
   if (mode == 2) return true;
   return C >= 1024 && dim >= 64;
@@ -381,7 +684,7 @@ int launch_split_bf16(mgpu_ctx *ctx, const float *dX, uint64_t n, uint32_t dim, 
 // d_Dt: B x C floats of workspace; d_qsplit: B x Kp bf16; d_qn: B floats
 int launch_coarse_tc(mgpu_ctx *ctx, const float *dQ, uint32_t B, const float *d_centroids, const void *d_csplit, const float *d_cn,
                      float cn_max, uint32_t C, uint32_t dim, uint32_t nprobe, void *d_qsplit, float *d_qn, float *d_Dt,
-                     uint32_t *d_overflow, uint32_t *out_ids, float *out_dist) {
+                     uint32_t *d_overflow, uint32_t *d_flags, int need_order, uint32_t *out_ids, float *out_dist) {
   const uint32_t Kp = coarse_tc_kp(dim);
   MGPU_TRY(launch_split_bf16(ctx, dQ, B, dim, 0, d_qsplit, d_qn));
   CUtensorMap mq, mc;
@@ -397,12 +700,26 @@ int launch_coarse_tc(mgpu_ctx *ctx, const float *dQ, uint32_t B, const float *d_
   }
   uint32_t cap = 1;
   while (cap < C) cap <<= 1;
-  size_t ssel = (size_t)C * 4 + ((dim + 3) & ~3u) * 4 + (size_t)cap * 12 + 1024 + 64;
+  size_t ssel = ((dim + 3) & ~3u) * 4 + (size_t)cap * 12 + SEL_BINS * 4 + 64;
+  static const bool force_order = getenv("MGPU_COARSE_ORDER") && getenv("MGPU_COARSE_ORDER")[0] == '1';
+  if (force_order || out_dist) need_order = 1;
   CUDA_TRY(ctx, cudaFuncSetAttribute(k_coarse_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssel));
+  static const bool no_warp = getenv("MGPU_SELECT_WARP") && getenv("MGPU_SELECT_WARP")[0] == '0';
+  const uint32_t *only_flagged = nullptr;
+  if (!no_warp && (dim & 3u) == 0 && nprobe <= SELW_CAP && C <= SELW_MAXC && d_flags) {
+    CUDA_TRY(ctx, cudaMemsetAsync(d_flags, 0, (size_t)B * 4, ctx->stream));
+    const size_t sw = (size_t)SELW_WARPS * SELW_BYTES;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_coarse_select_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw));
+    LaunchScope ls(ctx, MGPU_K_SELECT);
+    k_coarse_select_warp<<<(B + SELW_WARPS - 1) / SELW_WARPS, SELW_WARPS * 32, sw, ctx->stream>>>(
+        d_Dt, dQ, d_centroids, d_qn, cn_max, B, C, dim, nprobe, need_order, out_ids, out_dist, d_flags);
+    CUDA_TRY(ctx, cudaGetLastError());
+    only_flagged = d_flags;
+  }
   {
     LaunchScope ls(ctx, MGPU_K_SELECT);
-    k_coarse_select<<<B, SEL_THREADS, ssel, ctx->stream>>>(d_Dt, dQ, d_centroids, d_qn, cn_max, C, dim, nprobe, cap, out_ids, out_dist,
-                                                            d_overflow);
+    k_coarse_select<<<B, SEL_THREADS, ssel, ctx->stream>>>(d_Dt, dQ, d_centroids, d_qn, cn_max, C, dim, nprobe, cap, need_order, out_ids,
+                                                            out_dist, d_overflow, only_flagged);
     CUDA_TRY(ctx, cudaGetLastError());
   }
   return MGPU_OK;

@@ -22,6 +22,8 @@ struct mgpu_ctx {
   int sm_count = 0;
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux_stream = nullptr;           // side stream for work that is independent of the main chain (query encode)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::mutex mu;
   std::string err;
   // workspace (grown on demand)
@@ -55,13 +57,13 @@ int mgpu_fail(mgpu_ctx *ctx, int code, const char *fmt, ...);
 
 // Brackets one kernel launch for the per-class profiler and counts launches.
 struct LaunchScope {
-  mgpu_ctx *ctx; int cls;
-  LaunchScope(mgpu_ctx *c, int k) : ctx(c), cls(k) {
+  mgpu_ctx *ctx; int cls; cudaStream_t st;
+  LaunchScope(mgpu_ctx *c, int k, cudaStream_t s = nullptr) : ctx(c), cls(k), st(s ? s : c->stream) {
     ctx->launches++; ctx->prof[cls].launches++;
-    if (ctx->profiling) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); ctx->prof[cls].ev.push_back(e); }
+    if (ctx->profiling) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ctx->prof[cls].ev.push_back(e); }
   }
   ~LaunchScope() {
-    if (ctx->profiling) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); ctx->prof[cls].ev.push_back(e); }
+    if (ctx->profiling) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ctx->prof[cls].ev.push_back(e); }
   }
 };
 

@@ -26,24 +26,10 @@ __device__ __forceinline__ bool doc_less(uint32_t ka, mgpu_u128 a, uint32_t kb, 
   return a.lo < b.lo;
 }
 
-template <int METRIC>
-__global__ void __launch_bounds__(128) k_finalize(FinalizeArgs a) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (q >= a.B) return;
-  uint64_t ckey = a.cand_key[(size_t)q * MGPU_NCAND + lane];
-  uint32_t slot = a.cand_slot[(size_t)q * MGPU_NCAND + lane];
-  const bool valid = slot != MGPU_EMPTY_SLOT;
-  const uint32_t pid = (uint32_t)ckey;
-  uint32_t skey = (uint32_t)(ckey >> 32);
-  if (a.cb != nullptr && valid) {
-    // exact Quantizer::distance(quantized_query, row, StreamingSIMD) (index.rs:203-207, pq/mod.rs:231-266)
-    float d;
-    RowMajorCode qc{a.qcodes + (size_t)q * a.m};
-    if (a.pq_fast) d = pq_distance_streaming<METRIC>(a.cb, a.m, a.K, a.dsub, qc, FastLayoutCode{a.codes, slot, a.ng});
-    else d = pq_distance_streaming<METRIC>(a.cb, a.m, a.K, a.dsub, qc, RowMajorCode{a.codes + (size_t)slot * a.m});
-    skey = f2key(d);
-  }
+// Ordering + remap tail shared by both finalize kernels; called by one full warp per query.  `skey` is the exact score
+// key of this lane's candidate, `valid` whether the lane holds one.
+__device__ __forceinline__ void finalize_tail(const FinalizeArgs &a, uint32_t q, int lane, bool valid, uint32_t skey,
+                                              uint32_t pid, uint32_t slot) {
   WarpTop32 w;
   w.key = valid ? (((uint64_t)skey << 32) | pid) : MGPU_EMPTY_KEY;
   w.pay = slot;
@@ -78,13 +64,152 @@ __global__ void __launch_bounds__(128) k_finalize(FinalizeArgs a) {
   if (lane == 0 && a.out_counts) a.out_counts[q] = count;
 }
 
+// generic path: one warp per query, one candidate per lane (any dsub; flat rows arrive with exact keys already)
+template <int METRIC>
+__global__ void __launch_bounds__(128) k_finalize(FinalizeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= a.B) return;
+  uint64_t ckey = a.cand_key[(size_t)q * MGPU_NCAND + lane];
+  uint32_t slot = a.cand_slot[(size_t)q * MGPU_NCAND + lane];
+  const bool valid = slot != MGPU_EMPTY_SLOT;
+  const uint32_t pid = (uint32_t)ckey;
+  uint32_t skey = (uint32_t)(ckey >> 32);
+  if (a.cb != nullptr && valid) {
+    // exact Quantizer::distance(quantized_query, row, StreamingSIMD) (index.rs:203-207, pq/mod.rs:231-266)
+    float d;
+    RowMajorCode qc{a.qcodes + (size_t)q * a.m};
+    if (a.pq_fast) d = pq_distance_streaming<METRIC>(a.cb, a.m, a.K, a.dsub, qc, FastLayoutCode{a.codes, slot, a.ng});
+    else d = pq_distance_streaming<METRIC>(a.cb, a.m, a.K, a.dsub, qc, RowMajorCode{a.codes + (size_t)slot * a.m});
+    skey = f2key(d);
+  }
+  finalize_tail(a, q, lane, valid, skey, pid, slot);
+}
+
+// dsub == 8 (the reference default): one CTA of 128 threads per query.  Staging: the query's own centroids (m x 8 floats) and
+// the 32 candidates' code words go to shared memory with 16-byte loads.  Scoring: 2 threads per candidate, thread (c, h)
+// owns lane accumulators 4h..4h+3 of ProductQuantizer::distance's shared 8-lane sum (pq/mod.rs:231-266) and walks the m
+// subspaces in order -- the additions happen in exactly the reference's order while the m codebook gathers of a candidate
+// are independent 16-byte loads (no dependent code -> centroid -> accumulate latency chain per subspace).
+#define FIN8_THREADS 128
+#define FIN8_MLP 24
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+template <int METRIC>
+__global__ void __launch_bounds__(FIN8_THREADS) k_finalize_pq8(FinalizeArgs a) {
+  extern __shared__ __align__(16) uint8_t fsm[];
+  const uint32_t m = a.m, mp = (m + 15) & ~15u;
+  float4 *qv4 = (float4 *)fsm;                     // m x 2: centroid of the query code per subspace
+  uint8_t *cc = (uint8_t *)(qv4 + (size_t)m * 2);  // 32 x mp: candidate codes
+  uint32_t *skeys = (uint32_t *)(cc + (size_t)MGPU_NCAND * mp);  // 32 exact score keys
+  uint32_t *sslot = skeys + MGPU_NCAND;            // 32 slots
+  float4 *ring = (float4 *)(sslot + MGPU_NCAND);   // FIN8_MLP x 64 gathered centroid halves (16-byte aligned: all sizes above are)
+  const uint32_t q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < MGPU_NCAND) sslot[tid] = a.cand_slot[(size_t)q * MGPU_NCAND + tid];
+  const uint8_t *qc = a.qcodes + (size_t)q * m;
+  for (uint32_t i = tid; i < m * 2; i += FIN8_THREADS) {
+    const uint32_t s = i >> 1, h = i & 1;
+    qv4[i] = __ldg((const float4 *)(a.cb + ((size_t)s * a.K + qc[s]) * 8) + h);
+  }
+  __syncthreads();
+  if (a.pq_fast) {
+    // fast layout: a row's codes are 2*ng segments of 16 bytes; byte i of segment (g, u) is subspace 32g + (l ^ (16u + i))
+    for (uint32_t i = tid; i < MGPU_NCAND * 2 * a.ng; i += FIN8_THREADS) {
+      const uint32_t c = i & 31, seg = i >> 5, g = seg >> 1, u = seg & 1;
+      const uint32_t slot = sslot[c];
+      const uint32_t l = slot & 31;
+      // an empty candidate gets code 0 everywhere: it is scored like any other (keeps the warps converged) and ignored later
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (slot != MGPU_EMPTY_SLOT) v = __ldg((const uint4 *)(a.codes + (((size_t)(slot >> 5) * a.ng + g) * 2 + u) * 512 + l * 16));
+      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+      uint8_t *dst = cc + c * mp + 32 * g;
+#pragma unroll
+      for (int b = 0; b < 16; b++) dst[l ^ (16 * u + b)] = (uint8_t)(wv[b >> 2] >> (8 * (b & 3)));
+    }
+  } else {
+    for (uint32_t i = tid; i < MGPU_NCAND * m; i += FIN8_THREADS) {
+      const uint32_t c = i / m, s = i - c * m;
+      const uint32_t slot = sslot[c];
+      cc[c * mp + s] = slot != MGPU_EMPTY_SLOT ? a.codes[(size_t)slot * m + s] : (uint8_t)0;
+    }
+  }
+  __syncthreads();
+  if (tid < 2 * MGPU_NCAND) {
+    const uint32_t c = tid >> 1, h = tid & 1;
+    const uint8_t *code = cc + c * mp;
+    const float4 *cb4 = (const float4 *)a.cb + h;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    // The m codebook gathers of a candidate are independent, but a register-destination load is scheduled next to its use
+    // (2-3 in flight), which makes this loop a chain of L2 round trips.  cp.async has no register destination: FIN8_MLP
+    // 16-byte gathers are issued back to back into a thread-private (bank-interleaved) ring, waited for once, then consumed
+    // in subspace order.
+    for (uint32_t s0 = 0; s0 < m; s0 += FIN8_MLP) {
+      const uint32_t nb = min((uint32_t)FIN8_MLP, m - s0);
+      for (uint32_t j = 0; j < nb; j++)
+        cp_async16(&ring[j * (2 * MGPU_NCAND) + tid], cb4 + ((size_t)(s0 + j) * a.K + code[s0 + j]) * 2);
+      cp_async_commit_wait_all();
+      for (uint32_t j = 0; j < nb; j++) {
+        const float4 x = qv4[(s0 + j) * 2 + h], y = ring[j * (2 * MGPU_NCAND) + tid];
+        if (METRIC == MGPU_L2) {
+          float d;
+          d = __fsub_rn(x.x, y.x); a0 = __fadd_rn(a0, __fmul_rn(d, d));
+          d = __fsub_rn(x.y, y.y); a1 = __fadd_rn(a1, __fmul_rn(d, d));
+          d = __fsub_rn(x.z, y.z); a2 = __fadd_rn(a2, __fmul_rn(d, d));
+          d = __fsub_rn(x.w, y.w); a3 = __fadd_rn(a3, __fmul_rn(d, d));
+        } else {
+          a0 = __fadd_rn(a0, __fmul_rn(x.x, y.x)); a1 = __fadd_rn(a1, __fmul_rn(x.y, y.y));
+          a2 = __fadd_rn(a2, __fmul_rn(x.z, y.z)); a3 = __fadd_rn(a3, __fmul_rn(x.w, y.w));
+        }
+      }
+    }
+    // sum_16.reduce_sum() + sum_8.reduce_sum() + sum_4.reduce_sum() + sum_1 with empty 16/4/1 phases (pq/mod.rs:263-265)
+    float s8 = -0.0f;
+    const int base = lane & ~1;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      s8 = __fadd_rn(s8, __shfl_sync(0xffffffffu, a0, base + j));
+      s8 = __fadd_rn(s8, __shfl_sync(0xffffffffu, a1, base + j));
+      s8 = __fadd_rn(s8, __shfl_sync(0xffffffffu, a2, base + j));
+      s8 = __fadd_rn(s8, __shfl_sync(0xffffffffu, a3, base + j));
+    }
+    float r = __fadd_rn(__fadd_rn(-0.0f, 0.0f), s8);   // reduce(16 zero lanes) = +0.0
+    r = __fadd_rn(r, __fadd_rn(-0.0f, 0.0f));
+    r = __fadd_rn(r, 0.0f);
+    if (h == 0) skeys[c] = f2key(METRIC == MGPU_L2 ? r : -r);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const uint32_t slot = sslot[lane];
+    const bool valid = slot != MGPU_EMPTY_SLOT;
+    const uint32_t pid = (uint32_t)a.cand_key[(size_t)q * MGPU_NCAND + lane];
+    finalize_tail(a, q, lane, valid, skeys[lane], pid, slot);
+  }
+}
+
 int launch_finalize(mgpu_ctx *ctx, const FinalizeArgs &a) {
   if (a.B == 0) return MGPU_OK;
   if (a.k > MGPU_NCAND) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported by the scan kernels yet", a.k, MGPU_NCAND);
-  unsigned grid = (a.B + 3) / 4;
   LaunchScope ls(ctx, MGPU_K_FINALIZE);
-  if (a.metric == MGPU_L2) k_finalize<MGPU_L2><<<grid, 128, 0, ctx->stream>>>(a);
-  else k_finalize<MGPU_DOT><<<grid, 128, 0, ctx->stream>>>(a);
+  const size_t smem8 = (size_t)a.m * 32 + (size_t)MGPU_NCAND * ((a.m + 15) & ~15u) + MGPU_NCAND * 8 + (size_t)FIN8_MLP * 2 * MGPU_NCAND * 16;
+  static const bool no8 = getenv("MGPU_FINALIZE8") && getenv("MGPU_FINALIZE8")[0] == '0';
+  if (a.cb != nullptr && a.dsub == 8 && smem8 <= 96 * 1024 && !no8) {
+    if (a.metric == MGPU_L2) {
+      CUDA_TRY(ctx, cudaFuncSetAttribute(k_finalize_pq8<MGPU_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+      k_finalize_pq8<MGPU_L2><<<a.B, FIN8_THREADS, smem8, ctx->stream>>>(a);
+    } else {
+      CUDA_TRY(ctx, cudaFuncSetAttribute(k_finalize_pq8<MGPU_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+      k_finalize_pq8<MGPU_DOT><<<a.B, FIN8_THREADS, smem8, ctx->stream>>>(a);
+    }
+  } else {
+    unsigned grid = (a.B + 3) / 4;
+    if (a.metric == MGPU_L2) k_finalize<MGPU_L2><<<grid, 128, 0, ctx->stream>>>(a);
+    else k_finalize<MGPU_DOT><<<grid, 128, 0, ctx->stream>>>(a);
+  }
   CUDA_TRY(ctx, cudaGetLastError());
   return MGPU_OK;
 }

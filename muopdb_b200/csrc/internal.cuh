@@ -93,11 +93,14 @@ struct ScanArgs {
   unsigned long long *rows_scanned;
   unsigned int *next_query;  // zeroed before every launch: dynamic query scheduler
   const uint32_t *order;     // optional: queries in descending-work order (k_plan_queries)
+  // planner filter hook (index.rs:212-226): when non-null a scanned row survives only if bit `point id` of its query's
+  // bitmap is set; query q uses filter + q * filter_stride (stride 0 = one bitmap shared by the whole batch)
+  const uint32_t *filter; uint64_t filter_stride;
   int metric;
 };
 
 int launch_pq_build_table(mgpu_pq *pq);
-int launch_pq_quantize(mgpu_pq *pq, const float *dX, uint64_t n, uint8_t *dcodes);
+int launch_pq_quantize(mgpu_pq *pq, const float *dX, uint64_t n, uint8_t *dcodes, cudaStream_t st = nullptr);
 int launch_pq_distance_pairs(mgpu_pq *pq, const uint8_t *da, const uint8_t *db, uint64_t n, float *dout);
 int launch_build_layout(mgpu_ivf *ivf, const void *d_rows_by_pid);
 int launch_scan(mgpu_ivf *ivf, const ScanArgs &a);
@@ -132,7 +135,7 @@ bool coarse_tc_applicable(mgpu_ctx *ctx, uint32_t dim, uint32_t C, uint32_t npro
 int launch_split_bf16(mgpu_ctx *ctx, const float *dX, uint64_t n, uint32_t dim, int is_centroid, void *d_out, float *d_norms);
 int launch_coarse_tc(mgpu_ctx *ctx, const float *dQ, uint32_t B, const float *d_centroids, const void *d_csplit, const float *d_cn,
                      float cn_max, uint32_t C, uint32_t dim, uint32_t nprobe, void *d_qsplit, float *d_qn, float *d_Dt,
-                     uint32_t *d_overflow, uint32_t *out_ids, float *out_dist);
+                     uint32_t *d_overflow, uint32_t *d_flags, int need_order, uint32_t *out_ids, float *out_dist);
 
 struct HnswSearchArgs {
   const float *Q; uint32_t B, k, ef;

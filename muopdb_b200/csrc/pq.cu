@@ -58,19 +58,26 @@ int launch_pq_build_table(mgpu_pq *pq) {
 }
 
 // Quantizer::quantize for a batch (pq/mod.rs:152-177): grid = (row tiles, subspaces).  The subspace's centroids sit in
-// shared memory (every lane reads the same centroid -> broadcast), each thread owns one input row and keeps the
-// first minimum of the bit-exact calculate_squared.  ALWAYS the L2 calculator, whatever D is (pq/mod.rs:168).
-#define QT_ROWS 128
-__global__ void __launch_bounds__(QT_ROWS) k_pq_quantize(const float *__restrict__ X, uint64_t n, uint32_t dim,
-                                                          const float *__restrict__ cb, uint32_t dsub, uint32_t K,
-                                                          uint32_t m, uint8_t *__restrict__ codes) {
-  extern __shared__ float sm[];
+// shared memory; QT_SPLIT threads share one input row, thread j scoring centroids j, j + QT_SPLIT, ... with the bit-exact
+// calculate_squared and keeping its first minimum; the QT_SPLIT partial minima are combined by (distance, index), which
+// is the reference's strict-`<` first-minimum rule.  ALWAYS the L2 calculator, whatever D is (pq/mod.rs:168).
+#define QT_THREADS 256
+#define QT_SPLIT 4
+#define QT_ROWS (QT_THREADS / QT_SPLIT)
+__global__ void __launch_bounds__(QT_THREADS) k_pq_quantize(const float *__restrict__ X, uint64_t n, uint32_t dim,
+                                                             const float *__restrict__ cb, uint32_t dsub, uint32_t K,
+                                                             uint32_t m, uint8_t *__restrict__ codes) {
+  extern __shared__ __align__(16) float sm[];
   float *scb = sm;                       // K * dsub
   float *sx = sm + (size_t)K * dsub;     // QT_ROWS * (dsub + 1)
   uint32_t s = blockIdx.y;
   uint64_t row0 = (uint64_t)blockIdx.x * QT_ROWS;
   const float *gcb = cb + (size_t)s * K * dsub;
-  for (uint32_t i = threadIdx.x; i < K * dsub; i += blockDim.x) scb[i] = gcb[i];
+  if (((K * dsub) & 3u) == 0) {
+    for (uint32_t i = threadIdx.x; i < K * dsub / 4; i += blockDim.x) ((float4 *)scb)[i] = __ldg((const float4 *)gcb + i);
+  } else {
+    for (uint32_t i = threadIdx.x; i < K * dsub; i += blockDim.x) scb[i] = gcb[i];
+  }
   uint32_t pitch = dsub + 1;
   for (uint32_t i = threadIdx.x; i < QT_ROWS * dsub; i += blockDim.x) {
     uint32_t r = i / dsub, d = i % dsub;
@@ -78,46 +85,55 @@ __global__ void __launch_bounds__(QT_ROWS) k_pq_quantize(const float *__restrict
     sx[r * pitch + d] = row < n ? X[row * dim + (size_t)s * dsub + d] : 0.0f;
   }
   __syncthreads();
-  uint64_t row = row0 + threadIdx.x;
-  if (row >= n) return;
-  const float *x = sx + threadIdx.x * pitch;
+  const uint32_t r = threadIdx.x / QT_SPLIT, j = threadIdx.x % QT_SPLIT;
+  uint64_t row = row0 + r;
+  const float *x = sx + r * pitch;
   uint32_t best = 0;
   float best_d = 3.40282347e+38f;
   if (dsub == 8) {
-    // common case: the row's subvector lives in registers, every centroid is two broadcast 16-byte shared loads;
-    // arithmetic identical to calculate_squared on 8 values (one 8-lane chunk, ordered reduce, 0 + s)
+    // common case: the row's subvector lives in registers, every centroid is two 16-byte shared loads.  calculate_squared
+    // on 8 values is one 8-lane chunk: lane accumulators 0 + d*d (== d*d: a square is never -0), ordered reduce starting
+    // from -0.0 (-0.0 + p == p for p >= +0), then 0 + s (== s).  The identities hold for NaN as well, so only the 8
+    // subtractions, 8 products and 7 ordered additions are executed.
     float xv[8];
 #pragma unroll
     for (int l = 0; l < 8; l++) xv[l] = x[l];
 #pragma unroll 4
-    for (uint32_t c = 0; c < K; c++) {
+    for (uint32_t c = j; c < K; c += QT_SPLIT) {
       const float4 c0 = *(const float4 *)(scb + c * 8), c1 = *(const float4 *)(scb + c * 8 + 4);
       const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-      float s2 = -0.0f;
+      float d0 = __fsub_rn(xv[0], cv[0]);
+      float s2 = __fmul_rn(d0, d0);
 #pragma unroll
-      for (int l = 0; l < 8; l++) { float d = __fsub_rn(xv[l], cv[l]); s2 = __fadd_rn(s2, __fadd_rn(0.0f, __fmul_rn(d, d))); }
-      const float dd = __fadd_rn(0.0f, s2);
-      if (dd < best_d) { best_d = dd; best = c; }
+      for (int l = 1; l < 8; l++) { float d = __fsub_rn(xv[l], cv[l]); s2 = __fadd_rn(s2, __fmul_rn(d, d)); }
+      if (s2 < best_d) { best_d = s2; best = c; }
     }
-    codes[row * m + s] = (uint8_t)best;
-    return;
+  } else {
+    for (uint32_t c = j; c < K; c += QT_SPLIT) {
+      float d = ref_distance<MGPU_L2>(PtrAcc{x}, PtrAcc{scb + (size_t)c * dsub}, (int)dsub);
+      if (d < best_d) { best_d = d; best = c; }
+    }
   }
-  for (uint32_t c = 0; c < K; c++) {
-    float d = ref_distance<MGPU_L2>(PtrAcc{x}, PtrAcc{scb + (size_t)c * dsub}, (int)dsub);
-    if (d < best_d) { best_d = d; best = c; }
+  // combine the QT_SPLIT partial first-minima: smaller distance, then smaller index
+#pragma unroll
+  for (int o = 1; o < QT_SPLIT; o <<= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, best_d, o);
+    const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, o);
+    if (od < best_d || (od == best_d && ob < best)) { best_d = od; best = ob; }
   }
-  codes[row * m + s] = (uint8_t)best;
+  if (j == 0 && row < n) codes[row * m + s] = (uint8_t)best;
 }
 
-int launch_pq_quantize(mgpu_pq *pq, const float *dX, uint64_t n, uint8_t *dcodes) {
+int launch_pq_quantize(mgpu_pq *pq, const float *dX, uint64_t n, uint8_t *dcodes, cudaStream_t st) {
   mgpu_ctx *ctx = pq->ctx;
+  if (!st) st = ctx->stream;
   if (n == 0) return MGPU_OK;
   size_t smem = ((size_t)pq->K * pq->dsub + (size_t)QT_ROWS * (pq->dsub + 1)) * sizeof(float);
   if (smem > ctx->smem_optin) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "pq quantize: codebook slice of %zu bytes exceeds shared memory", smem);
   CUDA_TRY(ctx, cudaFuncSetAttribute(k_pq_quantize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((n + QT_ROWS - 1) / QT_ROWS), pq->m);
-  LaunchScope ls(ctx, MGPU_K_QUANTIZE);
-  k_pq_quantize<<<grid, QT_ROWS, smem, ctx->stream>>>(dX, n, pq->dim, pq->d_cb, pq->dsub, pq->K, pq->m, dcodes);
+  LaunchScope ls(ctx, MGPU_K_QUANTIZE, st);
+  k_pq_quantize<<<grid, QT_THREADS, smem, st>>>(dX, n, pq->dim, pq->d_cb, pq->dsub, pq->K, pq->m, dcodes);
   CUDA_TRY(ctx, cudaGetLastError());
   return MGPU_OK;
 }

@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(NT, 1) k_scan(ScanArgs a, ScanSmemLayout L) {
       const uint32_t pid = a.slot_pid[slot];
       bool valid = pid != MGPU_EMPTY_SLOT;
       if (a.invalid && valid) valid = !((a.invalid[pid >> 5] >> (pid & 31)) & 1u);  // index.rs:198-200
+      if (a.filter && valid) valid = (a.filter[(size_t)q * a.filter_stride + (pid >> 5)] >> (pid & 31)) & 1u;  // index.rs:212-226
 
       uint32_t key;
       if (MODE == SCAN_PQ_FAST) {

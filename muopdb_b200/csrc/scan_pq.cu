@@ -100,6 +100,7 @@ struct DbConsumerCtx {
       }
       bool valid = pid != MGPU_EMPTY_SLOT;
       if (a.invalid && valid) valid = !((a.invalid[pid >> 5] >> (pid & 31)) & 1u);  // index.rs:198-200
+      if (a.filter && valid) valid = (a.filter[(size_t)q * a.filter_stride + (pid >> 5)] >> (pid & 31)) & 1u;  // index.rs:212-226
 
       uint32_t acc0 = 0, acc1 = 0;
 #pragma unroll

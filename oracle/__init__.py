@@ -85,6 +85,12 @@ def _declare(L):
     L.orc_ivf_search.argtypes = [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, _u64p, _f32p]
     L.orc_ivf_search_batch.restype = None
     L.orc_ivf_search_batch.argtypes = [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _u64p, _f32p, _i32p, C.c_int]
+    L.orc_ivf_search_batch_f.restype = None
+    L.orc_ivf_search_batch_f.argtypes = [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, C.c_uint64, _u64p, _f32p,
+                                         _i32p, C.c_int]
+    L.orc_spann_search_batch_f.restype = None
+    L.orc_spann_search_batch_f.argtypes = [C.c_void_p, C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                           C.c_float, _u32p, C.c_uint64, _u64p, _f32p, _i32p, C.c_int]
     L.orc_ivf_assign.restype = None
     L.orc_ivf_assign.argtypes = [_f32p, C.c_uint64, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, _u32p, _u32p]
     L.orc_kmeans_assign.restype = None
@@ -299,15 +305,22 @@ class Ivf:
             raise ValueError("num_probes out of range (reference panics)")
         return pairs_to_u128(od[:n]), os_[:n].copy()
 
-    def search_batch(self, Q, k, nprobe, nthreads=0):
-        """-> doc_ids (B,k,2) u64, scores (B,k) f32, counts (B,) i32"""
+    def search_batch(self, Q, k, nprobe, nthreads=0, filter_bits=None):
+        """-> doc_ids (B,k,2) u64, scores (B,k) f32, counts (B,) i32.  filter_bits: planner filter as point-id bitmaps,
+        (words,) shared by all queries or (B, words) one per query (index.rs:212-226)."""
         Q = _f32(Q)
         B = Q.shape[0]
         od = np.zeros((B, max(k, 1), 2), dtype=np.uint64)
         os_ = np.zeros((B, max(k, 1)), dtype=np.float32)
         cnt = np.zeros(B, dtype=np.int32)
-        lib().orc_ivf_search_batch(self.h, _p(Q, _f32p), B, k, nprobe, _p(od, _u64p), _p(os_, _f32p), _p(cnt, _i32p),
-                                   nthreads)
+        if filter_bits is None:
+            lib().orc_ivf_search_batch(self.h, _p(Q, _f32p), B, k, nprobe, _p(od, _u64p), _p(os_, _f32p), _p(cnt, _i32p),
+                                       nthreads)
+        else:
+            fb = np.ascontiguousarray(filter_bits, dtype=np.uint32)
+            stride = fb.shape[1] if fb.ndim == 2 else 0
+            lib().orc_ivf_search_batch_f(self.h, _p(Q, _f32p), B, k, nprobe, _p(fb, _u32p), stride, _p(od, _u64p),
+                                         _p(os_, _f32p), _p(cnt, _i32p), nthreads)
         return od, os_, cnt
 
 
@@ -432,16 +445,23 @@ class Spann:
         return pairs_to_u128(od[:n]), os_[:n].copy()
 
     def search_batch(self, Q, top_k, ef_construction, num_explored_centroids=None, centroid_distance_ratio=0.1,
-                     nthreads=0):
+                     nthreads=0, filter_bits=None):
         Q = _f32(Q)
         B = Q.shape[0]
         ne = top_k if num_explored_centroids is None else num_explored_centroids
         od = np.zeros((B, max(top_k, 1), 2), dtype=np.uint64)
         os_ = np.zeros((B, max(top_k, 1)), dtype=np.float32)
         cnt = np.zeros(B, dtype=np.int32)
-        lib().orc_spann_search_batch(self.centroids.h, self.posting_lists.h, _p(Q, _f32p), B, top_k, ef_construction,
-                                     ne, float(centroid_distance_ratio), _p(od, _u64p), _p(os_, _f32p),
-                                     _p(cnt, _i32p), nthreads)
+        if filter_bits is None:
+            lib().orc_spann_search_batch(self.centroids.h, self.posting_lists.h, _p(Q, _f32p), B, top_k, ef_construction,
+                                         ne, float(centroid_distance_ratio), _p(od, _u64p), _p(os_, _f32p),
+                                         _p(cnt, _i32p), nthreads)
+        else:
+            fb = np.ascontiguousarray(filter_bits, dtype=np.uint32)
+            stride = fb.shape[1] if fb.ndim == 2 else 0
+            lib().orc_spann_search_batch_f(self.centroids.h, self.posting_lists.h, _p(Q, _f32p), B, top_k, ef_construction,
+                                           ne, float(centroid_distance_ratio), _p(fb, _u32p), stride, _p(od, _u64p),
+                                           _p(os_, _f32p), _p(cnt, _i32p), nthreads)
         return od, os_, cnt
 
 

@@ -424,8 +424,11 @@ static void heap_sift_down(orc_pd *h, uint32_t n, uint32_t i) {
 
 /* scan_posting_list (index.rs:175-237) + search_with_centroids (index.rs:250-285).
  * Returns number of results (<= k), sorted by (distance, point_id). */
-ORC_API int orc_ivf_search_with_centroids(const orc_ivf *x, const float *query, const uint32_t *cids, uint32_t ncids,
-                                          uint32_t k, uint32_t *out_pids, float *out_dists) {
+/* `filter` (may be NULL) stands for Some(planner): planner.plan_with_ids(all_ids) yields the scanned ids that are in the
+ * request's DocumentFilter (rs/index/src/query/planner.rs:43-60); here the filter is that id set as a bitmap over point
+ * ids.  Distances are computed for every non-invalidated row BEFORE the filter is applied (index.rs:196-226). */
+ORC_API int orc_ivf_search_with_centroids_f(const orc_ivf *x, const float *query, const uint32_t *cids, uint32_t ncids,
+                                            uint32_t k, const uint32_t *filter, uint32_t *out_pids, float *out_dists) {
   orc_pd *heap = (orc_pd *)malloc(sizeof(orc_pd) * (k ? k : 1));
   uint32_t hn = 0;
   void *qq_hoisted = x->hoist_quantize ? q_process_vector(&x->q, query) : NULL;
@@ -441,6 +444,12 @@ ORC_API int orc_ivf_search_with_centroids(const orc_ivf *x, const float *query, 
       if (ivf_is_invalid(x, pid)) continue;                       /* index.rs:198-200 */
       float d = q_distance(&x->q, qq, q_row(&x->q, x->rows, pid)); /* index.rs:202-207 */
       pds[np].distance = d; pds[np].point_id = pid; np++;
+    }
+    if (filter) {                                                 /* index.rs:214-226: retain ids the planner yields */
+      uint32_t w = 0;
+      for (uint32_t i = 0; i < np; i++)
+        if ((filter[pds[i].point_id >> 5] >> (pds[i].point_id & 31)) & 1u) pds[w++] = pds[i];
+      np = w;
     }
     /* index.rs:212 sort by id, :228 stable sort by distance (total_cmp) == sort by (distance, id) */
     qsort(pds, np, sizeof(orc_pd), pd_cmp_q);
@@ -458,18 +467,23 @@ ORC_API int orc_ivf_search_with_centroids(const orc_ivf *x, const float *query, 
   return (int)hn;
 }
 
+ORC_API int orc_ivf_search_with_centroids(const orc_ivf *x, const float *query, const uint32_t *cids, uint32_t ncids,
+                                          uint32_t k, uint32_t *out_pids, float *out_dists) {
+  return orc_ivf_search_with_centroids_f(x, query, cids, ncids, k, NULL, out_pids, out_dists);
+}
+
 static inline void ivf_doc_id(const orc_ivf *x, uint32_t pid, uint64_t *lo, uint64_t *hi) {
   if (x->doc_ids) { *lo = x->doc_ids[2 * (size_t)pid]; *hi = x->doc_ids[2 * (size_t)pid + 1]; }
   else { *lo = pid; *hi = 0; }
 }
 
 /* search_with_centroids_and_remap (index.rs:298-332): point ids -> doc ids, sort by (score, doc_id) */
-ORC_API int orc_ivf_search_with_centroids_and_remap(const orc_ivf *x, const float *query, const uint32_t *cids,
-                                                    uint32_t ncids, uint32_t k, uint64_t *out_doc_ids,
-                                                    float *out_scores) {
+ORC_API int orc_ivf_search_with_centroids_and_remap_f(const orc_ivf *x, const float *query, const uint32_t *cids,
+                                                      uint32_t ncids, uint32_t k, const uint32_t *filter,
+                                                      uint64_t *out_doc_ids, float *out_scores) {
   uint32_t *pids = (uint32_t *)malloc(sizeof(uint32_t) * (k ? k : 1));
   float *ds = (float *)malloc(sizeof(float) * (k ? k : 1));
-  int n = orc_ivf_search_with_centroids(x, query, cids, ncids, k, pids, ds);
+  int n = orc_ivf_search_with_centroids_f(x, query, cids, ncids, k, filter, pids, ds);
   orc_ids *v = (orc_ids *)malloc(sizeof(orc_ids) * (n ? n : 1));
   for (int i = 0; i < n; i++) { ivf_doc_id(x, pids[i], &v[i].lo, &v[i].hi); v[i].score = ds[i]; }
   qsort(v, n, sizeof(orc_ids), ids_cmp_q);
@@ -478,15 +492,38 @@ ORC_API int orc_ivf_search_with_centroids_and_remap(const orc_ivf *x, const floa
   return n;
 }
 
-/* BlockBasedIvf::search (index.rs:396-412) */
-ORC_API int orc_ivf_search(const orc_ivf *x, const float *query, uint32_t k, uint32_t nprobe, uint64_t *out_doc_ids,
-                           float *out_scores) {
+ORC_API int orc_ivf_search_with_centroids_and_remap(const orc_ivf *x, const float *query, const uint32_t *cids,
+                                                    uint32_t ncids, uint32_t k, uint64_t *out_doc_ids,
+                                                    float *out_scores) {
+  return orc_ivf_search_with_centroids_and_remap_f(x, query, cids, ncids, k, NULL, out_doc_ids, out_scores);
+}
+
+/* BlockBasedIvf::search (index.rs:396-412); filter = Some(planner) or NULL */
+ORC_API int orc_ivf_search_f(const orc_ivf *x, const float *query, uint32_t k, uint32_t nprobe, const uint32_t *filter,
+                             uint64_t *out_doc_ids, float *out_scores) {
   uint32_t *cids = (uint32_t *)malloc(sizeof(uint32_t) * (nprobe ? nprobe : 1));
   int r = orc_ivf_find_nearest_centroids(x, query, nprobe, cids, NULL);
   if (r < 0) { free(cids); return -1; }
-  r = orc_ivf_search_with_centroids_and_remap(x, query, cids, nprobe, k, out_doc_ids, out_scores);
+  r = orc_ivf_search_with_centroids_and_remap_f(x, query, cids, nprobe, k, filter, out_doc_ids, out_scores);
   free(cids);
   return r;
+}
+ORC_API int orc_ivf_search(const orc_ivf *x, const float *query, uint32_t k, uint32_t nprobe, uint64_t *out_doc_ids,
+                           float *out_scores) {
+  return orc_ivf_search_f(x, query, k, nprobe, NULL, out_doc_ids, out_scores);
+}
+
+/* filtered batch: query b uses filter + b * stride_words (stride 0: one bitmap for all) */
+ORC_API void orc_ivf_search_batch_f(const orc_ivf *x, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe,
+                                    const uint32_t *filter, uint64_t stride_words, uint64_t *out_doc_ids,
+                                    float *out_scores, int32_t *out_counts, int nthreads) {
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t b = 0; b < (int64_t)B; b++)
+    out_counts[b] = orc_ivf_search_f(x, Q + (size_t)b * x->q.dim, k, nprobe, filter ? filter + (size_t)b * stride_words : NULL,
+                                     out_doc_ids + (size_t)b * k * 2, out_scores + (size_t)b * k);
 }
 
 /* one query per thread over a batch (the reference has no batching; this is B independent calls) */
@@ -707,9 +744,9 @@ ORC_API void orc_hnsw_search_batch(const orc_hnsw *h, const float *Q, uint32_t B
 
 /* centroids: HNSW over the IVF centroids (NoQuantizer<L2>), whose doc ids are centroid indices.
  * Returns result count, or -1 for None. */
-ORC_API int orc_spann_search(const orc_hnsw *centroids, const orc_ivf *lists, const float *query, uint32_t top_k,
-                             uint32_t ef, uint32_t num_explored_centroids, float centroid_distance_ratio,
-                             uint64_t *out_doc_ids, float *out_scores) {
+ORC_API int orc_spann_search_f(const orc_hnsw *centroids, const orc_ivf *lists, const float *query, uint32_t top_k,
+                               uint32_t ef, uint32_t num_explored_centroids, float centroid_distance_ratio,
+                               const uint32_t *filter, uint64_t *out_doc_ids, float *out_scores) {
   uint32_t ne = num_explored_centroids;
   uint64_t *cdoc = (uint64_t *)malloc(sizeof(uint64_t) * 2 * (ne ? ne : 1));
   float *cs = (float *)malloc(sizeof(float) * (ne ? ne : 1));
@@ -721,9 +758,28 @@ ORC_API int orc_spann_search(const orc_hnsw *centroids, const orc_ivf *lists, co
   uint32_t kept = 0;
   for (int i = 0; i < nc; i++)
     if (cs[i] - nearest <= nearest * centroid_distance_ratio) cids[kept++] = (uint32_t)cdoc[2 * i]; /* :239-246 */
-  int r = orc_ivf_search_with_centroids_and_remap(lists, query, cids, kept, top_k, out_doc_ids, out_scores);
+  int r = orc_ivf_search_with_centroids_and_remap_f(lists, query, cids, kept, top_k, filter, out_doc_ids, out_scores);
   free(cids); free(cdoc); free(cs);
   return r;
+}
+ORC_API int orc_spann_search(const orc_hnsw *centroids, const orc_ivf *lists, const float *query, uint32_t top_k,
+                             uint32_t ef, uint32_t num_explored_centroids, float centroid_distance_ratio,
+                             uint64_t *out_doc_ids, float *out_scores) {
+  return orc_spann_search_f(centroids, lists, query, top_k, ef, num_explored_centroids, centroid_distance_ratio, NULL,
+                            out_doc_ids, out_scores);
+}
+ORC_API void orc_spann_search_batch_f(const orc_hnsw *centroids, const orc_ivf *lists, const float *Q, uint32_t B,
+                                      uint32_t top_k, uint32_t ef, uint32_t num_explored_centroids, float ratio,
+                                      const uint32_t *filter, uint64_t stride_words, uint64_t *out_doc_ids,
+                                      float *out_scores, int32_t *out_counts, int nthreads) {
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t b = 0; b < (int64_t)B; b++)
+    out_counts[b] = orc_spann_search_f(centroids, lists, Q + (size_t)b * lists->q.dim, top_k, ef, num_explored_centroids, ratio,
+                                       filter ? filter + (size_t)b * stride_words : NULL,
+                                       out_doc_ids + (size_t)b * top_k * 2, out_scores + (size_t)b * top_k);
 }
 
 ORC_API void orc_spann_search_batch(const orc_hnsw *centroids, const orc_ivf *lists, const float *Q, uint32_t B,

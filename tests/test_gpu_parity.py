@@ -380,6 +380,134 @@ def test_spann_parity(M, pq):
             assert _same_f32(r.scores[b, :n], os_[b, :n])
 
 
+# ---- planner filter hook ---------------------------------------------------------------------------------
+def _bits(ids, n):
+    b = np.zeros((n + 31) // 32, dtype=np.uint32)
+    ids = np.asarray(ids, dtype=np.int64)
+    np.bitwise_or.at(b, ids >> 5, (np.uint32(1) << (ids & 31).astype(np.uint32)))
+    return b
+
+
+def test_spann_where_document_reference_golden(M):
+    """multi_spann/index.rs:787-882 (only even docs come back) and :884-980 (a filter matching nothing -> no results)."""
+    n = 10
+    X = np.repeat(np.arange(n, dtype=np.float32)[:, None], 4, axis=1)
+    _, gs, _, _ = _spann_pair(M, X, list(range(n)), 3)
+    res = gs.search([4.4] * 4, M.SearchParams(10, 5, False, 3, 10.0), planner=M.Planner([0, 2, 4, 6, 8]))
+    got = [x.doc_id for x in res.id_with_scores]
+    assert got and all(d % 2 == 0 for d in got) and got[0] == 4
+    res = gs.search([2.4] * 4, M.SearchParams(10, 2, False, 3, 10.0), planner=M.Planner([]))
+    assert res is not None and res.id_with_scores == []
+
+
+@pytest.mark.parametrize("pq", [None, (8, 8, 1500)])
+@pytest.mark.parametrize("on_device", [False, True])
+def test_ivf_planner_filter_parity(M, pq, on_device):
+    """BlockBasedIvf::search with Some(planner) (index.rs:212-226, 396-412): one shared filter, one filter per query (with a
+    None entry = unfiltered), a filter that leaves fewer than k rows, together with invalidations -- vs the oracle."""
+    X = synth.clustered(6000, 256, n_blobs=20, seed=11)
+    docs = synth.doc_ids_for(len(X), seed=2)
+    _, _, oivf, givf = _spann_pair(M, X, docs, 32, pq_params=pq)
+    rng = np.random.default_rng(9)
+    Q = (X[100:164] + 0.01).astype(np.float32)
+    B, n = len(Q), len(X)
+    oivf.invalidate_batch([101, 105, 3000]); givf.invalidate_batch([101, 105, 3000])
+    Qg = Q
+    if on_device:
+        import torch
+        Qg = torch.from_numpy(Q).cuda()
+    shared = np.sort(rng.choice(n, 900, replace=False))
+    od, os_, oc = oivf.search_batch(Q, 10, 8, filter_bits=_bits(shared, n))
+    r = givf.search_batch(Qg, 10, 8, planner=M.Planner(shared))
+    _cmp_batch(r, od, os_, oc)
+    sets = [np.sort(rng.choice(n, int(sz), replace=False)) for sz in rng.integers(3, 2000, B)]
+    sets[5] = np.array([7], dtype=np.int64)   # fewer than k survivors
+    per_q = np.stack([_bits(s_, n) for s_ in sets])
+    planners = [M.Planner(s_) for s_ in sets]
+    per_q[9] = 0xFFFFFFFF
+    planners[9] = None                        # no filter for this query
+    od, os_, oc = oivf.search_batch(Q, 10, 8, filter_bits=per_q)
+    r = givf.search_batch(Qg, 10, 8, planner=planners)
+    _cmp_batch(r, od, os_, oc)
+
+
+def _cmp_batch(r, od, os_, oc):
+    d = r.doc_ids.cpu().numpy().view(np.uint64) if hasattr(r.doc_ids, "cpu") else r.doc_ids
+    s = r.scores.cpu().numpy() if hasattr(r.scores, "cpu") else r.scores
+    c = r.counts.cpu().numpy() if hasattr(r.counts, "cpu") else r.counts
+    assert np.array_equal(np.asarray(c).astype(np.int64), oc.astype(np.int64))
+    for b in range(len(oc)):
+        n = int(oc[b])
+        assert np.array_equal(d[b, :n], od[b, :n]), b
+        assert _same_f32(s[b, :n], os_[b, :n])
+
+
+def test_spann_planner_filter_parity(M):
+    X = synth.clustered(4000, 128, n_blobs=24, seed=41)
+    docs = synth.doc_ids_for(len(X), seed=4)
+    osp, gsp, _, _ = _spann_pair(M, X, docs, 48, pq_params=(8, 8, 1500))
+    Q = X[200:240] + 0.01
+    allowed = np.sort(np.random.default_rng(1).choice(len(X), 700, replace=False))
+    od, os_, oc = osp.search_batch(Q, 10, 50, 8, 1.0, filter_bits=_bits(allowed, len(X)))
+    r = gsp.search_batch(Q, M.SearchParams(10, 50, False, 8, 1.0), planner=M.Planner(allowed))
+    assert np.array_equal(np.asarray(r.counts).astype(np.int32), oc)
+    for b in range(len(Q)):
+        n = max(int(oc[b]), 0)
+        assert np.array_equal(r.doc_ids[b, :n], od[b, :n]), b
+        assert _same_f32(r.scores[b, :n], os_[b, :n])
+
+
+# ---- micro-batcher (SURVEY.md 8f row 4) ---------------------------------------------------------------------------------------
+def test_micro_batcher_concurrent_callers_match_oracle(M):
+    """Many threads call the single-query search (the reference's call shape, index.rs:396-412); the native batcher groups
+    them into batched GPU searches.  Every caller must get exactly the oracle's answer for ITS query (also with a per-request
+    planner filter), and the calls must really have been batched."""
+    import threading
+    X = synth.clustered(5000, 128, n_blobs=16, seed=21)
+    docs = synth.doc_ids_for(len(X), seed=6)
+    _, _, oivf, givf = _spann_pair(M, X, docs, 32, pq_params=(8, 8, 1500))
+    nthreads, per_thread = 24, 12
+    Q = (X[:nthreads * per_thread] + 0.01).astype(np.float32)
+    rng = np.random.default_rng(3)
+    allowed = [np.sort(rng.choice(len(X), 800, replace=False)) if i % 3 == 0 else None for i in range(len(Q))]
+    mb = M.MicroBatcher(givf, k=10, num_probes=8, max_batch=16, max_wait_us=20000)
+    got, errs = [None] * len(Q), []
+
+    def worker(t):
+        try:
+            for j in range(per_thread):
+                i = t * per_thread + j
+                got[i] = mb.search(Q[i], planner=M.Planner(allowed[i]) if allowed[i] is not None else None)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(nthreads)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    st = mb.stats()
+    mb.close()
+    assert st["queries"] == len(Q) and st["batches"] < len(Q) and st["largest_batch"] > 1
+    for i in range(len(Q)):
+        fb = None if allowed[i] is None else _bits(allowed[i], len(X))
+        od, os_, oc = oivf.search_batch(Q[i:i + 1], 10, 8, filter_bits=fb)
+        n = int(oc[0])
+        exp_ids = [int(lo) | (int(hi) << 64) for lo, hi in od[0, :n]]
+        assert [x.doc_id for x in got[i].id_with_scores] == exp_ids, i
+        assert _same_f32(np.array([x.score for x in got[i].id_with_scores], dtype=np.float32), os_[0, :n])
+
+
+def test_micro_batcher_spann_and_errors(M):
+    X = np.repeat(np.arange(1000, dtype=np.float32)[:, None], 4, axis=1)
+    _, gs, _, givf = _spann_pair(M, X, list(range(1000)), 10)
+    mb = M.MicroBatcher(gs, k=2, params=M.SearchParams(2, 2), max_batch=8, max_wait_us=100)
+    res = mb.search([2.4, 3.4, 4.4, 5.4])     # spann/index.rs:293-366
+    assert [x.doc_id for x in res.id_with_scores] == [4, 3]
+    mb.close()
+    with pytest.raises(M.OutOfRange):          # num_probes == 0 panics in the reference (index.rs:158)
+        M.MicroBatcher(givf, k=2, num_probes=0)
+
+
 # ---- tensor-core coarse scoring --------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dim,nlist,nprobe", [(64, 1024, 16), (128, 2048, 64), (768, 1280, 32), (80, 1028, 7)])
 def test_coarse_tensor_core_path_matches_exact(M, dim, nlist, nprobe):
@@ -401,3 +529,12 @@ def test_coarse_tensor_core_path_matches_exact(M, dim, nlist, nprobe):
         assert np.array_equal(op, gp[b]), (b, op[:8], gp[b][:8])
         assert _same_f32(od, gd[b])
     assert givf.ctx.profile_get(0)[1] > 0
+    # the search path only asks the selection for the probe SET (certain members are not re-scored, only the uncertain
+    # band is): results must still be the oracle's
+    od, os_, oc = oivf.search_batch(Q, 10, nprobe)
+    r = givf.search_batch(Q, 10, nprobe)
+    assert np.array_equal(np.asarray(r.counts, dtype=np.int64), oc.astype(np.int64))
+    for b in range(len(Q)):
+        n = int(oc[b])
+        assert np.array_equal(r.doc_ids[b, :n], od[b, :n]), b
+        assert _same_f32(r.scores[b, :n], os_[b, :n])

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 import oracle as O
+from tests import synth
 
 
 # ---- distance kernels ------------------------------------------------------------------------
@@ -214,6 +215,51 @@ def test_spann_search_with_pq_golden():
     assert len(ids_) == 5 and (scores == 0.0).all()
     # ties are ordered by doc id (utils.rs:95-114)
     assert ids_ == sorted(ids_)
+
+
+def _bits(ids, n):
+    b = np.zeros((n + 31) // 32, dtype=np.uint32)
+    for i in ids:
+        b[i >> 5] |= np.uint32(1 << (i & 31))
+    return b
+
+
+def test_spann_search_with_where_document_golden():
+    """rs/index/src/multi_spann/index.rs:787-882 -- 10 docs [i,i,i,i], filter `field contains even` (= point ids 0,2,4,6,8),
+    q=[4.4]*4, k=10, ef=5: every result is an even doc; and :884-980 -- a filter that matches nothing -> 0 results.
+    The planner filter reaches the scan as the id set `plan_with_ids` yields (ivf/block_based/index.rs:212-226)."""
+    n = 10
+    X = np.repeat(np.arange(n, dtype=np.float32)[:, None], 4, axis=1)
+    cents = O.kmeans(X, 3, iters=10, seed=7)
+    offsets, ids = O.build_posting_lists(X, cents, 1, 0.1)
+    ivf = O.Ivf(cents, offsets, ids, X, doc_ids=list(range(n)))
+    g = O.hnsw_build(cents, 10, 2, 100, seed=3)
+    hn = O.Hnsw(g["num_layers"], g["edges"], g["points"], g["edge_offsets"], g["level_offsets"], cents)
+    sp = O.Spann(hn, ivf)
+    q = np.full((1, 4), 4.4, dtype=np.float32)
+    od, os_, oc = sp.search_batch(q, 10, 5, 3, 10.0, filter_bits=_bits([0, 2, 4, 6, 8], n))
+    got = [int(x) for x in od[0, :oc[0], 0]]
+    assert oc[0] > 0 and all(d % 2 == 0 for d in got)
+    assert got[0] == 4 and (np.diff(os_[0, :oc[0]]) >= 0).all()
+    od, os_, oc = sp.search_batch(np.full((1, 4), 2.4, dtype=np.float32), 10, 2, 3, 10.0, filter_bits=_bits([], n))
+    assert oc[0] == 0
+
+
+def test_ivf_filter_equals_bruteforce_over_allowed_ids():
+    """index.rs:212-226: with every list probed, the filtered search is the exact top-k over the allowed ids."""
+    X = synth.clustered(1500, 32, n_blobs=6, seed=3)
+    cents = O.kmeans(X, 12, iters=8, seed=1)
+    offsets, ids = O.build_posting_lists(X, cents, 1, 0.1)
+    ivf = O.Ivf(cents, offsets, ids, X)
+    rng = np.random.default_rng(5)
+    allowed = np.sort(rng.choice(len(X), 300, replace=False))
+    Q = X[:20] + 0.01
+    od, os_, oc = ivf.search_batch(Q, 7, 12, filter_bits=_bits(allowed.tolist(), len(X)))
+    for b in range(len(Q)):
+        d = np.array([O.l2(Q[b], X[i]) for i in allowed], dtype=np.float32)
+        order = np.lexsort((allowed, d))[:7]
+        assert oc[b] == 7
+        assert [int(x) for x in od[b, :7, 0]] == [int(allowed[i]) for i in order]
 
 
 def test_multi_spann_search_golden():
