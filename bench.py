@@ -220,17 +220,20 @@ def build_oracle_index(col, args):
     return O, opq
 
 
-def cpu_leg(O, oivf, Qh, k, nprobe, seconds, nthreads, per_call):
-    """Times the oracle on successive slices of Qh until `seconds` of CPU wall time are used."""
+def cpu_leg(O, oivf, Qh, k, nprobe, seconds, nthreads, per_call, keep):
+    """Times the oracle on successive slices of Qh (cycling) until `seconds` of CPU wall time are used; the results of the
+    first `keep` queries are returned for the parity check."""
     done, t_used, i = 0, 0.0, 0
     res = []
     oivf.search_batch(Qh[:min(per_call, Qh.shape[0])], k, nprobe, nthreads)  # warm-up (page faults, thread pool)
-    while t_used < seconds and i < Qh.shape[0]:
-        q = Qh[i:i + per_call]
+    while t_used < seconds:
+        lo = i % Qh.shape[0]
+        q = Qh[lo:lo + per_call]
         t0 = time.perf_counter()
         r = oivf.search_batch(q, k, nprobe, nthreads)
         t_used += time.perf_counter() - t0
-        res.append(r)
+        if i < keep:
+            res.append(r)
         done += q.shape[0]
         i += per_call
     return done, t_used, res
@@ -436,9 +439,12 @@ def main():
         opq = O.ProductQuantizer(args.dim, args.dsub, 8, col["codebook"].cpu().numpy())
         oivf = O.Ivf(col["centroids"].cpu().numpy(), col["offsets"].cpu().numpy().astype(np.uint64),
                      col["list_ids"].cpu().numpy().astype(np.uint32), codes.cpu().numpy(), doc_ids=docs_pairs, pq=opq)
-        Qcpu = Qall[:B].cpu().numpy()
+        Qcpu = Qall.cpu().numpy()
         nthreads = ncores
-        done, secs, rr = cpu_leg(O, oivf, Qcpu, k, nprobe, args.cpu_seconds, nthreads, per_call=nthreads * 2)
+        per_call = max(nthreads * 2, 1)
+        while B % per_call:
+            per_call -= 1  # slices must tile the first batch exactly (its results are compared with the GPU's)
+        done, secs, rr = cpu_leg(O, oivf, Qcpu, k, nprobe, args.cpu_seconds, nthreads, per_call=per_call, keep=B)
         cpu_qps = done / secs
         # parity on the sample: identical doc ids and bit-identical scores
         ok = True
@@ -449,7 +455,7 @@ def main():
             ok = ok and np.array_equal(od, gi[off:off + nqs]) and np.array_equal(os_.view(np.uint32), gs[off:off + nqs].view(np.uint32))
             off += nqs
         out["cpu_baseline"] = {"value": cpu_qps, "unit": UNIT, "cores": nthreads, "kind": "port",
-                               "sample": f"{done} queries of the first batch, {secs:.1f} s, C oracle (one query per thread, "
+                               "sample": f"{done} queries (the {Qcpu.shape[0]} bench queries, cycled), {secs:.1f} s, C oracle (one query per thread, "
                                          f"query re-quantized per probed list as in ivf/block_based/index.rs:193)",
                                "parity_with_gpu_on_sample": bool(ok)}
     if rank == 0:

@@ -10,6 +10,7 @@ use std::os::raw::{c_char, c_float, c_int, c_void};
 #[repr(C)] pub struct mgpu_ivf { _p: [u8; 0] }
 #[repr(C)] pub struct mgpu_hnsw { _p: [u8; 0] }
 #[repr(C)] pub struct mgpu_spann { _p: [u8; 0] }
+#[repr(C)] pub struct mgpu_batcher { _p: [u8; 0] }
 #[repr(C)] #[derive(Clone, Copy, Default)] pub struct mgpu_u128 { pub lo: u64, pub hi: u64 }
 
 pub const MGPU_OK: c_int = 0;
@@ -44,6 +45,21 @@ extern "C" {
     pub fn mgpu_spann_search(s: *mut mgpu_spann, q: *const c_float, b: u32, top_k: u32, ef: u32, num_explored_centroids: u32,
                              centroid_distance_ratio: c_float, out_doc_ids: *mut mgpu_u128, out_scores: *mut c_float,
                              out_counts: *mut u32, mem: c_int) -> c_int;
+    pub fn mgpu_ivf_search_filtered(ivf: *mut mgpu_ivf, q: *const c_float, b: u32, k: u32, nprobe: u32, filter_bits: *const u32,
+                                    filter_stride_words: u64, out_doc_ids: *mut mgpu_u128, out_scores: *mut c_float,
+                                    out_counts: *mut u32, mem: c_int) -> c_int;
+    pub fn mgpu_spann_search_filtered(s: *mut mgpu_spann, q: *const c_float, b: u32, top_k: u32, ef: u32,
+                                      num_explored_centroids: u32, centroid_distance_ratio: c_float, filter_bits: *const u32,
+                                      filter_stride_words: u64, out_doc_ids: *mut mgpu_u128, out_scores: *mut c_float,
+                                      out_counts: *mut u32, mem: c_int) -> c_int;
+    pub fn mgpu_batcher_create(ivf: *mut mgpu_ivf, max_batch: u32, max_wait_us: u32, k: u32, nprobe: u32,
+                               out: *mut *mut mgpu_batcher) -> c_int;
+    pub fn mgpu_batcher_create_spann(s: *mut mgpu_spann, max_batch: u32, max_wait_us: u32, top_k: u32, ef: u32,
+                                     num_explored_centroids: u32, centroid_distance_ratio: c_float,
+                                     out: *mut *mut mgpu_batcher) -> c_int;
+    pub fn mgpu_batcher_destroy(b: *mut mgpu_batcher);
+    pub fn mgpu_batcher_search_filtered(b: *mut mgpu_batcher, query: *const c_float, filter_bits: *const u32,
+                                        out_doc_ids: *mut mgpu_u128, out_scores: *mut c_float, out_count: *mut u32) -> c_int;
     // ... the remaining entry points of include/muopdb_gpu.h bind the same way
 }
 
@@ -79,3 +95,24 @@ impl GpuIvf {
         }).collect()).collect())
     }
 }
+
+/// Per-request front door: what `Spann::search` / `BlockBasedIvf::search` call for ONE query (from `spawn_blocking`); the
+/// native worker thread behind `mgpu_batcher_*` forms the batches.
+pub struct GpuBatcher { ctx: *mut mgpu_ctx, b: *mut mgpu_batcher, k: usize }
+unsafe impl Send for GpuBatcher {}
+unsafe impl Sync for GpuBatcher {}
+
+impl GpuBatcher {
+    /// `filter`: the planner's allowed point ids as a bitmap (ceil(N/32) words), or None (index.rs:212-226).
+    pub fn search(&self, query: &[f32], filter: Option<&[u32]>) -> anyhow::Result<Option<Vec<(u128, f32)>>> {
+        let mut ids = vec![mgpu_u128::default(); self.k];
+        let mut scores = vec![0f32; self.k];
+        let mut count = 0u32;
+        let fp = filter.map_or(std::ptr::null(), |f| f.as_ptr());
+        let st = unsafe { mgpu_batcher_search_filtered(self.b, query.as_ptr(), fp, ids.as_mut_ptr(), scores.as_mut_ptr(), &mut count) };
+        check(self.ctx, st)?;
+        if count == u32::MAX { return Ok(None); }                      // Spann::search returned None
+        Ok(Some((0..count as usize).map(|i| (((ids[i].hi as u128) << 64) | ids[i].lo as u128, scores[i])).collect()))
+    }
+}
+impl Drop for GpuBatcher { fn drop(&mut self) { unsafe { mgpu_batcher_destroy(self.b) } } }

@@ -374,6 +374,7 @@ void mgpu_ivf_destroy(mgpu_ivf *ivf) {
   cudaStreamSynchronize(ivf->ctx->stream);
   cudaFree(ivf->d_centroids); cudaFree(ivf->d_csplit); cudaFree(ivf->d_cn); cudaFree(ivf->d_chunk_start); cudaFree(ivf->d_list_len); cudaFree(ivf->d_slot_pid);
   cudaFree(ivf->d_codes); cudaFree(ivf->d_rows); cudaFree(ivf->d_doc_ids); cudaFree(ivf->d_invalid); cudaFree(ivf->d_scan_rows);
+  cudaFree(ivf->d_scan_overflow);
   delete ivf;
 }
 
@@ -433,9 +434,13 @@ static size_t ivf_coarse_extra_ws(mgpu_ivf *ivf, uint32_t B) {  // query split +
 }
 
 // need_order: the caller wants the probes nearest-first (mgpu_ivf_coarse); a search only needs the probe SET
+// fork_ev (optional): recorded at the point after which work that does not depend on the probes may run concurrently
+// d_work / work_done (optional): per-query chunk counts of the chosen lists, when the selection kernel can emit them
 static int ivf_coarse_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, uint32_t nprobe, float *dD, uint32_t *d_ids, float *d_dist,
-                          void *extra_ws, int need_order) {
+                          void *extra_ws, int need_order, cudaEvent_t fork_ev = nullptr, uint32_t *d_work = nullptr,
+                          bool *work_done = nullptr) {
   mgpu_ctx *ctx = ivf->ctx;
+  if (work_done) *work_done = false;
   if (ivf->d_csplit && extra_ws && coarse_tc_applicable(ctx, ivf->dim, ivf->nlist, nprobe)) {
     // tensor-core pass + exact re-score of a provably sufficient candidate set: identical probes to the exact path
     WsAlloc w(extra_ws, ivf_coarse_extra_ws(ivf, B));
@@ -444,8 +449,9 @@ static int ivf_coarse_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, uint32_t n
     uint32_t *ovf = w.get<uint32_t>(4);
     uint32_t *flags = w.get<uint32_t>(B);
     return launch_coarse_tc(ctx, dQ, B, ivf->d_centroids, ivf->d_csplit, ivf->d_cn, ivf->cn_max, ivf->nlist, ivf->dim, nprobe, qsplit,
-                            qn, dD, ovf, flags, need_order, d_ids, d_dist);
+                            qn, dD, ovf, flags, need_order, d_ids, d_dist, ivf->d_chunk_start, d_work, work_done, fork_ev);
   }
+  if (fork_ev) CUDA_TRY(ctx, cudaEventRecord(fork_ev, ctx->stream));
   // always the L2 calculator with sqrt (index.rs:155), whatever the quantizer's metric
   MGPU_TRY(launch_distance_matrix(ctx, dQ, B, ivf->d_centroids, ivf->nlist, ivf->dim, MGPU_L2, 1, dD, MGPU_K_COARSE));
   return launch_select_smallest(ctx, dD, B, ivf->nlist, nprobe, d_ids, d_dist);
@@ -482,7 +488,8 @@ int mgpu_ivf_coarse(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t nprobe, 
 static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32_t *d_probes, uint32_t max_probes,
                         const uint32_t *d_counts, uint32_t k, uint8_t *d_qcodes, uint64_t *d_ckey, uint32_t *d_cslot,
                         uint32_t *d_order, uint32_t *d_out_pids, mgpu_u128 *d_out_docs, float *d_out_scores, uint32_t *d_out_counts,
-                        bool qcodes_on_aux = false, const uint32_t *d_filter = nullptr, uint64_t filter_stride = 0) {
+                        bool qcodes_on_aux = false, const uint32_t *d_filter = nullptr, uint64_t filter_stride = 0,
+                        bool have_work = false) {
   mgpu_ctx *ctx = ivf->ctx;
   CUDA_TRY(ctx, cudaMemsetAsync(ivf->d_scan_rows, 0, 8, ctx->stream));
   ScanArgs a;
@@ -505,7 +512,7 @@ static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32
   // longest-first query schedule for the persistent scan CTAs (MGPU_PLAN=0 disables it)
   static const bool use_plan = !(getenv("MGPU_PLAN") && getenv("MGPU_PLAN")[0] == '0');
   if (use_plan && d_order && B > 2 * (uint32_t)ctx->sm_count) {
-    MGPU_TRY(launch_plan_queries(ivf, d_probes, max_probes, d_counts, B, d_order, d_order + B));
+    MGPU_TRY(launch_plan_queries(ivf, d_probes, max_probes, d_counts, B, d_order, d_order + B, have_work));
     a.order = d_order;
   }
   MGPU_TRY(launch_scan(ivf, a));
@@ -587,18 +594,20 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
   const uint32_t *dF = filter_bits;
   if (bF) { const void *t; MGPU_TRY(stage_in(ctx, filter_bits, bF, mem, sF, &t)); dF = (const uint32_t *)t; }
   const uint32_t *dP, *dPC = nullptr;
-  bool qcodes_on_aux = false;
+  bool qcodes_on_aux = false, have_work = false;
   if (do_coarse) {
-    // the query encode (index.rs:193) does not depend on the coarse scoring: run it on the side stream meanwhile
+    // the query encode (index.rs:193) does not depend on the probes: it runs on the side stream next to the (latency
+    // bound) selection kernel, forked right after the coarse GEMM -- the GEMM itself wants every SM's shared memory
     static const bool use_aux = !(getenv("MGPU_AUX_STREAM") && getenv("MGPU_AUX_STREAM")[0] == '0');
-    if (use_aux && ivf->quant == MGPU_QUANT_PQ) {
-      CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    const bool fork = use_aux && ivf->quant == MGPU_QUANT_PQ;
+    MGPU_TRY(ivf_coarse_dev(ivf, (const float *)dQ, B, nprobe_coarse, dD, sP, nullptr, xws, 0, fork ? ctx->ev_fork : nullptr,
+                            dOrd + B, &have_work));
+    if (fork) {
       CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
       MGPU_TRY(launch_pq_quantize(ivf->pq, (const float *)dQ, B, dQC, ctx->aux_stream));
       CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
       qcodes_on_aux = true;
     }
-    MGPU_TRY(ivf_coarse_dev(ivf, (const float *)dQ, B, nprobe_coarse, dD, sP, nullptr, xws, 0));
     dP = sP;
   } else {
     const void *t;
@@ -610,7 +619,7 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
   mgpu_u128 *oD = out_docs ? (mem == MGPU_DEVICE ? out_docs : sDocs) : nullptr;
   float *oS = mem == MGPU_DEVICE ? out_scores : sScores;
   uint32_t *oC = mem == MGPU_DEVICE ? out_counts : sCounts;
-  MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, dP, max_probes, dPC, k, dQC, dCK, dCS, dOrd, oP, oD, oS, oC, qcodes_on_aux, dF, filter_stride));
+  MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, dP, max_probes, dPC, k, dQC, dCK, dCS, dOrd, oP, oD, oS, oC, qcodes_on_aux, dF, filter_stride, have_work));
   if (mem == MGPU_HOST) {
     MGPU_TRY(stage_out(ctx, out_pids, oP, (size_t)B * k * 4, mem));
     MGPU_TRY(stage_out(ctx, out_docs, oD, (size_t)B * k * 16, mem));
@@ -899,7 +908,28 @@ int mgpu_hnsw_create(mgpu_ctx *ctx, uint32_t dim, uint32_t num_layers, const uin
       }
     }
   }
+  // fixed-stride copy of the layer-0 adjacency lists (layer 0 is addressed by point id, graph_storage.rs:465-478)
+  std::vector<uint32_t> edges0;
+  {
+    const uint64_t l0 = level_offsets[num_layers - 1];
+    uint64_t maxdeg = 0;
+    bool ok = true;
+    for (uint64_t p = 0; p < n && ok; p++) {
+      if (edge_offsets[l0 + p + 1] < edge_offsets[l0 + p] || edge_offsets[l0 + p + 1] > n_edges) ok = false;
+      else maxdeg = std::max<uint64_t>(maxdeg, edge_offsets[l0 + p + 1] - edge_offsets[l0 + p]);
+    }
+    const uint64_t stride = (maxdeg + 7) & ~7ull;
+    if (ok && maxdeg > 0 && stride <= 64 && n * stride * 4 <= (4ull << 30)) {
+      h->deg0 = (uint32_t)stride;
+      edges0.assign((size_t)n * stride, 0xFFFFFFFFu);
+      for (uint64_t p = 0; p < n; p++) {
+        const uint64_t b = edge_offsets[l0 + p], e = edge_offsets[l0 + p + 1];
+        for (uint64_t i = b; i < e; i++) edges0[(size_t)p * stride + (i - b)] = edges[i];
+      }
+    }
+  }
   int s = dev_alloc_copy(ctx, &h->d_edges, edges, n_edges);
+  if (s == MGPU_OK && !edges0.empty()) s = dev_alloc_copy(ctx, &h->d_edges0, edges0.data(), edges0.size());
   if (s == MGPU_OK && !dense.empty()) s = dev_alloc_copy(ctx, &h->d_upper_dense, dense.data(), dense.size());
   if (s == MGPU_OK) s = dev_alloc_copy(ctx, &h->d_points, points, n_points);
   if (s == MGPU_OK) s = dev_alloc_copy(ctx, &h->d_edge_offsets, edge_offsets, n_edge_offsets);
@@ -919,7 +949,7 @@ void mgpu_hnsw_destroy(mgpu_hnsw *h) {
   cudaSetDevice(h->ctx->device);
   cudaStreamSynchronize(h->ctx->stream);
   cudaFree(h->d_edges); cudaFree(h->d_points); cudaFree(h->d_edge_offsets); cudaFree(h->d_level_offsets);
-  cudaFree(h->d_upper_sorted_pid); cudaFree(h->d_upper_sorted_pos); cudaFree(h->d_upper_dense); cudaFree(h->d_rows); cudaFree(h->d_doc_ids);
+  cudaFree(h->d_upper_sorted_pid); cudaFree(h->d_upper_sorted_pos); cudaFree(h->d_upper_dense); cudaFree(h->d_edges0); cudaFree(h->d_rows); cudaFree(h->d_doc_ids);
   delete h;
 }
 

@@ -436,48 +436,49 @@ k_coarse_select(const float *__restrict__ Dt, const float *__restrict__ Q, const
   }
 }
 
-// ---- warp-per-query selection (the fast path) --------------------------------------------------------------------------------
-// Same rule as k_coarse_select, but one WARP owns a query and there are no CTA barriers.  The D~ row (C <= 4096 values) is
-// pulled into a private slice of shared memory with ONE burst of cp.async (every 16-byte piece in flight at once),
-// converted to ordered keys in place, and all later passes (range, two histogram levels, classification) run at
-// shared-memory speed.  Sure centroids are emitted in ascending D~ order (the scan prunes best when the nearest lists come
-// first), the band is re-scored exactly and appended.  Queries whose band does not fit the private lists are flagged and
-// finished by k_coarse_select.
-#define SELW_WARPS 4
+// ---- small-CTA selection (the fast path) -------------------------------------------------------------------------------------
+// Same rule as k_coarse_select, one CTA of 4 warps per query, built for latency: the D~ row (C <= 4096 values) is pulled
+// into shared memory with ONE burst of cp.async (every 16-byte piece in flight at once), converted to ordered keys in
+// place, and all later passes (range, two histogram levels, classification) run at shared-memory speed.  Sure centroids
+// are emitted in ascending D~ order (the scan prunes best when the nearest lists come first), the band is re-scored
+// exactly and appended.  Queries whose band does not fit the candidate lists are flagged and finished by
+// k_coarse_select.  Optionally emits work[q] = number of 32-row chunks in the chosen lists (the scan's LPT schedule).
+#define SELQ_THREADS 128
+#define SELQ_WARPS (SELQ_THREADS / 32)
 #define SELW_CAP 256
 #define SELW_MAXC 4096
 #define SELW_BINS 1024
-#define SELW_BYTES (SELW_MAXC * 4 + SELW_BINS * 4 + SELW_CAP * 8 + SELW_CAP * 8 + SELW_CAP * 4 + 16)
-#define SELW_MLP 16
+#define SELW_BYTES (SELW_MAXC * 4 + SELW_BINS * 4 + SELW_CAP * 8 + SELW_CAP * 8 + SELW_CAP * 4 + 64)
+#define SELW_MLP 8   /* 4 warps x 8 x 32 lanes x 16 B = the 16 KB key space */
 __device__ __forceinline__ void selw_cp_async16(void *smem_dst, const void *gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void selw_cp_async_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
-__global__ void __launch_bounds__(SELW_WARPS * 32)
-k_coarse_select_warp(const float *__restrict__ Dt, const float *__restrict__ Q, const float *__restrict__ centroids,
-                     const float *__restrict__ qn, float cn_max, uint32_t B, uint32_t C, uint32_t dim, uint32_t nprobe,
-                     int need_order, uint32_t *__restrict__ out_ids, float *__restrict__ out_dist, uint32_t *__restrict__ flags) {
+__global__ void __launch_bounds__(SELQ_THREADS)
+k_coarse_select_q(const float *__restrict__ Dt, const float *__restrict__ Q, const float *__restrict__ centroids,
+                  const float *__restrict__ qn, float cn_max, uint32_t C, uint32_t dim, uint32_t nprobe, int need_order,
+                  uint32_t *__restrict__ out_ids, float *__restrict__ out_dist, uint32_t *__restrict__ flags,
+                  const uint32_t *__restrict__ chunk_start, uint32_t *__restrict__ work_out) {
   extern __shared__ __align__(16) uint8_t sm[];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const uint32_t q = blockIdx.x * SELW_WARPS + w;
-  if (q >= B) return;
-  uint8_t *my = sm + (size_t)w * SELW_BYTES;
-  uint32_t *keys = (uint32_t *)my;                       // C ordered keys (first the raw floats)
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t q = blockIdx.x;
+  uint32_t *keys = (uint32_t *)sm;                       // C ordered keys (first the raw floats)
   uint32_t *hist = keys + SELW_MAXC;                     // SELW_BINS
   uint64_t *skey = (uint64_t *)(hist + SELW_BINS);       // SELW_CAP: (approximate key, index) of the sure centroids
   uint64_t *ckey = skey + SELW_CAP;                      // SELW_CAP: (exact key, index) of the band
   uint32_t *cand = (uint32_t *)(ckey + SELW_CAP);        // SELW_CAP: band indices
-  uint32_t *cnt = cand + SELW_CAP;                       // [0] sure, [1] band
+  uint32_t *misc = cand + SELW_CAP;                      // [0] sure [1] band [2] bin [3] rank [4..7] warp sums [8] kmin [9] kmax [10] work
   const float4 *row4 = (const float4 *)(Dt + (size_t)q * C);
   const uint32_t C4 = C / 4;
-  // ---- the row, one burst
-  for (uint32_t i = lane; i < C4; i += 32) selw_cp_async16((uint4 *)keys + i, row4 + i);
+  // ---- the row, one burst; every thread converts the pieces it fetched itself (no barrier needed in between)
+  for (uint32_t i = tid; i < C4; i += SELQ_THREADS) selw_cp_async16((uint4 *)keys + i, row4 + i);
+  for (int i = tid; i < SELW_BINS / 4; i += SELQ_THREADS) ((uint4 *)hist)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) { misc[0] = 0; misc[1] = 0; misc[3] = nprobe - 1; misc[8] = 0xFFFFFFFFu; misc[9] = 0u; misc[10] = 0u; }
   selw_cp_async_wait();
-  // ---- keys in place + key range
   uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
 #pragma unroll 4
-  for (uint32_t i = lane; i < C4; i += 32) {
+  for (uint32_t i = tid; i < C4; i += SELQ_THREADS) {
     const float4 v = ((const float4 *)keys)[i];
     const uint4 k4 = make_uint4(f2key(v.x), f2key(v.y), f2key(v.z), f2key(v.w));
     ((uint4 *)keys)[i] = k4;
@@ -489,143 +490,192 @@ k_coarse_select_warp(const float *__restrict__ Dt, const float *__restrict__ Q, 
     kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
     kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
   }
+  __syncthreads();  // misc / hist initialised
+  if (lane == 0) { atomicMin(&misc[8], kmin); atomicMax(&misc[9], kmax); }
+  __syncthreads();
   // ---- two histogram levels over [kmin, kmax]: the key interval [lo_key, hi_key] of width range / 2^20 holding tau
-  uint32_t base = kmin, width_log = 32 - __clz((kmax - kmin) | 1u);
-  uint32_t lo_key = kmin, hi_key = kmax, rank = nprobe - 1;
+  uint32_t base = misc[8];
+  uint32_t width_log = 32 - __clz((misc[9] - base) | 1u);
+  uint32_t lo_key = base, hi_key = misc[9];
   for (int pass = 0; pass < 2; pass++) {
     const uint32_t shift = width_log > 10 ? width_log - 10 : 0;
-    for (int i = lane; i < SELW_BINS / 4; i += 32) ((uint4 *)hist)[i] = make_uint4(0, 0, 0, 0);
-    __syncwarp();
 #pragma unroll 4
-    for (uint32_t i = lane; i < C4; i += 32) {
+    for (uint32_t i = tid; i < C4; i += SELQ_THREADS) {
       const uint4 k4 = ((const uint4 *)keys)[i];
       if (k4.x >= lo_key && k4.x <= hi_key) atomicAdd(&hist[(k4.x - base) >> shift], 1u);
       if (k4.y >= lo_key && k4.y <= hi_key) atomicAdd(&hist[(k4.y - base) >> shift], 1u);
       if (k4.z >= lo_key && k4.z <= hi_key) atomicAdd(&hist[(k4.z - base) >> shift], 1u);
       if (k4.w >= lo_key && k4.w <= hi_key) atomicAdd(&hist[(k4.w - base) >> shift], 1u);
     }
-    __syncwarp();
-    // lane l owns bins [32 l, 32 l + 32); rotated read order keeps the 32 lanes on 32 different banks
-    constexpr int PER = SELW_BINS / 32;
-    uint32_t sum = 0;
-#pragma unroll 8
-    for (int j = 0; j < PER; j++) sum += hist[lane * PER + ((j + lane) & (PER - 1))];
+    __syncthreads();
+    // thread t owns bins [8 t, 8 t + 8); rotated read order spreads a warp over the banks
+    constexpr int PER = SELW_BINS / SELQ_THREADS;
+    uint32_t loc[PER], sum = 0;
+#pragma unroll
+    for (int j = 0; j < PER; j++) { loc[j] = hist[tid * PER + ((j + lane) & (PER - 1))]; sum += loc[j]; }
     uint32_t incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += v;
     }
-    const uint32_t excl = incl - sum;
-    const bool mine = rank >= excl && rank < incl;  // exactly one lane
-    uint32_t bsel = 0, rr = 0;
-    if (mine) {
-      rr = rank - excl;
+    if (lane == 31) misc[4 + w] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (int j = 0; j < SELQ_WARPS; j++) before += j < w ? misc[4 + j] : 0u;
+    const uint32_t rank = misc[3];
+    const uint32_t excl = before + incl - sum;
+    if (rank >= excl && rank < excl + sum) {  // exactly one thread
+      uint32_t rr = rank - excl;
       int bb = 0;
-      for (; bb < PER - 1; bb++) { uint32_t h = hist[lane * PER + bb]; if (rr < h) break; rr -= h; }
-      bsel = (uint32_t)(lane * PER + bb);
+      for (; bb < PER - 1; bb++) { uint32_t h = hist[tid * PER + bb]; if (rr < h) break; rr -= h; }
+      misc[2] = (uint32_t)(tid * PER + bb);
+      misc[3] = rr;
     }
-    const int owner = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
-    bsel = __shfl_sync(0xffffffffu, bsel, owner);
-    rank = __shfl_sync(0xffffffffu, rr, owner);
+    __syncthreads();
+    const uint32_t bsel = misc[2];
     lo_key = base + (bsel << shift);
     hi_key = shift ? lo_key + ((1u << shift) - 1u) : lo_key;
     if (shift == 0) break;
     base = lo_key;
     width_log = shift;
+    if (pass == 0) {
+      for (int i = tid; i < SELW_BINS / 4; i += SELQ_THREADS) ((uint4 *)hist)[i] = make_uint4(0, 0, 0, 0);
+      __syncthreads();
+    }
   }
-  if (lane == 0) { cnt[0] = 0; cnt[1] = 0; }
-  __syncwarp();
   const float eps = TC_ERR_REL * (qn[q] + cn_max);
   const uint32_t lim_hi = f2key(sel_key2f(hi_key) + 2.0f * eps);
   const uint32_t lim_lo = need_order ? 0u : f2key(sel_key2f(lo_key) - 2.0f * eps);
   // ---- classification (hits are rare: plain shared-memory counters)
 #pragma unroll 4
-  for (uint32_t i = lane; i < C4; i += 32) {
+  for (uint32_t i = tid; i < C4; i += SELQ_THREADS) {
     const uint4 k4 = ((const uint4 *)keys)[i];
     const uint32_t kk[4] = {k4.x, k4.y, k4.z, k4.w};
 #pragma unroll
     for (int c = 0; c < 4; c++) {
       if (kk[c] < lim_lo) {
-        const uint32_t pos = atomicAdd(&cnt[0], 1u);
+        const uint32_t pos = atomicAdd(&misc[0], 1u);
         if (pos < SELW_CAP) skey[pos] = ((uint64_t)kk[c] << 32) | (4 * i + c);
       } else if (kk[c] <= lim_hi) {
-        const uint32_t pos = atomicAdd(&cnt[1], 1u);
+        const uint32_t pos = atomicAdd(&misc[1], 1u);
         if (pos < SELW_CAP) cand[pos] = 4 * i + c;
       }
     }
   }
-  __syncwarp();
-  const uint32_t nsure = min(cnt[0], nprobe);   // <= nprobe - 1 by construction
-  const uint32_t ncand = cnt[1];
-  if (ncand > SELW_CAP || nsure > SELW_CAP) {   // does not fit the private lists: k_coarse_select finishes this query
-    if (lane == 0) flags[q] = 1u;
+  __syncthreads();
+  const uint32_t nsure = min(misc[0], nprobe);   // <= nprobe - 1 by construction
+  const uint32_t ncand = misc[1];
+  if (ncand > SELW_CAP || nsure > SELW_CAP) {   // does not fit the candidate lists: k_coarse_select finishes this query
+    if (tid == 0) { flags[q] = 1u; if (work_out) work_out[q] = 0; }
     return;
   }
   const uint32_t need = nprobe - nsure;
   uint32_t *oi = out_ids + (size_t)q * nprobe;
+  uint32_t mywork = 0;
   // sure centroids, ascending approximate distance (rank by counting; keys are distinct)
-  for (uint32_t e = lane; e < nsure; e += 32) {
+  for (uint32_t e = tid; e < nsure; e += SELQ_THREADS) {
     const uint64_t kk = skey[e];
     uint32_t r = 0;
     for (uint32_t j = 0; j < nsure; j++) r += skey[j] < kk ? 1u : 0u;
     oi[r] = (uint32_t)kk;
+    if (chunk_start) mywork += chunk_start[(uint32_t)kk + 1] - chunk_start[(uint32_t)kk];
   }
   if (!need_order && ncand <= need) {  // the whole band belongs to the answer
-    for (uint32_t e = lane; e < ncand; e += 32) oi[nsure + e] = cand[e];
-    return;
-  }
-  // ---- exact sqrt-L2 (l2.rs:30-74) of the band: 4 lanes per pair, lane r owns lane-accumulators 4r..4r+3.
-  // cp.async (no register destination) keeps SELW_MLP 16-byte centroid loads in flight per lane -- a plain load is
-  // scheduled next to its use, which turns the loop into a chain of L2 round trips.  The ring re-uses the key space.
-  const int n = (int)dim, chunks = n / 16;
-  const int r4 = lane & 3, grp = lane >> 2, gl = lane & ~3;
-  const float4 *q4 = (const float4 *)(Q + (size_t)q * dim) + r4;
-  float4 *ring = (float4 *)keys;
-  __syncwarp();
-  for (uint32_t b0 = 0; b0 < ncand; b0 += 8) {
-    const uint32_t j = b0 + grp;
-    const uint32_t cidx = cand[j < ncand ? j : ncand - 1];
-    const float *crow = centroids + (size_t)cidx * dim;
-    const float4 *c4 = (const float4 *)crow + r4;
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-    for (int c = 0; c < chunks; c += SELW_MLP) {
-      const int nb = min(SELW_MLP, chunks - c);
-      for (int u = 0; u < nb; u++) selw_cp_async16(&ring[u * 32 + lane], c4 + (c + u) * 4);
+    for (uint32_t e = tid; e < ncand; e += SELQ_THREADS) {
+      oi[nsure + e] = cand[e];
+      if (chunk_start) mywork += chunk_start[cand[e] + 1] - chunk_start[cand[e]];
+    }
+  } else {
+    // ---- exact sqrt-L2 (l2.rs:30-74) of the band: 4 lanes per pair, lane r owns lane-accumulators 4r..4r+3.
+    // cp.async (no register destination) keeps SELW_MLP 16-byte centroid loads in flight per lane -- a plain load is
+    // scheduled next to its use, which turns the loop into a chain of L2 round trips.  The ring re-uses the key space.
+    const int n = (int)dim, chunks = n / 16;
+    const int r4 = lane & 3, grp = lane >> 2, gl = lane & ~3;
+    const float4 *q4 = (const float4 *)(Q + (size_t)q * dim) + r4;
+    float4 *ring = (float4 *)keys + w * (SELW_MLP * 32);
+    // small band (the usual case): ONE burst brings every band row and the query into shared memory (key + histogram
+    // space, both dead by now), so the exact arithmetic runs from shared memory after a single L2 round trip
+    const uint32_t dim4 = dim / 4;
+    const bool burst = (size_t)ncand * dim <= SELW_MAXC && dim <= SELW_BINS;
+    float4 *rowbuf = (float4 *)keys, *qbuf = (float4 *)hist;
+    if (burst) {
+      __syncthreads();  // every thread is done reading keys / hist
+      for (uint32_t i = tid; i < ncand * dim4; i += SELQ_THREADS) {
+        const uint32_t j = i / dim4, piece = i - j * dim4;
+        selw_cp_async16(rowbuf + i, (const float4 *)(centroids + (size_t)cand[j] * dim) + piece);
+      }
+      for (uint32_t i = tid; i < dim4; i += SELQ_THREADS) selw_cp_async16(qbuf + i, (const float4 *)(Q + (size_t)q * dim) + i);
       selw_cp_async_wait();
-      for (int u = 0; u < nb; u++) {
-        const float4 x = __ldg(q4 + (c + u) * 4), y = ring[u * 32 + lane];
-        float d;
-        d = __fsub_rn(x.x, y.x); a0 = __fadd_rn(a0, __fmul_rn(d, d));
-        d = __fsub_rn(x.y, y.y); a1 = __fadd_rn(a1, __fmul_rn(d, d));
-        d = __fsub_rn(x.z, y.z); a2 = __fadd_rn(a2, __fmul_rn(d, d));
-        d = __fsub_rn(x.w, y.w); a3 = __fadd_rn(a3, __fmul_rn(d, d));
+      __syncthreads();
+    }
+    for (uint32_t b0 = w * 8; b0 < ncand; b0 += SELQ_WARPS * 8) {
+      const uint32_t j = b0 + grp;
+      const uint32_t jc = j < ncand ? j : ncand - 1;
+      const uint32_t cidx = cand[jc];
+      const float *crow = centroids + (size_t)cidx * dim;
+      const float4 *c4 = (const float4 *)crow + r4;
+      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+      if (burst) {
+        const float4 *rb = rowbuf + (size_t)jc * dim4 + r4, *qb = qbuf + r4;
+#pragma unroll 4
+        for (int c = 0; c < chunks; c++) {
+          const float4 x = qb[c * 4], y = rb[c * 4];
+          float d;
+          d = __fsub_rn(x.x, y.x); a0 = __fadd_rn(a0, __fmul_rn(d, d));
+          d = __fsub_rn(x.y, y.y); a1 = __fadd_rn(a1, __fmul_rn(d, d));
+          d = __fsub_rn(x.z, y.z); a2 = __fadd_rn(a2, __fmul_rn(d, d));
+          d = __fsub_rn(x.w, y.w); a3 = __fadd_rn(a3, __fmul_rn(d, d));
+        }
+      } else {
+        for (int c = 0; c < chunks; c += SELW_MLP) {
+          const int nb = min(SELW_MLP, chunks - c);
+          for (int u = 0; u < nb; u++) selw_cp_async16(&ring[u * 32 + lane], c4 + (c + u) * 4);
+          selw_cp_async_wait();
+          for (int u = 0; u < nb; u++) {
+            const float4 x = __ldg(q4 + (c + u) * 4), y = ring[u * 32 + lane];
+            float d;
+            d = __fsub_rn(x.x, y.x); a0 = __fadd_rn(a0, __fmul_rn(d, d));
+            d = __fsub_rn(x.y, y.y); a1 = __fadd_rn(a1, __fmul_rn(d, d));
+            d = __fsub_rn(x.z, y.z); a2 = __fadd_rn(a2, __fmul_rn(d, d));
+            d = __fsub_rn(x.w, y.w); a3 = __fadd_rn(a3, __fmul_rn(d, d));
+          }
+        }
+      }
+      float s2 = -0.0f;  // ordered lane reduction 0..15
+#pragma unroll
+      for (int l = 0; l < 4; l++) {
+        s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, a0, gl + l));
+        s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, a1, gl + l));
+        s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, a2, gl + l));
+        s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, a3, gl + l));
+      }
+      float ret = __fadd_rn(0.0f, s2);
+      const int p = chunks * 16;
+      if (p < n) ret = ref_tail<MGPU_L2>(PtrAcc{Q + (size_t)q * dim}, PtrAcc{crow}, p, n, ret);
+      const float dist = sqrtf(ret);
+      if (j < ncand && r4 == 0) ckey[j] = ((uint64_t)f2key(dist) << 32) | cidx;
+    }
+    __syncthreads();
+    float *od = out_dist ? out_dist + (size_t)q * nprobe + nsure : nullptr;
+    for (uint32_t e = tid; e < ncand; e += SELQ_THREADS) {
+      const uint64_t kk = ckey[e];
+      uint32_t r = 0;
+      for (uint32_t j = 0; j < ncand; j++) r += ckey[j] < kk ? 1u : 0u;
+      if (r < need) {
+        oi[nsure + r] = (uint32_t)kk;
+        if (od) od[r] = sel_key2f((uint32_t)(kk >> 32));
+        if (chunk_start) mywork += chunk_start[(uint32_t)kk + 1] - chunk_start[(uint32_t)kk];
       }
     }
-    float s2 = -0.0f;  // ordered lane reduction 0..15
-#pragma unroll
-    for (int l = 0; l < 4; l++) {
-      s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, a0, gl + l));
-      s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, a1, gl + l));
-      s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, a2, gl + l));
-      s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, a3, gl + l));
-    }
-    float ret = __fadd_rn(0.0f, s2);
-    const int p = chunks * 16;
-    if (p < n) ret = ref_tail<MGPU_L2>(PtrAcc{Q + (size_t)q * dim}, PtrAcc{crow}, p, n, ret);
-    const float dist = sqrtf(ret);
-    if (j < ncand && r4 == 0) ckey[j] = ((uint64_t)f2key(dist) << 32) | cidx;
   }
-  __syncwarp();
-  float *od = out_dist ? out_dist + (size_t)q * nprobe + nsure : nullptr;
-  for (uint32_t e = lane; e < ncand; e += 32) {
-    const uint64_t kk = ckey[e];
-    uint32_t r = 0;
-    for (uint32_t j = 0; j < ncand; j++) r += ckey[j] < kk ? 1u : 0u;
-    if (r < need) {
-      oi[nsure + r] = (uint32_t)kk;
-      if (od) od[r] = sel_key2f((uint32_t)(kk >> 32));
-    }
+  if (work_out) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mywork += __shfl_xor_sync(0xffffffffu, mywork, o);
+    if (lane == 0 && mywork) atomicAdd(&misc[10], mywork);
+    __syncthreads();
+    if (tid == 0) work_out[q] = misc[10];
   }
 }
 
@@ -684,7 +734,8 @@ int launch_split_bf16(mgpu_ctx *ctx, const float *dX, uint64_t n, uint32_t dim, 
 // d_Dt: B x C floats of workspace; d_qsplit: B x Kp bf16; d_qn: B floats
 int launch_coarse_tc(mgpu_ctx *ctx, const float *dQ, uint32_t B, const float *d_centroids, const void *d_csplit, const float *d_cn,
                      float cn_max, uint32_t C, uint32_t dim, uint32_t nprobe, void *d_qsplit, float *d_qn, float *d_Dt,
-                     uint32_t *d_overflow, uint32_t *d_flags, int need_order, uint32_t *out_ids, float *out_dist) {
+                     uint32_t *d_overflow, uint32_t *d_flags, int need_order, uint32_t *out_ids, float *out_dist,
+                     const uint32_t *chunk_start, uint32_t *d_work, bool *work_done, cudaEvent_t after_gemm) {
   const uint32_t Kp = coarse_tc_kp(dim);
   MGPU_TRY(launch_split_bf16(ctx, dQ, B, dim, 0, d_qsplit, d_qn));
   CUtensorMap mq, mc;
@@ -698,23 +749,25 @@ int launch_coarse_tc(mgpu_ctx *ctx, const float *dQ, uint32_t B, const float *d_
     k_coarse_gemm<<<grid, TC_THREADS, smem, ctx->stream>>>(mq, mc, d_qn, d_cn, B, C, Kp, d_Dt);
     CUDA_TRY(ctx, cudaGetLastError());
   }
+  if (after_gemm) CUDA_TRY(ctx, cudaEventRecord(after_gemm, ctx->stream));  // fork point for work that may overlap the selection
   uint32_t cap = 1;
   while (cap < C) cap <<= 1;
   size_t ssel = ((dim + 3) & ~3u) * 4 + (size_t)cap * 12 + SEL_BINS * 4 + 64;
   static const bool force_order = getenv("MGPU_COARSE_ORDER") && getenv("MGPU_COARSE_ORDER")[0] == '1';
   if (force_order || out_dist) need_order = 1;
   CUDA_TRY(ctx, cudaFuncSetAttribute(k_coarse_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssel));
-  static const bool no_warp = getenv("MGPU_SELECT_WARP") && getenv("MGPU_SELECT_WARP")[0] == '0';
+  static const bool no_warp = getenv("MGPU_SELECT_FAST") && getenv("MGPU_SELECT_FAST")[0] == '0';
   const uint32_t *only_flagged = nullptr;
+  if (work_done) *work_done = false;
   if (!no_warp && (dim & 3u) == 0 && nprobe <= SELW_CAP && C <= SELW_MAXC && d_flags) {
     CUDA_TRY(ctx, cudaMemsetAsync(d_flags, 0, (size_t)B * 4, ctx->stream));
-    const size_t sw = (size_t)SELW_WARPS * SELW_BYTES;
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_coarse_select_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_coarse_select_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELW_BYTES));
     LaunchScope ls(ctx, MGPU_K_SELECT);
-    k_coarse_select_warp<<<(B + SELW_WARPS - 1) / SELW_WARPS, SELW_WARPS * 32, sw, ctx->stream>>>(
-        d_Dt, dQ, d_centroids, d_qn, cn_max, B, C, dim, nprobe, need_order, out_ids, out_dist, d_flags);
+    k_coarse_select_q<<<B, SELQ_THREADS, SELW_BYTES, ctx->stream>>>(d_Dt, dQ, d_centroids, d_qn, cn_max, C, dim, nprobe, need_order,
+                                                                     out_ids, out_dist, d_flags, d_work ? chunk_start : nullptr, d_work);
     CUDA_TRY(ctx, cudaGetLastError());
     only_flagged = d_flags;
+    if (work_done && d_work) *work_done = true;
   }
   {
     LaunchScope ls(ctx, MGPU_K_SELECT);

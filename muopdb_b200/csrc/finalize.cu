@@ -102,7 +102,7 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 template <int METRIC>
 __global__ void __launch_bounds__(FIN8_THREADS) k_finalize_pq8(FinalizeArgs a) {
   extern __shared__ __align__(16) uint8_t fsm[];
-  const uint32_t m = a.m, mp = (m + 15) & ~15u;
+  const uint32_t m = a.m, mp = ((m + 15) & ~15u) + 4;  // +4: odd word stride between candidates (bank spread)
   float4 *qv4 = (float4 *)fsm;                     // m x 2: centroid of the query code per subspace
   uint8_t *cc = (uint8_t *)(qv4 + (size_t)m * 2);  // 32 x mp: candidate codes
   uint32_t *skeys = (uint32_t *)(cc + (size_t)MGPU_NCAND * mp);  // 32 exact score keys
@@ -195,7 +195,7 @@ int launch_finalize(mgpu_ctx *ctx, const FinalizeArgs &a) {
   if (a.B == 0) return MGPU_OK;
   if (a.k > MGPU_NCAND) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported by the scan kernels yet", a.k, MGPU_NCAND);
   LaunchScope ls(ctx, MGPU_K_FINALIZE);
-  const size_t smem8 = (size_t)a.m * 32 + (size_t)MGPU_NCAND * ((a.m + 15) & ~15u) + MGPU_NCAND * 8 + (size_t)FIN8_MLP * 2 * MGPU_NCAND * 16;
+  const size_t smem8 = (size_t)a.m * 32 + (size_t)MGPU_NCAND * (((a.m + 15) & ~15u) + 4) + MGPU_NCAND * 8 + (size_t)FIN8_MLP * 2 * MGPU_NCAND * 16;
   static const bool no8 = getenv("MGPU_FINALIZE8") && getenv("MGPU_FINALIZE8")[0] == '0';
   if (a.cb != nullptr && a.dsub == 8 && smem8 <= 96 * 1024 && !no8) {
     if (a.metric == MGPU_L2) {

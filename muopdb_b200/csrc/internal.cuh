@@ -47,6 +47,10 @@ struct mgpu_ivf {
   unsigned long long *d_scan_rows = nullptr;  // [0] rows scanned by the last scan, [1] query scheduler counter
   uint64_t bytes_per_row = 0;
   std::vector<uint32_t> h_list_len;
+  uint32_t *d_scan_overflow = nullptr;   // [0] count, [1..] query ids deferred by the table-driven PQ scan
+  uint32_t scan_overflow_cap = 0;
+  uint32_t scan_bound_probes = 0;        // cache: upper bound of chunks any `scan_bound_probes` lists can hold
+  uint64_t scan_bound_chunks = 0;
 };
 
 struct mgpu_hnsw {
@@ -66,6 +70,10 @@ struct mgpu_hnsw {
   // upper-layer point -> position lookup: sorted (point, pos) pairs per layer
   uint32_t *d_upper_sorted_pid = nullptr, *d_upper_sorted_pos = nullptr;
   int32_t *d_upper_dense = nullptr;  // dense (layer, point) -> position map for the upper layers (optional)
+  // layer-0 adjacency in fixed-stride rows (optional): edges0[p * deg0 .. ) = the edges of point p in stored order, padded
+  // with 0xFFFFFFFF.  One load instead of edge_offsets -> edges (two dependent loads) per expansion.
+  uint32_t *d_edges0 = nullptr;
+  uint32_t deg0 = 0;
 };
 
 struct mgpu_spann {
@@ -96,6 +104,8 @@ struct ScanArgs {
   // planner filter hook (index.rs:212-226): when non-null a scanned row survives only if bit `point id` of its query's
   // bitmap is set; query q uses filter + q * filter_stride (stride 0 = one bitmap shared by the whole batch)
   const uint32_t *filter; uint64_t filter_stride;
+  // PQ table-driven scan: queries with more chunks than the shared-memory chunk table are deferred to a second launch
+  unsigned int *overflow_count; uint32_t *overflow_list;
   int metric;
 };
 
@@ -105,7 +115,7 @@ int launch_pq_distance_pairs(mgpu_pq *pq, const uint8_t *da, const uint8_t *db, 
 int launch_build_layout(mgpu_ivf *ivf, const void *d_rows_by_pid);
 int launch_scan(mgpu_ivf *ivf, const ScanArgs &a);
 int launch_plan_queries(mgpu_ivf *ivf, const uint32_t *d_probes, uint32_t max_probes, const uint32_t *d_counts, uint32_t B,
-                        uint32_t *d_order, uint32_t *d_work);
+                        uint32_t *d_order, uint32_t *d_work, bool have_work = false);
 int launch_scan_pq_db(mgpu_ivf *ivf, const ScanArgs &a);  // MGPU_ERR_UNSUPPORTED => use launch_scan's generic kernels
 size_t scan_max_probes_supported(mgpu_ivf *ivf);
 
@@ -135,7 +145,9 @@ bool coarse_tc_applicable(mgpu_ctx *ctx, uint32_t dim, uint32_t C, uint32_t npro
 int launch_split_bf16(mgpu_ctx *ctx, const float *dX, uint64_t n, uint32_t dim, int is_centroid, void *d_out, float *d_norms);
 int launch_coarse_tc(mgpu_ctx *ctx, const float *dQ, uint32_t B, const float *d_centroids, const void *d_csplit, const float *d_cn,
                      float cn_max, uint32_t C, uint32_t dim, uint32_t nprobe, void *d_qsplit, float *d_qn, float *d_Dt,
-                     uint32_t *d_overflow, uint32_t *d_flags, int need_order, uint32_t *out_ids, float *out_dist);
+                     uint32_t *d_overflow, uint32_t *d_flags, int need_order, uint32_t *out_ids, float *out_dist,
+                     const uint32_t *chunk_start = nullptr, uint32_t *d_work = nullptr, bool *work_done = nullptr,
+                     cudaEvent_t after_gemm = nullptr);
 
 struct HnswSearchArgs {
   const float *Q; uint32_t B, k, ef;

@@ -381,10 +381,11 @@ __global__ void __launch_bounds__(1024) k_plan_bucket(const uint32_t *__restrict
 }
 
 int launch_plan_queries(mgpu_ivf *ivf, const uint32_t *d_probes, uint32_t max_probes, const uint32_t *d_counts, uint32_t B,
-                        uint32_t *d_order, uint32_t *d_work) {
+                        uint32_t *d_order, uint32_t *d_work, bool have_work) {
   mgpu_ctx *ctx = ivf->ctx;
   LaunchScope ls(ctx, MGPU_K_OTHER);
-  k_query_work<<<(B + 7) / 8, 256, 0, ctx->stream>>>(d_probes, max_probes, d_counts, ivf->d_chunk_start, B, d_work);
+  // the coarse selection already emitted work[q] when it chose the probes itself
+  if (!have_work) k_query_work<<<(B + 7) / 8, 256, 0, ctx->stream>>>(d_probes, max_probes, d_counts, ivf->d_chunk_start, B, d_work);
   k_plan_bucket<<<1, 1024, 0, ctx->stream>>>(d_work, B, d_order);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches++;

@@ -178,6 +178,21 @@ def test_ivf_pq_exact_ties_and_duplicates(M):
     _check_ivf(M, X, nlist=8, nprobe=3, k=16, max_clusters=2, seed=79)
 
 
+def test_ivf_pq_heavy_queries_take_the_prefix_search_launch(M):
+    """The table-driven PQ scan keeps one shared-memory word per 32-row chunk of a query (2048 of them); a query whose
+    probed lists are longer is deferred to the second, prefix-search launch.  Mixed batch: light and heavy queries, plus
+    invalidations (applied only to rows that pass the running threshold on the table path)."""
+    rng = np.random.default_rng(5)
+    dim = 256
+    big = (rng.standard_normal((70000, dim)) * 0.05 + 3.0).astype(np.float32)      # one huge, tight cluster
+    small = synth.clustered(3000, dim, n_blobs=6, seed=9)
+    X = np.vstack([big, small]).astype(np.float32)
+    inv = np.arange(5, 73000, 97, dtype=np.uint32)
+    Q = np.vstack([big[:12] + 0.001, small[:12] + 0.01]).astype(np.float32)
+    givf, _, _ = _check_ivf(M, X, nlist=8, nprobe=3, k=10, pq_params=(8, 8), invalidate=inv, seed=31, queries=Q)
+    assert max(givf.ctx.lib.mgpu_ivf_last_scan_rows(givf.handle), 0) > 0
+
+
 def test_ivf_invalidation_and_short_results(M):
     """index.rs:198-200: invalidated ids are skipped; fewer than k results are possible."""
     X = synth.clustered(600, 64, n_blobs=4, seed=5)
