@@ -141,6 +141,15 @@ int mgpu_ivf_scan_remap(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint32_
 /* BlockBasedIvf::search (index.rs:396-412): coarse + scan + remap. */
 int mgpu_ivf_search(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, mgpu_u128 *out_doc_ids,
                     float *out_scores, uint32_t *out_counts, int mem);
+/* Pipelined form of mgpu_ivf_search for HOST buffers (Q and the outputs should be page-locked): the call enqueues the H2D
+ * copy of Q, the search and the D2H copies of the results and returns at once with a ticket; the outputs are valid after
+ * mgpu_search_wait(ctx, ticket).  Two submissions may be in flight per context: batch i+1's upload and batch i-1's
+ * download overlap batch i's kernels (the tokio tasks of the reference overlap their awaits the same way,
+ * rs/index_server/src/index_server.rs:171-271).  Submitting a third one first completes the oldest.  Q and the output
+ * buffers must stay untouched until the wait returns.  Results are identical to mgpu_ivf_search. */
+int mgpu_ivf_search_submit(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, mgpu_u128 *out_doc_ids,
+                           float *out_scores, uint32_t *out_counts, uint64_t *ticket);
+int mgpu_search_wait(mgpu_ctx *ctx, uint64_t ticket);
 /* Planner filter hook (index.rs:212-226; Planner::plan_with_ids rs/index/src/query/planner.rs:43-60): the caller evaluates
  * the request's DocumentFilter to a point-id set and passes it as a bitmap (bit p of word p/32 = point id p allowed).  A
  * scanned row is kept only if its bit is set; distances are still computed for every non-invalidated row, as in the

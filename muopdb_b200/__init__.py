@@ -572,6 +572,25 @@ class BlockBasedIvf:
         _lib.check(self.ctx.lib.mgpu_ivf_search(self.handle, q.ptr, B, k, num_probes, ip, sp, cp, q.mem), self.ctx.h)
         return BatchResult(ids, scores, cnt)
 
+    def search_batch_submit(self, Q, k: int, num_probes: int, out) -> int:
+        """Pipelined search_batch over page-locked HOST buffers (mgpu_ivf_search_submit): returns a ticket at once; `out`
+        = (ids, scores, counts) is valid after `search_wait(ticket)`.  Two batches may be in flight, so the next batch's
+        upload and the previous one's download overlap the kernels."""
+        q = _Buf(Q, np.float32, (None, self.dim))
+        if q.mem != HOST:
+            raise ValueError("search_batch_submit takes host buffers (device buffers are asynchronous already)")
+        ip, sp, cp = (x.data_ptr() if _is_torch(x) else x.ctypes.data for x in out)
+        t = C.c_uint64(0)
+        _lib.check(self.ctx.lib.mgpu_ivf_search_submit(self.handle, q.ptr, q.shape[0], k, num_probes, ip, sp, cp, C.byref(t)),
+                   self.ctx.h)
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[t.value] = (Q, out)  # keep the buffers alive until the wait
+        return int(t.value)
+
+    def search_wait(self, ticket: int) -> None:
+        _lib.check(self.ctx.lib.mgpu_search_wait(self.ctx.h, ticket), self.ctx.h)
+        getattr(self, "_inflight", {}).pop(ticket, None)
+
     def last_scan_rows(self) -> int:
         return int(self.ctx.lib.mgpu_ivf_last_scan_rows(self.handle))
 

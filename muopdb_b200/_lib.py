@@ -74,6 +74,8 @@ SIGNATURES = {
     "mgpu_ivf_coarse": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, _u32p, _f32p, C.c_int]),
     "mgpu_ivf_scan": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, _u32p, C.c_uint32, _u32p, C.c_uint32, _u32p, _f32p, _u32p, C.c_int]),
     "mgpu_ivf_scan_remap": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, _u32p, C.c_uint32, _u32p, C.c_uint32, _vp, _f32p, _u32p, C.c_int]),
+    "mgpu_ivf_search_submit": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _f32p, _u32p, C.POINTER(C.c_uint64)]),
+    "mgpu_search_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
     "mgpu_ivf_search": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _f32p, _u32p, C.c_int]),
     "mgpu_ivf_search_filtered": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, C.c_uint64, _vp, _f32p, _u32p,
                                            C.c_int]),

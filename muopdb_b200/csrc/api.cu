@@ -79,6 +79,16 @@ void mgpu_destroy(mgpu_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   mgpu_comm_destroy(ctx);
   mgpu_profile_reset(ctx);
+  for (auto &pp : ctx->pipe) {
+    if (pp.ev_out && pp.pending) cudaEventSynchronize(pp.ev_out);
+    if (pp.q) cudaFree(pp.q);
+    if (pp.out) cudaFree(pp.out);
+    if (pp.ev_h2d) cudaEventDestroy(pp.ev_h2d);
+    if (pp.ev_done) cudaEventDestroy(pp.ev_done);
+    if (pp.ev_out) cudaEventDestroy(pp.ev_out);
+  }
+  if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   cudaEventDestroy(ctx->t0);
@@ -528,13 +538,39 @@ static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32
   return launch_finalize(ctx, f);
 }
 
+// slot of a pipelined search: lazily created streams/events, staging grown on demand; a slot whose previous ticket was never
+// waited for is drained first (its results are already on their way to the caller's buffers)
+static int pipe_prepare(mgpu_ctx *ctx, mgpu_ctx::Pipe *pp, size_t q_bytes, size_t out_bytes) {
+  if (!ctx->h2d_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+  if (!ctx->d2h_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+  if (!pp->ev_h2d) {
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&pp->ev_h2d, cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&pp->ev_done, cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&pp->ev_out, cudaEventDisableTiming));
+  }
+  if (pp->pending) { CUDA_TRY(ctx, cudaEventSynchronize(pp->ev_out)); pp->pending = false; }
+  if (pp->q_bytes < q_bytes) {
+    if (pp->q) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(pp->q); pp->q = nullptr; pp->q_bytes = 0; }
+    CUDA_TRY(ctx, cudaMalloc(&pp->q, q_bytes));
+    pp->q_bytes = q_bytes;
+  }
+  if (pp->out_bytes < out_bytes) {
+    if (pp->out) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(pp->out); pp->out = nullptr; pp->out_bytes = 0; }
+    CUDA_TRY(ctx, cudaMalloc(&pp->out, out_bytes));
+    pp->out_bytes = out_bytes;
+  }
+  return MGPU_OK;
+}
+
 // shared implementation of scan / scan_remap / search
 static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint32_t *probe_ids, uint32_t max_probes,
                            const uint32_t *probe_counts, uint32_t nprobe_coarse, uint32_t k, uint32_t *out_pids,
                            mgpu_u128 *out_docs, float *out_scores, uint32_t *out_counts, int mem,
-                           const uint32_t *filter_bits = nullptr, uint64_t filter_stride = 0) {
+                           const uint32_t *filter_bits = nullptr, uint64_t filter_stride = 0, uint64_t *ticket = nullptr) {
   mgpu_ctx *ctx = ivf->ctx;
   const bool do_coarse = probe_ids == nullptr;
+  if (ticket) *ticket = 0;
+  if (ticket && (mem != MGPU_HOST || !out_docs || out_pids)) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "search_submit: host buffers and doc-id output only");
   if (do_coarse) {
     if (nprobe_coarse == 0 || nprobe_coarse > ivf->nlist)
       return mgpu_fail(ctx, MGPU_ERR_OUT_OF_RANGE, "num_probes %u out of range 1..%u (the reference panics)", nprobe_coarse, ivf->nlist);
@@ -590,7 +626,19 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
   uint32_t *sF = w.get<uint32_t>(bF / 4);
 
   const void *dQ;
-  MGPU_TRY(stage_in(ctx, Q, bQ, mem, sQ, &dQ));
+  mgpu_ctx::Pipe *pp = nullptr;
+  if (ticket) {
+    // pipelined call: queries go through this slot's own staging buffer on the H2D stream
+    pp = &ctx->pipe[ctx->pipe_seq & 1];
+    MGPU_TRY(pipe_prepare(ctx, pp, bQ, (size_t)B * k * 24 + (size_t)B * 4 + 768));
+    if (pp->used) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->h2d_stream, pp->ev_done, 0));  // the previous user of the buffer has read it
+    CUDA_TRY(ctx, cudaMemcpyAsync(pp->q, Q, bQ, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    CUDA_TRY(ctx, cudaEventRecord(pp->ev_h2d, ctx->h2d_stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, pp->ev_h2d, 0));
+    dQ = pp->q;
+  } else {
+    MGPU_TRY(stage_in(ctx, Q, bQ, mem, sQ, &dQ));
+  }
   const uint32_t *dF = filter_bits;
   if (bF) { const void *t; MGPU_TRY(stage_in(ctx, filter_bits, bF, mem, sF, &t)); dF = (const uint32_t *)t; }
   const uint32_t *dP, *dPC = nullptr;
@@ -619,7 +667,23 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
   mgpu_u128 *oD = out_docs ? (mem == MGPU_DEVICE ? out_docs : sDocs) : nullptr;
   float *oS = mem == MGPU_DEVICE ? out_scores : sScores;
   uint32_t *oC = mem == MGPU_DEVICE ? out_counts : sCounts;
+  if (pp) {
+    WsAlloc wo(pp->out, pp->out_bytes);
+    oD = wo.get<mgpu_u128>((size_t)B * k); oS = wo.get<float>((size_t)B * k); oC = wo.get<uint32_t>(B);
+  }
   MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, dP, max_probes, dPC, k, dQC, dCK, dCS, dOrd, oP, oD, oS, oC, qcodes_on_aux, dF, filter_stride, have_work));
+  if (pp) {
+    // results leave on the D2H stream; the ticket completes when they have landed in the caller's buffers
+    CUDA_TRY(ctx, cudaEventRecord(pp->ev_done, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->d2h_stream, pp->ev_done, 0));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_docs, oD, (size_t)B * k * 16, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_scores, oS, (size_t)B * k * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_counts, oC, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    CUDA_TRY(ctx, cudaEventRecord(pp->ev_out, ctx->d2h_stream));
+    pp->seq = ++ctx->pipe_seq; pp->pending = true; pp->used = true;
+    *ticket = pp->seq;
+    return MGPU_OK;
+  }
   if (mem == MGPU_HOST) {
     MGPU_TRY(stage_out(ctx, out_pids, oP, (size_t)B * k * 4, mem));
     MGPU_TRY(stage_out(ctx, out_docs, oD, (size_t)B * k * 16, mem));
@@ -664,6 +728,39 @@ int mgpu_ivf_search(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint3
                     float *out_scores, uint32_t *out_counts, int mem) {
   if (!ivf) return MGPU_ERR_INVALID_ARG;
   return ivf_search_impl(ivf, Q, B, nullptr, 0, nullptr, nprobe, k, nullptr, out_doc_ids, out_scores, out_counts, mem);
+}
+
+/* Pipelined BlockBasedIvf::search over host buffers: enqueue and return; mgpu_search_wait(ticket) completes it. */
+int mgpu_ivf_search_submit(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, mgpu_u128 *out_doc_ids,
+                           float *out_scores, uint32_t *out_counts, uint64_t *ticket) {
+  if (!ivf || !ticket) return MGPU_ERR_INVALID_ARG;
+  if (B == 0 || k == 0) {  // nothing to put in flight
+    *ticket = 0;
+    return ivf_search_impl(ivf, Q, B, nullptr, 0, nullptr, nprobe, k, nullptr, out_doc_ids, out_scores, out_counts, MGPU_HOST);
+  }
+  return ivf_search_impl(ivf, Q, B, nullptr, 0, nullptr, nprobe, k, nullptr, out_doc_ids, out_scores, out_counts, MGPU_HOST, nullptr, 0,
+                         ticket);
+}
+
+int mgpu_search_wait(mgpu_ctx *ctx, uint64_t ticket) {
+  if (!ctx) return MGPU_ERR_INVALID_ARG;
+  if (ticket == 0) return MGPU_OK;
+  cudaEvent_t ev = nullptr;
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (ticket > ctx->pipe_seq) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "search_wait: unknown ticket %llu", (unsigned long long)ticket);
+    mgpu_ctx::Pipe &pp = ctx->pipe[(ticket - 1) & 1];
+    if (pp.seq != ticket || !pp.pending) return MGPU_OK;  // already drained (waited for, or its slot was reused)
+    ev = pp.ev_out;
+  }
+  cudaSetDevice(ctx->device);
+  CUDA_TRY(ctx, cudaEventSynchronize(ev));  // not under the lock: other threads keep submitting
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    mgpu_ctx::Pipe &pp = ctx->pipe[(ticket - 1) & 1];
+    if (pp.seq == ticket) pp.pending = false;
+  }
+  return MGPU_OK;
 }
 
 /* Planner filter hook (index.rs:212-226): BlockBasedIvf::search with Some(planner). */

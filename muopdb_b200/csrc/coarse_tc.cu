@@ -720,7 +720,7 @@ bool coarse_tc_applicable(mgpu_ctx *ctx, uint32_t dim, uint32_t C, uint32_t npro
   size_t smem = ((dim + 3) & ~3u) * 4 + cap * 12 + SEL_BINS * 4 + 64;
   if (smem > ctx->smem_optin || nprobe > C) return false;
   if (mode == 2) return true;
-  return C >= 1024 && dim >= 64;
+  return C >= 256 && dim >= 64;
 }
 
 int launch_split_bf16(mgpu_ctx *ctx, const float *dX, uint64_t n, uint32_t dim, int is_centroid, void *d_out, float *d_norms) {

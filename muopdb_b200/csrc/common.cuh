@@ -35,6 +35,16 @@ struct mgpu_ctx {
   struct Prof { std::vector<cudaEvent_t> ev; uint64_t launches = 0; float done_ms = 0.f; };
   Prof prof[MGPU_K_COUNT];
   uint64_t launches = 0;
+  // pipelined host-buffer searches (mgpu_ivf_search_submit / mgpu_search_wait): two slots alternate, each with its own
+  // device staging for the queries and the results, so batch i+1's H2D copy and batch i-1's D2H copy overlap batch i's kernels
+  struct Pipe {
+    void *q = nullptr; size_t q_bytes = 0;       // staged queries
+    void *out = nullptr; size_t out_bytes = 0;   // doc ids | scores | counts
+    cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_out = nullptr;
+    uint64_t seq = 0; bool pending = false, used = false;
+  } pipe[2];
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  uint64_t pipe_seq = 0;
   // nccl
   void *nccl_lib = nullptr; void *nccl_comm = nullptr; int nranks = 1, rank = 0;
 };

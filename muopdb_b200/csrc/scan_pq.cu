@@ -22,6 +22,12 @@
 #include <algorithm>
 #include <functional>
 
+#ifdef MGPU_SCAN_DBG
+// experiment build only (make DBG=1): bit0 = no row ever passes, bit1 = skip the merge rounds; g_dbg = pass statistics
+__device__ unsigned long long g_dbg[8];
+__constant__ unsigned int c_dbg;
+#endif
+
 struct DbLayout {
   uint32_t lut_bytes, off_ctab, off_pref, off_pcs, off_plen, off_mkey, off_mpay, off_misc, total, maxp;
 };
@@ -81,6 +87,9 @@ struct DbConsumerCtx {
                                              uint32_t thr) {
     constexpr int NCW_ = NCW;
     uint32_t worst;
+#ifdef MGPU_SCAN_DBG
+    { unsigned mm = __ballot_sync(0xffffffffu, pass); if (lane == 0) { atomicAdd(&g_dbg[0], 1ull); atomicAdd(&g_dbg[1], (unsigned long long)__popc(mm)); if (first) atomicAdd(&g_dbg[2], 1ull);} }
+#endif
     if (first) {
       top.key = pass ? (((uint64_t)key << 32) | pid) : MGPU_EMPTY_KEY;
       top.pay = pass ? slot : MGPU_EMPTY_SLOT;
@@ -216,7 +225,11 @@ struct DbConsumerCtx {
     const uint32_t total = qinfo[P * 4 + 1];
     const uint32_t *prefp = pref + P * (L.maxp + 1), *pcsp = pcs + P * L.maxp;
     if (warp == 0) {
+#ifdef MGPU_SCAN_DBG
+      if (lane == 0) *thr_p = (c_dbg & 1) ? 0u : 0xFFFFFFFFu;
+#else
       if (lane == 0) *thr_p = 0xFFFFFFFFu;
+#endif
       b2[lane] = 0xFFFFFFFFu;
     }
     named_bar_sync(1, NCT);
@@ -235,6 +248,9 @@ struct DbConsumerCtx {
     named_bar_sync(1, NCT);
 #pragma unroll
     for (int half = 16; half >= 1; half >>= 1) {
+#ifdef MGPU_SCAN_DBG
+      if (c_dbg & 2) break;
+#endif
       if (warp < half && warp + half < NCW) {
         top.merge(mkey[(warp + half) * 32 + lane], mpay[(warp + half) * 32 + lane]);
         mkey[warp * 32 + lane] = top.key;
@@ -434,6 +450,15 @@ static int launch_db_t(mgpu_ivf *ivf, const ScanArgs &a0) {
   unsigned grid = a.B < (uint32_t)ctx->sm_count ? a.B : (unsigned)ctx->sm_count;
   CUDA_TRY(ctx, cudaMemsetAsync(a.next_query, 0, 4, ctx->stream));
   CUDA_TRY(ctx, cudaMemsetAsync(a.overflow_count, 0, 4, ctx->stream));
+#ifdef MGPU_SCAN_DBG
+  {
+    static int n = 0;
+    unsigned int d = getenv("MGPU_SCAN_DBG") ? atoi(getenv("MGPU_SCAN_DBG")) : 0;
+    cudaMemcpyToSymbolAsync(c_dbg, &d, 4, 0, cudaMemcpyHostToDevice, ctx->stream);
+    if (++n == 8) { unsigned long long h[8]; cudaStreamSynchronize(ctx->stream); cudaMemcpyFromSymbol(h, g_dbg, 64);
+      fprintf(stderr, "[scan dbg] after 7 launches: offer calls %llu rows offered %llu first %llu\n", h[0], h[1], h[2]); }
+  }
+#endif
   {
     LaunchScope ls(ctx, MGPU_K_SCAN);
     k_scan_pq_db<NG, NCW, NPW, true><<<grid, (NCW + NPW) * 32, L.total, ctx->stream>>>(a, L);

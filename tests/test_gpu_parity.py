@@ -524,7 +524,7 @@ def test_micro_batcher_spann_and_errors(M):
 
 
 # ---- tensor-core coarse scoring --------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("dim,nlist,nprobe", [(64, 1024, 16), (128, 2048, 64), (768, 1280, 32), (80, 1028, 7)])
+@pytest.mark.parametrize("dim,nlist,nprobe", [(64, 1024, 16), (128, 2048, 64), (768, 1280, 32), (80, 1028, 7), (768, 512, 8), (96, 256, 256)])
 def test_coarse_tensor_core_path_matches_exact(M, dim, nlist, nprobe):
     """find_nearest_centroids (index.rs:147-163) through the tcgen05 GEMM + margin + exact re-score: the probe lists and
     distances must be IDENTICAL to the oracle's (the tensor-core pass only proposes candidates).  Includes duplicated
@@ -553,3 +553,36 @@ def test_coarse_tensor_core_path_matches_exact(M, dim, nlist, nprobe):
         n = int(oc[b])
         assert np.array_equal(r.doc_ids[b, :n], od[b, :n]), b
         assert _same_f32(r.scores[b, :n], os_[b, :n])
+
+
+def test_pipelined_submit_wait_matches_blocking_search(M):
+    """mgpu_ivf_search_submit / mgpu_search_wait: batches in flight two at a time through their own staging buffers must
+    return exactly what the blocking call (and the oracle) returns, in any wait order, including reuse of a slot whose
+    ticket was never waited for."""
+    import torch
+    X = synth.clustered(6000, 256, n_blobs=12, seed=3)
+    givf, oivf, _ = _check_ivf(M, X, nlist=24, nprobe=6, k=10, pq_params=(8, 8), seed=4)
+    rng = np.random.default_rng(11)
+    k, nprobe, nb, B = 10, 6, 7, 96
+    Qs = [torch.from_numpy((X[rng.integers(0, len(X), B)] + 0.02 * rng.standard_normal((B, 256))).astype(np.float32)).pin_memory()
+          for _ in range(nb)]
+    outs = [(torch.zeros((B, k, 2), dtype=torch.int64).pin_memory(), torch.zeros((B, k), dtype=torch.float32).pin_memory(),
+             torch.zeros((B,), dtype=torch.int32).pin_memory()) for _ in range(nb)]
+    tickets = []
+    for i in range(nb):
+        tickets.append(givf.search_batch_submit(Qs[i], k, nprobe, outs[i]))
+        if i >= 1 and i != 4:          # batch 3's ticket is only waited for at the end: its slot is reused by batch 5
+            givf.search_wait(tickets[i - 1])
+    for t in reversed(tickets):
+        givf.search_wait(t)
+    givf.search_wait(tickets[0])       # waiting twice is harmless
+    for i in range(nb):
+        od, os_, oc = oivf.search_batch(Qs[i].numpy(), k, nprobe)
+        ids, sc, cn = (x.numpy() for x in outs[i])
+        assert np.array_equal(cn.astype(np.int64), oc.astype(np.int64)), i
+        for b in range(B):
+            n = int(oc[b])
+            assert np.array_equal(ids[b, :n].view(np.uint64), np.asarray(od[b, :n], dtype=np.uint64)), (i, b)
+            assert _same_f32(sc[b, :n], os_[b, :n]), (i, b)
+    with pytest.raises(M.InvalidArgument):
+        givf.search_wait(10 ** 9)
