@@ -292,10 +292,11 @@ def main():
 
     def step_device(i):
         Qb = Qall[(i % nbatches) * B:(i % nbatches + 1) * B]
-        ivf.search_batch(Qb, k, nprobe, out=out_local)
         if world > 1:
-            ctx.shard_allgather_merge(out_local[0], out_local[1], out_local[2], B, k, *out_merged)
+            # one collective call: split query encode + all-gather of codes, local shard search, all-gather + merge
+            ivf.shard_search_batch(Qb, k, nprobe, out=out_merged, shared_codebook=True)
             return out_merged
+        ivf.search_batch(Qb, k, nprobe, out=out_local)
         return out_local
 
     def barrier():
@@ -349,17 +350,8 @@ def main():
         if world == 1:
             ivf.search_batch(Qh[i % nbatches], k, nprobe, out=(h_ids, h_sc, h_cn))
         else:
-            # H2D, local search, exchange + merge, D2H
-            qd = Qall.new_empty((B, args.dim))
-            with torch.cuda.stream(ext):
-                qd.copy_(Qh[i % nbatches], non_blocking=True)
-            ivf.search_batch(qd, k, nprobe, out=out_local)
-            ctx.shard_allgather_merge(out_local[0], out_local[1], out_local[2], B, k, *out_merged)
-            with torch.cuda.stream(ext):
-                h_ids.copy_(out_merged[0], non_blocking=True)
-                h_sc.copy_(out_merged[1], non_blocking=True)
-                h_cn.copy_(out_merged[2], non_blocking=True)
-            ctx.sync()
+            # H2D, split encode, local search, exchange + merge, D2H: all inside the one host-buffer collective call
+            ivf.shard_search_batch(Qh[i % nbatches], k, nprobe, out=(h_ids, h_sc, h_cn), shared_codebook=True)
 
     for i in range(3):
         step_host(i)

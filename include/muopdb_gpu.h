@@ -234,6 +234,14 @@ int mgpu_shard_allgather_merge(mgpu_ctx *ctx, const mgpu_u128 *local_doc_ids, co
                                const uint32_t *local_counts, uint32_t B, uint32_t k, mgpu_u128 *out_doc_ids,
                                float *out_scores, uint32_t *out_counts);
 
+/* The sharded query path in one call: every rank passes the same (replicated) batch, searches its own shard with
+ * BlockBasedIvf::search semantics, the per-shard top-k lists are all-gathered over NVLink and merged; every rank receives
+ * the merged result.  shared_codebook != 0 states that all shards use one PQ codebook: the query encode (index.rs:193) is
+ * then split across the ranks and its B x m code bytes all-gathered instead of being repeated on every rank.
+ * Collective: all ranks must call it with the same B, k.  Buffers in `mem` space. */
+int mgpu_shard_ivf_search(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, int shared_codebook,
+                          mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, int mem);
+
 /* ---- Readers of the reference's on-disk formats -------------- */
 /* One Elias-Fano posting-list payload (rs/compression/src/elias_fano/ef.rs:197-215; decode rule
  * block_based_decoder.rs:162-179,257-266) -> ascending values.  Host-only (no device needed).

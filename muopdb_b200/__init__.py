@@ -572,6 +572,20 @@ class BlockBasedIvf:
         _lib.check(self.ctx.lib.mgpu_ivf_search(self.handle, q.ptr, B, k, num_probes, ip, sp, cp, q.mem), self.ctx.h)
         return BatchResult(ids, scores, cnt)
 
+    def shard_search_batch(self, Q, k: int, num_probes: int, out=None, shared_codebook: bool = True) -> BatchResult:
+        """Sharded BlockBasedIvf::search (mgpu_shard_ivf_search): this rank's shard is searched for the replicated batch
+        Q, the per-shard top-k are all-gathered and merged (snapshot.rs:60-61); collective over the context's ranks."""
+        q = _Buf(Q, np.float32, (None, self.dim))
+        B = q.shape[0]
+        if out is None:
+            ids, scores, cnt, ip, sp, cp = _alloc_out(B, k, Q if q.mem == DEVICE else None)
+        else:
+            ids, scores, cnt = out
+            ip, sp, cp = (x.data_ptr() if _is_torch(x) else x.ctypes.data for x in out)
+        _lib.check(self.ctx.lib.mgpu_shard_ivf_search(self.handle, q.ptr, B, k, num_probes, 1 if shared_codebook else 0, ip, sp, cp,
+                                                      q.mem), self.ctx.h)
+        return BatchResult(ids, scores, cnt)
+
     def search_batch_submit(self, Q, k: int, num_probes: int, out) -> int:
         """Pipelined search_batch over page-locked HOST buffers (mgpu_ivf_search_submit): returns a ticket at once; `out`
         = (ids, scores, counts) is valid after `search_wait(ticket)`.  Two batches may be in flight, so the next batch's

@@ -87,6 +87,7 @@ void mgpu_destroy(mgpu_ctx *ctx) {
     if (pp.ev_done) cudaEventDestroy(pp.ev_done);
     if (pp.ev_out) cudaEventDestroy(pp.ev_out);
   }
+  if (ctx->shard_ws) cudaFree(ctx->shard_ws);
   if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
   if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   if (ctx->ws) cudaFree(ctx->ws);
@@ -499,7 +500,7 @@ static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32
                         const uint32_t *d_counts, uint32_t k, uint8_t *d_qcodes, uint64_t *d_ckey, uint32_t *d_cslot,
                         uint32_t *d_order, uint32_t *d_out_pids, mgpu_u128 *d_out_docs, float *d_out_scores, uint32_t *d_out_counts,
                         bool qcodes_on_aux = false, const uint32_t *d_filter = nullptr, uint64_t filter_stride = 0,
-                        bool have_work = false) {
+                        bool have_work = false, bool have_codes = false) {
   mgpu_ctx *ctx = ivf->ctx;
   CUDA_TRY(ctx, cudaMemsetAsync(ivf->d_scan_rows, 0, 8, ctx->stream));
   ScanArgs a;
@@ -515,7 +516,8 @@ static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32
     mgpu_pq *pq = ivf->pq;
     a.m = pq->m; a.K = pq->K; a.table = pq->d_table; a.rowmin = pq->d_rowmin; a.rowmax = pq->d_rowmax;
     // the query is quantized with the same codebook (index.rs:193) -- once per query here, not once per list
-    if (qcodes_on_aux) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // encoded on the side stream
+    if (have_codes) {}  // the caller already holds the query codes (sharded search: encoded once across the ranks)
+    else if (qcodes_on_aux) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // encoded on the side stream
     else MGPU_TRY(launch_pq_quantize(pq, dQ, B, d_qcodes));
     a.qcodes = d_qcodes;
   }
@@ -566,7 +568,8 @@ static int pipe_prepare(mgpu_ctx *ctx, mgpu_ctx::Pipe *pp, size_t q_bytes, size_
 static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint32_t *probe_ids, uint32_t max_probes,
                            const uint32_t *probe_counts, uint32_t nprobe_coarse, uint32_t k, uint32_t *out_pids,
                            mgpu_u128 *out_docs, float *out_scores, uint32_t *out_counts, int mem,
-                           const uint32_t *filter_bits = nullptr, uint64_t filter_stride = 0, uint64_t *ticket = nullptr) {
+                           const uint32_t *filter_bits = nullptr, uint64_t filter_stride = 0, uint64_t *ticket = nullptr,
+                           const uint8_t *d_qcodes_ext = nullptr, bool caller_holds_lock = false) {
   mgpu_ctx *ctx = ivf->ctx;
   const bool do_coarse = probe_ids == nullptr;
   if (ticket) *ticket = 0;
@@ -578,7 +581,8 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
   }
   if (k > MGPU_NCAND) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported yet", k, MGPU_NCAND);
   if (B && (!Q || !out_scores || !out_counts || (!out_pids && !out_docs))) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "search: null buffer");
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::unique_lock<std::mutex> g(ctx->mu, std::defer_lock);
+  if (!caller_holds_lock) g.lock();
   cudaSetDevice(ctx->device);
   if (B == 0) return MGPU_OK;
   if (k == 0) {  // heap of capacity 0 keeps nothing (index.rs:265-274)
@@ -647,7 +651,7 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
     // the query encode (index.rs:193) does not depend on the probes: it runs on the side stream next to the (latency
     // bound) selection kernel, forked right after the coarse GEMM -- the GEMM itself wants every SM's shared memory
     static const bool use_aux = !(getenv("MGPU_AUX_STREAM") && getenv("MGPU_AUX_STREAM")[0] == '0');
-    const bool fork = use_aux && ivf->quant == MGPU_QUANT_PQ;
+    const bool fork = use_aux && ivf->quant == MGPU_QUANT_PQ && !d_qcodes_ext;
     MGPU_TRY(ivf_coarse_dev(ivf, (const float *)dQ, B, nprobe_coarse, dD, sP, nullptr, xws, 0, fork ? ctx->ev_fork : nullptr,
                             dOrd + B, &have_work));
     if (fork) {
@@ -671,7 +675,8 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
     WsAlloc wo(pp->out, pp->out_bytes);
     oD = wo.get<mgpu_u128>((size_t)B * k); oS = wo.get<float>((size_t)B * k); oC = wo.get<uint32_t>(B);
   }
-  MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, dP, max_probes, dPC, k, dQC, dCK, dCS, dOrd, oP, oD, oS, oC, qcodes_on_aux, dF, filter_stride, have_work));
+  MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, dP, max_probes, dPC, k, d_qcodes_ext ? (uint8_t *)d_qcodes_ext : dQC, dCK, dCS, dOrd, oP, oD,
+                        oS, oC, qcodes_on_aux, dF, filter_stride, have_work, d_qcodes_ext != nullptr));
   if (pp) {
     // results leave on the D2H stream; the ticket completes when they have landed in the caller's buffers
     CUDA_TRY(ctx, cudaEventRecord(pp->ev_done, ctx->stream));
@@ -922,14 +927,15 @@ int mgpu_comm_destroy(mgpu_ctx *ctx) {
   return MGPU_OK;
 }
 
-int mgpu_shard_allgather_merge(mgpu_ctx *ctx, const mgpu_u128 *local_doc_ids, const float *local_scores,
-                               const uint32_t *local_counts, uint32_t B, uint32_t k, mgpu_u128 *out_doc_ids,
-                               float *out_scores, uint32_t *out_counts) {
+static int shard_allgather_merge_impl(mgpu_ctx *ctx, const mgpu_u128 *local_doc_ids, const float *local_scores,
+                                      const uint32_t *local_counts, uint32_t B, uint32_t k, mgpu_u128 *out_doc_ids,
+                                      float *out_scores, uint32_t *out_counts, bool caller_holds_lock) {
   if (!ctx) return MGPU_ERR_INVALID_ARG;
   if (!ctx->nccl_comm) return mgpu_fail(ctx, MGPU_ERR_NCCL, "shard_allgather_merge: communicator not initialised");
   auto ag = (fn_ncclAllGather)nccl_sym("ncclAllGather");
   if (!ag) return mgpu_fail(ctx, MGPU_ERR_NCCL, "ncclAllGather not found");
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::unique_lock<std::mutex> g(ctx->mu, std::defer_lock);
+  if (!caller_holds_lock) g.lock();
   cudaSetDevice(ctx->device);
   if (B == 0 || k == 0) return MGPU_OK;
   const uint32_t S = (uint32_t)ctx->nranks;
@@ -946,6 +952,86 @@ int mgpu_shard_allgather_merge(mgpu_ctx *ctx, const mgpu_u128 *local_doc_ids, co
   if (r != 0) return mgpu_fail(ctx, MGPU_ERR_NCCL, "ncclAllGather failed (%d)", r);
   ctx->launches += 3;
   return launch_merge_topk(ctx, gD, gS, gC, S, B, k, out_doc_ids, out_scores, out_counts);
+}
+
+int mgpu_shard_allgather_merge(mgpu_ctx *ctx, const mgpu_u128 *local_doc_ids, const float *local_scores,
+                               const uint32_t *local_counts, uint32_t B, uint32_t k, mgpu_u128 *out_doc_ids,
+                               float *out_scores, uint32_t *out_counts) {
+  return shard_allgather_merge_impl(ctx, local_doc_ids, local_scores, local_counts, B, k, out_doc_ids, out_scores, out_counts, false);
+}
+
+// The whole sharded query path in one call: every rank passes the SAME replicated batch and searches its own
+// doc-shard; the per-shard top-k lists are all-gathered and merged with the leaf ordering (snapshot.rs:60-61,105-106), so
+// every rank returns the merged result.  With a codebook shared by all shards (shared_codebook != 0) the query encode
+// (index.rs:193) -- per-query work that does not shrink with the shard -- is split across the ranks: rank r encodes
+// queries [r*ceil(B/N), (r+1)*ceil(B/N)) and one all-gather of B x m code bytes replaces N-1 redundant encodes per query.
+int mgpu_shard_ivf_search(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, int shared_codebook,
+                          mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, int mem) {
+  if (!ivf) return MGPU_ERR_INVALID_ARG;
+  mgpu_ctx *ctx = ivf->ctx;
+  if (!ctx->nccl_comm) return mgpu_fail(ctx, MGPU_ERR_NCCL, "shard_ivf_search: communicator not initialised (mgpu_comm_init_rank)");
+  if (B && (!Q || !out_doc_ids || !out_scores || !out_counts)) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "shard_ivf_search: null buffer");
+  if (nprobe == 0 || nprobe > ivf->nlist) return mgpu_fail(ctx, MGPU_ERR_OUT_OF_RANGE, "num_probes %u out of range 1..%u (the reference panics)", nprobe, ivf->nlist);
+  if (k > MGPU_NCAND) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported yet", k, MGPU_NCAND);
+  auto ag = (fn_ncclAllGather)nccl_sym("ncclAllGather");
+  if (!ag) return mgpu_fail(ctx, MGPU_ERR_NCCL, "ncclAllGather not found");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (B == 0) return MGPU_OK;
+  if (k == 0) {
+    if (mem == MGPU_HOST) memset(out_counts, 0, (size_t)B * 4);
+    else CUDA_TRY(ctx, cudaMemsetAsync(out_counts, 0, (size_t)B * 4, ctx->stream));
+    return MGPU_OK;
+  }
+  const uint32_t N = (uint32_t)ctx->nranks, r = (uint32_t)ctx->rank;
+  const bool split_encode = shared_codebook && ivf->quant == MGPU_QUANT_PQ && N > 1;
+  const uint32_t m = ivf->pq ? ivf->pq->m : 0;
+  const uint32_t slice = (B + N - 1) / N;
+  size_t need = 0;
+  need = ws_need(need, mem == MGPU_HOST ? (size_t)B * ivf->dim * 4 : 0);
+  need = ws_need(need, split_encode ? (size_t)N * slice * m : 0);
+  need = ws_need(need, split_encode ? (size_t)slice * m : 0);
+  need = ws_need(need, (size_t)B * k * 16); need = ws_need(need, (size_t)B * k * 4); need = ws_need(need, (size_t)B * 4);
+  need = ws_need(need, mem == MGPU_HOST ? (size_t)B * k * 16 : 0);
+  need = ws_need(need, mem == MGPU_HOST ? (size_t)B * k * 4 : 0);
+  need = ws_need(need, mem == MGPU_HOST ? (size_t)B * 4 : 0);
+  if (ctx->shard_ws_bytes < need) {
+    if (ctx->shard_ws) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->shard_ws); ctx->shard_ws = nullptr; ctx->shard_ws_bytes = 0; }
+    CUDA_TRY(ctx, cudaMalloc(&ctx->shard_ws, need + need / 4));
+    ctx->shard_ws_bytes = need + need / 4;
+  }
+  WsAlloc w(ctx->shard_ws, ctx->shard_ws_bytes);
+  float *sQ = w.get<float>(mem == MGPU_HOST ? (size_t)B * ivf->dim : 0);
+  uint8_t *codes_all = w.get<uint8_t>(split_encode ? (size_t)N * slice * m : 0);
+  uint8_t *codes_mine = w.get<uint8_t>(split_encode ? (size_t)slice * m : 0);
+  mgpu_u128 *locD = w.get<mgpu_u128>((size_t)B * k); float *locS = w.get<float>((size_t)B * k); uint32_t *locC = w.get<uint32_t>(B);
+  mgpu_u128 *outD = w.get<mgpu_u128>(mem == MGPU_HOST ? (size_t)B * k : 0);
+  float *outS = w.get<float>(mem == MGPU_HOST ? (size_t)B * k : 0);
+  uint32_t *outC = w.get<uint32_t>(mem == MGPU_HOST ? B : 0);
+  const void *dQv;
+  MGPU_TRY(stage_in(ctx, Q, (size_t)B * ivf->dim * 4, mem, sQ, &dQv));
+  const float *dQ = (const float *)dQv;
+  const uint8_t *ext = nullptr;
+  if (split_encode) {
+    const uint32_t lo = std::min(B, r * slice), cnt = std::min(B, lo + slice) - lo;
+    if (cnt) MGPU_TRY(launch_pq_quantize(ivf->pq, dQ + (size_t)lo * ivf->dim, cnt, codes_mine));
+    int rc = ag(codes_mine, codes_all, (size_t)slice * m, 0, ctx->nccl_comm, ctx->stream);
+    if (rc != 0) return mgpu_fail(ctx, MGPU_ERR_NCCL, "ncclAllGather (query codes) failed (%d)", rc);
+    ctx->launches += 1;
+    ext = codes_all;  // rank j's slice starts at j*slice*m = (first query of the slice)*m: query q sits at q*m
+  }
+  MGPU_TRY(ivf_search_impl(ivf, dQ, B, nullptr, 0, nullptr, nprobe, k, nullptr, locD, locS, locC, MGPU_DEVICE, nullptr, 0, nullptr, ext, true));
+  mgpu_u128 *oD = mem == MGPU_DEVICE ? out_doc_ids : outD;
+  float *oS = mem == MGPU_DEVICE ? out_scores : outS;
+  uint32_t *oC = mem == MGPU_DEVICE ? out_counts : outC;
+  MGPU_TRY(shard_allgather_merge_impl(ctx, locD, locS, locC, B, k, oD, oS, oC, true));
+  if (mem == MGPU_HOST) {
+    MGPU_TRY(stage_out(ctx, out_doc_ids, oD, (size_t)B * k * 16, mem));
+    MGPU_TRY(stage_out(ctx, out_scores, oS, (size_t)B * k * 4, mem));
+    MGPU_TRY(stage_out(ctx, out_counts, oC, (size_t)B * 4, mem));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return MGPU_OK;
 }
 
 }  // extern "C"

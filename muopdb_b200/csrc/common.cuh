@@ -45,6 +45,7 @@ struct mgpu_ctx {
   } pipe[2];
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   uint64_t pipe_seq = 0;
+  void *shard_ws = nullptr; size_t shard_ws_bytes = 0;  // buffers of mgpu_shard_ivf_search (outlive the nested calls' workspace)
   // nccl
   void *nccl_lib = nullptr; void *nccl_comm = nullptr; int nranks = 1, rank = 0;
 };

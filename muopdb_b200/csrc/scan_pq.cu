@@ -384,6 +384,9 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) k_scan_pq_db(ScanArgs a, 
       // ---- LUT image, no staging: lane <-> LUT column (subspace), each lane streams its own 1 KB table row with 16-byte
       // loads and stores four codes' entries; every store is one conflict-free 128-byte wavefront (32 lanes = 32
       // consecutive columns of one code row).  The producer warps split the 256 codes.
+#ifdef MGPU_SCAN_DBG
+      if (!(c_dbg & 4))
+#endif
       {
         constexpr int CODES_PER_WARP = 256 / NPW;
 #pragma unroll 1

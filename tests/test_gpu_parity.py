@@ -586,3 +586,30 @@ def test_pipelined_submit_wait_matches_blocking_search(M):
             assert _same_f32(sc[b, :n], os_[b, :n]), (i, b)
     with pytest.raises(M.InvalidArgument):
         givf.search_wait(10 ** 9)
+
+
+def test_shard_search_single_rank_world(M):
+    """mgpu_shard_ivf_search on a 1-rank NCCL world (all-gather + merge of one shard) must equal the plain search and the
+    oracle, for device and host buffers.  Multi-rank equivalence is checked by tools/check_shard_search.py under torchrun."""
+    import torch
+    X = synth.clustered(5000, 256, n_blobs=10, seed=21)
+    ctx = M.Context(0)
+    ctx.comm_init(1, 0, M.Context.comm_unique_id())
+    rng = np.random.default_rng(2)
+    cents = O.kmeans(X, 20, iters=4, seed=1)
+    offsets, ids = O.build_posting_lists(X, cents)
+    cb = O.train_pq_codebook(X[:2000], 8, 8, iters=3, seed=2)
+    opq, gpq = O.ProductQuantizer(256, 8, 8, cb), M.ProductQuantizer(256, 8, 8, cb, ctx=ctx)
+    codes = opq.quantize(X)
+    oivf = O.Ivf(cents, offsets, ids, codes, pq=opq)
+    givf = M.BlockBasedIvf(cents, offsets, ids, codes, gpq, ctx=ctx)
+    Q = (X[rng.integers(0, len(X), 130)] + 0.02 * rng.standard_normal((130, 256))).astype(np.float32)
+    od, os_, oc = oivf.search_batch(Q, 10, 5)
+    for dev in (False, True):
+        r = givf.shard_search_batch(torch.from_numpy(Q).cuda() if dev else Q, 10, 5)
+        ids_, sc, cn = ((x.cpu().numpy() if dev else np.asarray(x)) for x in (r.doc_ids, r.scores, r.counts))
+        assert np.array_equal(cn.astype(np.int64), oc.astype(np.int64))
+        for b in range(len(Q)):
+            n = int(oc[b])
+            assert np.array_equal(ids_[b, :n].view(np.uint64), np.asarray(od[b, :n], dtype=np.uint64)), (dev, b)
+            assert _same_f32(sc[b, :n], os_[b, :n]), (dev, b)

@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Multi-rank check of the sharded query path (run under torchrun, one rank per GPU):
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/check_shard_search.py
+Every rank builds its doc-shard (doc_id mod N) of one seeded collection with a shared PQ codebook and compares
+  (a) mgpu_shard_ivf_search (split query encode + code all-gather + local search + result all-gather + merge), host and
+      device buffers, with
+  (b) the CPU oracle: per-shard oracle searches merged with the leaf ordering of snapshot.rs:60-61.
+Bit-exact doc ids and scores are required on every rank."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import muopdb_b200 as M  # noqa: E402
+import oracle as O  # noqa: E402
+import synth  # noqa: E402
+from muopdb_b200 import sharding  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")
+    ctx = M.Context(local)
+    sharding.init_comm(ctx)
+    dim, n, k, nprobe, B = 256, 12000, 10, 4, 203   # B not a multiple of the world size: the last encode slice is ragged
+    X = synth.clustered(n, dim, n_blobs=14, seed=5)
+    docs = np.arange(n, dtype=np.uint64) * 3 + 7
+    cb = O.train_pq_codebook(X[:3000], 8, 8, iters=3, seed=2)
+    rng = np.random.default_rng(9)
+    Q = (X[rng.integers(0, n, B)] + 0.02 * rng.standard_normal((B, dim))).astype(np.float32)
+    shards = []
+    for r in range(world):
+        sel = sharding.shard_of(docs, world) == r
+        Xs, ds = X[sel], docs[sel]
+        cents = O.kmeans(Xs, 16, iters=4, seed=1 + r)
+        offsets, ids = O.build_posting_lists(Xs, cents)
+        opq = O.ProductQuantizer(dim, 8, 8, cb)
+        codes = opq.quantize(Xs)
+        pairs = np.zeros((len(ds), 2), dtype=np.uint64)
+        pairs[:, 0] = ds
+        shards.append((cents, offsets, ids, codes, pairs, opq))
+    # oracle: every shard, then merge
+    per = [O.Ivf(c, o, i, cd, doc_ids=p, pq=q).search_batch(Q, k, nprobe) for (c, o, i, cd, p, q) in shards]
+    merged = []
+    for b in range(B):
+        d = np.concatenate([np.asarray(pr[0][b, :int(pr[2][b])]).reshape(-1, 2) for pr in per])
+        sc = np.concatenate([np.asarray(pr[1][b, :int(pr[2][b])], dtype=np.float32) for pr in per])
+        merged.append(O.merge_topk(d, sc, k))   # (list of u128 ints, f32 scores) ordered by (score, doc_id)
+    c, o, i, cd, p, _ = shards[rank]
+    givf = M.BlockBasedIvf(c, o, i, cd, M.ProductQuantizer(dim, 8, 8, cb, ctx=ctx), doc_ids=p, ctx=ctx)
+    ok = True
+
+    def same(r, dev, tag=""):
+        ids_, sc, cn = ((x.cpu().numpy() if dev else np.asarray(x)) for x in (r.doc_ids, r.scores, r.counts))
+        bad = 0
+        for b in range(B):
+            md, ms = merged[b]
+            nn = len(ms)
+            got = [int(lo) | (int(hi) << 64) for lo, hi in ids_[b, :nn].view(np.uint64).reshape(-1, 2)]
+            g = int(cn[b]) == nn and got == [int(x) for x in md] and \
+                np.array_equal(sc[b, :nn].view(np.uint32), np.asarray(ms, dtype=np.float32).view(np.uint32))
+            if not g:
+                if bad == 0:
+                    print(f"[rank {rank}] {tag} dev={dev} query {b}: count {int(cn[b])} vs {nn}\n  got {got[:6]} {sc[b, :6]}\n  ref {[int(x) for x in md][:6]} {ms[:6]}", flush=True)
+                bad += 1
+        if bad:
+            print(f"[rank {rank}] {tag} dev={dev}: {bad}/{B} queries differ", flush=True)
+        return bad == 0
+
+    for dev in (False, True):
+        ok &= same(givf.shard_search_batch(torch.from_numpy(Q).cuda() if dev else Q, k, nprobe, shared_codebook=True), dev, 'split')
+    # and without the split encode (every rank encodes every query): same answer
+    ok &= same(givf.shard_search_batch(Q, k, nprobe, shared_codebook=False), False, 'nosplit')
+    t = torch.tensor([1 if ok else 0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("shard search check:", "OK" if int(t.item()) == 1 else "MISMATCH", f"(world {world}, B {B})")
+    dist.destroy_process_group()
+    sys.exit(0 if int(t.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
