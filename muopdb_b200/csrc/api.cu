@@ -534,6 +534,8 @@ static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32
   if (ivf->quant == MGPU_QUANT_PQ) {
     f.cb = ivf->pq->d_cb; f.codes = ivf->d_codes; f.qcodes = d_qcodes; f.m = ivf->pq->m; f.K = ivf->pq->K;
     f.dsub = ivf->pq->dsub; f.ng = ivf->ng; f.pq_fast = ivf->pq_fast;
+    static const bool no_prune = getenv("MGPU_FINALIZE_PRUNE") && getenv("MGPU_FINALIZE_PRUNE")[0] == '0';
+    f.prune = ivf->metric == MGPU_L2 && !no_prune;
   }
   f.doc_ids = ivf->d_doc_ids;
   f.out_pids = d_out_pids; f.out_docs = d_out_docs; f.out_scores = d_out_scores; f.out_counts = d_out_counts;

@@ -26,6 +26,25 @@ __device__ __forceinline__ bool doc_less(uint32_t ka, mgpu_u128 a, uint32_t kb, 
   return a.lo < b.lo;
 }
 
+// Which of a query's 32 candidates can still reach the exact top k (FinalizeArgs::prune)?  Called by one full warp; lane =
+// candidate.  Returns this lane's verdict.
+__device__ __forceinline__ bool prune_keep(uint32_t k, bool valid, uint32_t key, int lane) {
+  const uint32_t nvalid = __popc(__ballot_sync(0xffffffffu, valid));
+  if (nvalid <= k) return valid;
+  // k-th smallest key among the valid candidates, by counting (keys may repeat)
+  uint32_t rank = 0;
+#pragma unroll 8
+  for (int j = 0; j < 32; j++) {
+    const uint32_t kj = __shfl_sync(0xffffffffu, key, j);
+    const bool vj = __shfl_sync(0xffffffffu, (int)valid, j);
+    rank += (vj && (kj < key || (kj == key && j < lane))) ? 1u : 0u;
+  }
+  const unsigned who = __ballot_sync(0xffffffffu, valid && rank == k - 1);
+  const uint32_t kth = __shfl_sync(0xffffffffu, key, __ffs(who) - 1);
+  const uint64_t bound = (uint64_t)kth + (kth >> 12) + 8192u;
+  return valid && (uint64_t)key <= bound;
+}
+
 // Ordering + remap tail shared by both finalize kernels; called by one full warp per query.  `skey` is the exact score
 // key of this lane's candidate, `valid` whether the lane holds one.
 __device__ __forceinline__ void finalize_tail(const FinalizeArgs &a, uint32_t q, int lane, bool valid, uint32_t skey,
@@ -72,9 +91,10 @@ __global__ void __launch_bounds__(128) k_finalize(FinalizeArgs a) {
   if (q >= a.B) return;
   uint64_t ckey = a.cand_key[(size_t)q * MGPU_NCAND + lane];
   uint32_t slot = a.cand_slot[(size_t)q * MGPU_NCAND + lane];
-  const bool valid = slot != MGPU_EMPTY_SLOT;
+  bool valid = slot != MGPU_EMPTY_SLOT;
   const uint32_t pid = (uint32_t)ckey;
   uint32_t skey = (uint32_t)(ckey >> 32);
+  if (a.cb != nullptr && a.prune) valid = prune_keep(a.k, valid, skey, lane);
   if (a.cb != nullptr && valid) {
     // exact Quantizer::distance(quantized_query, row, StreamingSIMD) (index.rs:203-207, pq/mod.rs:231-266)
     float d;
@@ -110,7 +130,12 @@ __global__ void __launch_bounds__(FIN8_THREADS) k_finalize_pq8(FinalizeArgs a) {
   float4 *ring = (float4 *)(sslot + MGPU_NCAND);   // FIN8_MLP x 64 gathered centroid halves (16-byte aligned: all sizes above are)
   const uint32_t q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
-  if (tid < MGPU_NCAND) sslot[tid] = a.cand_slot[(size_t)q * MGPU_NCAND + tid];
+  if (tid < MGPU_NCAND) {
+    uint32_t slot = a.cand_slot[(size_t)q * MGPU_NCAND + tid];
+    if (a.prune && !prune_keep(a.k, slot != MGPU_EMPTY_SLOT, (uint32_t)(a.cand_key[(size_t)q * MGPU_NCAND + tid] >> 32), lane))
+      slot = MGPU_EMPTY_SLOT;  // cannot reach the exact top k: treated like an empty candidate from here on
+    sslot[tid] = slot;
+  }
   const uint8_t *qc = a.qcodes + (size_t)q * m;
   for (uint32_t i = tid; i < m * 2; i += FIN8_THREADS) {
     const uint32_t s = i >> 1, h = i & 1;
@@ -148,7 +173,9 @@ __global__ void __launch_bounds__(FIN8_THREADS) k_finalize_pq8(FinalizeArgs a) {
     // (2-3 in flight), which makes this loop a chain of L2 round trips.  cp.async has no register destination: FIN8_MLP
     // 16-byte gathers are issued back to back into a thread-private (bank-interleaved) ring, waited for once, then consumed
     // in subspace order.
-    for (uint32_t s0 = 0; s0 < m; s0 += FIN8_MLP) {
+    // empty and pruned candidates issue no gathers (their key is never read)
+    const bool live = sslot[c] != MGPU_EMPTY_SLOT;
+    for (uint32_t s0 = 0; live && s0 < m; s0 += FIN8_MLP) {
       const uint32_t nb = min((uint32_t)FIN8_MLP, m - s0);
       for (uint32_t j = 0; j < nb; j++)
         cp_async16(&ring[j * (2 * MGPU_NCAND) + tid], cb4 + ((size_t)(s0 + j) * a.K + code[s0 + j]) * 2);

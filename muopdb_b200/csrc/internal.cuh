@@ -125,6 +125,11 @@ struct FinalizeArgs {
   // exact PQ re-rank inputs (null for flat: keys are already exact)
   const float *cb; const uint8_t *codes; const uint8_t *qcodes; uint32_t m, K, dsub, ng; bool pq_fast; int metric;
   const mgpu_u128 *doc_ids;
+  // L2 product quantizer only: the fixed-point ranking key of a row is its exact score times the query's scale to within
+  // ~1e-5 relative (every LUT row's minimum is table[s][a][a] = 0, so no offset is involved), hence a candidate whose key
+  // exceeds the k-th smallest key by more than 2^-12 relative + 8192 units cannot be among the exact top k and is not
+  // re-scored
+  bool prune;
   // outputs (either may be null)
   uint32_t *out_pids; mgpu_u128 *out_docs; float *out_scores; uint32_t *out_counts;
 };

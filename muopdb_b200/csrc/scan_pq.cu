@@ -387,6 +387,9 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) k_scan_pq_db(ScanArgs a, 
 #ifdef MGPU_SCAN_DBG
       if (!(c_dbg & 4))
 #endif
+#ifdef MGPU_SCAN_DBG
+      if (!(c_dbg & 4))
+#endif
       {
         constexpr int CODES_PER_WARP = 256 / NPW;
 #pragma unroll 1
