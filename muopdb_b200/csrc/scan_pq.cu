@@ -117,22 +117,27 @@ struct DbConsumerCtx {
     const uint32_t *ct = ctab + P * DB_CTAB_CAP;
     bool first = true;
     uint4 u[NG * 2];
-    uint32_t it = warp, e_n = 0;
+    uint32_t it = warp, e_n = 0, pid_n = MGPU_EMPTY_SLOT;
     if (it < total) {
       e_n = ct[it];
       const uint4 *base = (const uint4 *)a.codes + (size_t)(e_n >> 5) * (NG * 2 * 32) + lane;
 #pragma unroll
       for (int i = 0; i < NG * 2; i++) u[i] = ldg_stream16(base + i * 32);
+      pid_n = a.slot_pid[(e_n >> 5) * 32 + lane];
     }
 #pragma unroll 1
     while (it < total) {
       const uint32_t e = e_n;
+      // the point ids travel with the codes (one coalesced 128-byte load per chunk): a row that passes the threshold does
+      // not wait a memory round trip for its id (with a few chunks per warp and query those waits add up)
+      uint32_t pid = pid_n;
       it += NCW;
       const bool more = it < total;
       const uint4 *nbase = (const uint4 *)a.codes;
       if (more) {
         e_n = ct[it];
         nbase = (const uint4 *)a.codes + (size_t)(e_n >> 5) * (NG * 2 * 32) + lane;
+        pid_n = a.slot_pid[(e_n >> 5) * 32 + lane];
       }
       uint32_t key = 0;
 #pragma unroll
@@ -147,9 +152,7 @@ struct DbConsumerCtx {
       bool pass = (uint32_t)lane <= (e & 31u) && key <= thr;
       if (__any_sync(0xffffffffu, pass)) {
         const uint32_t slot = (e >> 5) * 32 + lane;
-        uint32_t pid = MGPU_EMPTY_SLOT;
         if (pass) {
-          pid = a.slot_pid[slot];
           if (a.invalid && ((a.invalid[pid >> 5] >> (pid & 31)) & 1u)) pass = false;            // index.rs:198-200
           if (a.filter && pass && !((a.filter[(size_t)q * a.filter_stride + (pid >> 5)] >> (pid & 31)) & 1u)) pass = false;  // :212-226
         }
@@ -390,6 +393,9 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) k_scan_pq_db(ScanArgs a, 
 #ifdef MGPU_SCAN_DBG
       if (!(c_dbg & 4))
 #endif
+#ifdef MGPU_SCAN_DBG
+      if (!(c_dbg & 4))
+#endif
       {
         constexpr int CODES_PER_WARP = 256 / NPW;
 #pragma unroll 1
@@ -502,6 +508,8 @@ int launch_scan_pq_db(mgpu_ivf *ivf, const ScanArgs &a) {
       switch (cfg) {
         case 1: return launch_db_t<3, 20, 4>(ivf, a);
         case 2: return launch_db_t<3, 12, 4>(ivf, a);
+        case 3: return launch_db_t<3, 12, 8>(ivf, a);
+        case 4: return launch_db_t<3, 16, 8>(ivf, a);
         default: return launch_db_t<3, 16, 4>(ivf, a);
       }
     default: return MGPU_ERR_UNSUPPORTED;
