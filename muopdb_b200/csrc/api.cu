@@ -527,10 +527,45 @@ static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32
     MGPU_TRY(launch_plan_queries(ivf, d_probes, max_probes, d_counts, B, d_order, d_order + B, have_work));
     a.order = d_order;
   }
-  MGPU_TRY(launch_scan(ivf, a));
   FinalizeArgs f;
   memset(&f, 0, sizeof(f));
   f.cand_key = d_ckey; f.cand_slot = d_cslot; f.B = B; f.k = k; f.slot_pid = ivf->d_slot_pid; f.metric = ivf->metric;
+  if (k > MGPU_NCAND) {
+    // ---- k > 32: multi-round top-k.  Every round is the ordinary scan restricted to rows whose composite (ranking key,
+    // point id) is not below the bound left by the previous round, followed by the exact re-score of its (up to) 31 newly
+    // reported candidates; the rounds' exact results are merged with the reference's ordering.  Rounds = ceil((k+16)/31):
+    // 16 spare candidates cover swaps between the fixed-point ranking and the exact scores at the k boundary.
+    if (k > MGPU_MAX_K) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported", k, MGPU_MAX_K);
+    const uint32_t R = (k + 16 + 30) / 31;
+    const size_t per = (size_t)B * MGPU_NCAND;
+    size_t need = 0;
+    need = ws_need(need, (size_t)B * 8); need = ws_need(need, R * per * 4); need = ws_need(need, R * per * 4);
+    need = ws_need(need, (size_t)R * B * 4);
+    uint8_t *priv = nullptr;
+    CUDA_TRY(ctx, cudaMallocAsync((void **)&priv, need + 256, ctx->stream));
+    WsAlloc pw(priv, need + 256);
+    uint64_t *lb = pw.get<uint64_t>(B);
+    uint32_t *rP = pw.get<uint32_t>(R * per); float *rS = pw.get<float>(R * per); uint32_t *rC = pw.get<uint32_t>((size_t)R * B);
+    int st = MGPU_OK;
+    if (cudaMemsetAsync(lb, 0, (size_t)B * 8, ctx->stream) != cudaSuccess) st = mgpu_fail(ctx, MGPU_ERR_CUDA, "memset failed");
+    a.lower_bound = lb;
+    if (ivf->quant == MGPU_QUANT_PQ) {
+      f.cb = ivf->pq->d_cb; f.codes = ivf->d_codes; f.qcodes = d_qcodes; f.m = ivf->pq->m; f.K = ivf->pq->K;
+      f.dsub = ivf->pq->dsub; f.ng = ivf->ng; f.pq_fast = ivf->pq_fast;
+    }
+    f.doc_ids = nullptr; f.k = MGPU_NCAND; f.prune = false;
+    for (uint32_t r = 0; r < R && st == MGPU_OK; r++) {
+      st = launch_scan(ivf, a);
+      if (st == MGPU_OK) st = launch_round_prepare(ctx, d_ckey, d_cslot, B, lb);
+      f.out_docs = nullptr; f.out_pids = rP + r * per; f.out_scores = rS + r * per; f.out_counts = rC + (size_t)r * B;
+      if (st == MGPU_OK) st = launch_finalize(ctx, f);
+    }
+    // the k smallest by (distance, point_id) over all rounds, then (remap variants) doc ids ordered by (score, doc_id)
+    if (st == MGPU_OK) st = launch_merge_rounds(ctx, rP, rS, rC, R, B, k, ivf->d_doc_ids, d_out_pids, d_out_docs, d_out_scores, d_out_counts);
+    cudaFreeAsync(priv, ctx->stream);
+    return st;
+  }
+  MGPU_TRY(launch_scan(ivf, a));
   if (ivf->quant == MGPU_QUANT_PQ) {
     f.cb = ivf->pq->d_cb; f.codes = ivf->d_codes; f.qcodes = d_qcodes; f.m = ivf->pq->m; f.K = ivf->pq->K;
     f.dsub = ivf->pq->dsub; f.ng = ivf->ng; f.pq_fast = ivf->pq_fast;
@@ -581,7 +616,7 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
       return mgpu_fail(ctx, MGPU_ERR_OUT_OF_RANGE, "num_probes %u out of range 1..%u (the reference panics)", nprobe_coarse, ivf->nlist);
     max_probes = nprobe_coarse;
   }
-  if (k > MGPU_NCAND) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported yet", k, MGPU_NCAND);
+  if (k > MGPU_MAX_K) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported", k, MGPU_MAX_K);
   if (B && (!Q || !out_scores || !out_counts || (!out_pids && !out_docs))) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "search: null buffer");
   std::unique_lock<std::mutex> g(ctx->mu, std::defer_lock);
   if (!caller_holds_lock) g.lock();
@@ -974,7 +1009,7 @@ int mgpu_shard_ivf_search(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k,
   if (!ctx->nccl_comm) return mgpu_fail(ctx, MGPU_ERR_NCCL, "shard_ivf_search: communicator not initialised (mgpu_comm_init_rank)");
   if (B && (!Q || !out_doc_ids || !out_scores || !out_counts)) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "shard_ivf_search: null buffer");
   if (nprobe == 0 || nprobe > ivf->nlist) return mgpu_fail(ctx, MGPU_ERR_OUT_OF_RANGE, "num_probes %u out of range 1..%u (the reference panics)", nprobe, ivf->nlist);
-  if (k > MGPU_NCAND) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported yet", k, MGPU_NCAND);
+  if (k > MGPU_MAX_K) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported", k, MGPU_MAX_K);
   auto ag = (fn_ncclAllGather)nccl_sym("ncclAllGather");
   if (!ag) return mgpu_fail(ctx, MGPU_ERR_NCCL, "ncclAllGather not found");
   std::lock_guard<std::mutex> g(ctx->mu);
@@ -1221,7 +1256,7 @@ static int spann_search_impl(mgpu_spann *sp, const float *Q, uint32_t B, uint32_
   mgpu_ivf *ivf = sp->lists;
   mgpu_hnsw *hn = sp->centroids;
   if (B && (!Q || !out_doc_ids || !out_scores || !out_counts)) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "spann_search: null buffer");
-  if (top_k > MGPU_NCAND) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported yet", top_k, MGPU_NCAND);
+  if (top_k > MGPU_MAX_K) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported", top_k, MGPU_MAX_K);
   std::lock_guard<std::mutex> g(ctx->mu);
   cudaSetDevice(ctx->device);
   if (B == 0) return MGPU_OK;

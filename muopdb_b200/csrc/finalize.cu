@@ -294,3 +294,116 @@ int launch_merge_topk(mgpu_ctx *ctx, const mgpu_u128 *docs, const float *scores,
   CUDA_TRY(ctx, cudaGetLastError());
   return MGPU_OK;
 }
+
+// ---- multi-round top-k (k > 32) -----------------------------------------------------------------------------------------
+// After one scan round the query's 32 candidates are sorted by composite (ranking key << 32 | point id).  A full round
+// (32 valid entries) only REPORTS the entries strictly below its last composite c32; the group equal to c32 (duplicates of one
+// point in several probed lists share a composite) is left to the next round, whose scan ignores composites < c32.  A short
+// round has seen every remaining row: everything is reported and later rounds find nothing.
+__global__ void k_round_prepare(uint64_t *__restrict__ cand_key, uint32_t *__restrict__ cand_slot, uint32_t B,
+                                uint64_t *__restrict__ lower_bound) {
+  const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= B) return;
+  const uint64_t key = cand_key[(size_t)q * MGPU_NCAND + lane];
+  const uint32_t slot = cand_slot[(size_t)q * MGPU_NCAND + lane];
+  const unsigned valid = __ballot_sync(0xffffffffu, slot != MGPU_EMPTY_SLOT);
+  if (valid == 0xffffffffu) {
+    const uint64_t c32 = shfl64(key, 31);
+    if (key == c32) cand_slot[(size_t)q * MGPU_NCAND + lane] = MGPU_EMPTY_SLOT;
+    if (lane == 0) lower_bound[q] = c32;
+  } else if (lane == 0) {
+    lower_bound[q] = MGPU_EMPTY_KEY;
+  }
+}
+
+int launch_round_prepare(mgpu_ctx *ctx, uint64_t *cand_key, uint32_t *cand_slot, uint32_t B, uint64_t *lower_bound) {
+  if (B == 0) return MGPU_OK;
+  LaunchScope ls(ctx, MGPU_K_FINALIZE);
+  k_round_prepare<<<(B + 3) / 4, 128, 0, ctx->stream>>>(cand_key, cand_slot, B, lower_bound);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return MGPU_OK;
+}
+
+// Merge of the rounds' exact results: the reference keeps the k smallest by (distance, point_id) (bounded heap,
+// index.rs:265-274; utils.rs:71-76) and only then maps to doc ids and orders by (score, doc_id) (index.rs:311-326).  Both
+// orders by counting in shared memory; one block per query.  pids/scores: [R][B][32], counts: [R][B].
+__global__ void k_merge_rounds(const uint32_t *__restrict__ pids, const float *__restrict__ scores,
+                               const uint32_t *__restrict__ counts, uint32_t R, uint32_t B, uint32_t k,
+                               const mgpu_u128 *__restrict__ doc_ids, int remap, uint32_t *__restrict__ out_pids,
+                               mgpu_u128 *__restrict__ out_docs, float *__restrict__ out_scores,
+                               uint32_t *__restrict__ out_counts) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  const uint32_t n = R * MGPU_NCAND;
+  mgpu_u128 *sd = (mgpu_u128 *)sm;      // doc id of a selected entry
+  uint32_t *sk = (uint32_t *)(sd + n);  // score key
+  uint32_t *sp = sk + n;                // point id
+  uint32_t *sf = sp + n;                // 0 absent, 1 present, 2 selected (among the k smallest by (distance, point_id))
+  const uint32_t q = blockIdx.x;
+  for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+    const uint32_t r = e / MGPU_NCAND, i = e % MGPU_NCAND;
+    const bool valid = i < counts[(size_t)r * B + q];
+    const size_t src = ((size_t)r * B + q) * MGPU_NCAND + i;
+    sk[e] = valid ? f2key(scores[src]) : 0xFFFFFFFFu;
+    sp[e] = valid ? pids[src] : 0xFFFFFFFFu;
+    sf[e] = valid ? 1u : 0u;
+  }
+  __syncthreads();
+  uint32_t total = 0;
+  for (uint32_t e = 0; e < n; e++) total += sf[e] ? 1u : 0u;
+  const uint32_t cnt = total < k ? total : k;
+  __syncthreads();
+  for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+    if (!sf[e]) continue;
+    uint32_t rank = 0;
+    const uint32_t ke = sk[e], pe = sp[e];
+    for (uint32_t j = 0; j < n; j++) {
+      const uint32_t kj = sk[j], pj = sp[j];   // absent entries carry the maximal (key, pid): never counted
+      rank += (kj < ke || (kj == ke && (pj < pe || (pj == pe && j < e)))) ? 1u : 0u;
+    }
+    if (rank < k) {
+      if (!remap) {
+        out_pids[(size_t)q * k + rank] = pe;
+        out_scores[(size_t)q * k + rank] = key2f(ke);
+      } else {
+        mgpu_u128 d;
+        if (doc_ids) d = doc_ids[pe]; else { d.lo = pe; d.hi = 0; }
+        sd[e] = d;
+      }
+    }
+    // publish the selection after the ranks of this pass are final for everyone (flags are only read as != 0 above)
+    if (rank < k && remap) atomicExch(&sf[e], 2u);
+  }
+  __syncthreads();
+  if (remap) {
+    for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+      if (sf[e] != 2u) continue;
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < n; j++) {
+        if (sf[j] != 2u) continue;
+        const bool less = doc_less(sk[j], sd[j], sk[e], sd[e]);
+        const bool same = sk[j] == sk[e] && sd[j].lo == sd[e].lo && sd[j].hi == sd[e].hi;
+        rank += (less || (same && j < e)) ? 1u : 0u;
+      }
+      out_docs[(size_t)q * k + rank] = sd[e];
+      out_scores[(size_t)q * k + rank] = key2f(sk[e]);
+    }
+  }
+  if (threadIdx.x == 0) out_counts[q] = cnt;
+}
+
+int launch_merge_rounds(mgpu_ctx *ctx, const uint32_t *pids, const float *scores, const uint32_t *counts, uint32_t R, uint32_t B,
+                        uint32_t k, const mgpu_u128 *doc_ids, uint32_t *out_pids, mgpu_u128 *out_docs, float *out_scores,
+                        uint32_t *out_counts) {
+  if (B == 0 || k == 0) return MGPU_OK;
+  const size_t n = (size_t)R * MGPU_NCAND;
+  const size_t smem = n * (sizeof(mgpu_u128) + 12);
+  if (smem > ctx->smem_optin) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "merge of %zu candidates per query exceeds shared memory", n);
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k_merge_rounds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LaunchScope ls(ctx, MGPU_K_FINALIZE);
+  k_merge_rounds<<<B, 256, smem, ctx->stream>>>(pids, scores, counts, R, B, k, doc_ids, out_docs != nullptr ? 1 : 0, out_pids, out_docs,
+                                                 out_scores, out_counts);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return MGPU_OK;
+}
+

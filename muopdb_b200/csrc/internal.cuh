@@ -84,6 +84,7 @@ struct mgpu_spann {
 
 // ---- candidates produced by a scan: per query 32 (composite key, slot) pairs -------------------
 #define MGPU_NCAND 32
+#define MGPU_MAX_K 2048   /* k > 32 runs ceil((k+16)/31) scan rounds (api.cu: ivf_scan_dev) */
 
 struct ScanArgs {
   // index
@@ -104,6 +105,9 @@ struct ScanArgs {
   // planner filter hook (index.rs:212-226): when non-null a scanned row survives only if bit `point id` of its query's
   // bitmap is set; query q uses filter + q * filter_stride (stride 0 = one bitmap shared by the whole batch)
   const uint32_t *filter; uint64_t filter_stride;
+  // k > 32 (multi-round top-k, api.cu): when non-null, a row whose composite (key << 32 | point id) is below
+  // lower_bound[q] is invisible to this scan (it was reported by an earlier round)
+  const uint64_t *lower_bound;
   // PQ table-driven scan: queries with more chunks than the shared-memory chunk table are deferred to a second launch
   unsigned int *overflow_count; uint32_t *overflow_list;
   int metric;
@@ -143,6 +147,11 @@ int launch_assign_filter(mgpu_ctx *ctx, const uint32_t *sel_ids, const float *se
                          float threshold, uint32_t *out_cids, uint32_t *out_counts);
 int launch_merge_topk(mgpu_ctx *ctx, const mgpu_u128 *docs, const float *scores, const uint32_t *counts, uint32_t S,
                       uint32_t B, uint32_t k, mgpu_u128 *out_docs, float *out_scores, uint32_t *out_counts);
+// multi-round top-k helpers (finalize.cu)
+int launch_round_prepare(mgpu_ctx *ctx, uint64_t *cand_key, uint32_t *cand_slot, uint32_t B, uint64_t *lower_bound);
+int launch_merge_rounds(mgpu_ctx *ctx, const uint32_t *pids, const float *scores, const uint32_t *counts, uint32_t R, uint32_t B,
+                        uint32_t k, const mgpu_u128 *doc_ids, uint32_t *out_pids, mgpu_u128 *out_docs, float *out_scores,
+                        uint32_t *out_counts);
 
 // tensor-core coarse scoring (coarse_tc.cu)
 uint32_t coarse_tc_kp(uint32_t dim);

@@ -283,7 +283,8 @@ __global__ void __launch_bounds__(NT, 1) k_scan(ScanArgs a, ScanSmemLayout L) {
       }
 
       const uint32_t thr = *(volatile uint32_t *)&sh[0];
-      const bool pass = valid && key <= thr;
+      bool pass = valid && key <= thr;
+      if (a.lower_bound && pass && (((uint64_t)key << 32) | pid) < a.lower_bound[q]) pass = false;  // reported by an earlier round
       if (__any_sync(0xffffffffu, pass)) {
         uint32_t worst;
         if (first) {

@@ -155,6 +155,7 @@ struct DbConsumerCtx {
         if (pass) {
           if (a.invalid && ((a.invalid[pid >> 5] >> (pid & 31)) & 1u)) pass = false;            // index.rs:198-200
           if (a.filter && pass && !((a.filter[(size_t)q * a.filter_stride + (pid >> 5)] >> (pid & 31)) & 1u)) pass = false;  // :212-226
+          if (a.lower_bound && pass && (((uint64_t)key << 32) | pid) < a.lower_bound[q]) pass = false;  // reported by an earlier round
         }
         if (__any_sync(0xffffffffu, pass)) offer_rows(top, first, pass, key, pid, slot, thr);
       }
@@ -214,7 +215,8 @@ struct DbConsumerCtx {
         }
       }
       const uint32_t thr = *(volatile uint32_t *)thr_p;
-      const bool pass = valid && key <= thr;
+      bool pass = valid && key <= thr;
+      if (a.lower_bound && pass && (((uint64_t)key << 32) | pid) < a.lower_bound[q]) pass = false;  // reported by an earlier round
       if (__any_sync(0xffffffffu, pass)) offer_rows(top, first, pass, key, pid, slot, thr);
     }
   }

@@ -607,9 +607,40 @@ def test_shard_search_single_rank_world(M):
     od, os_, oc = oivf.search_batch(Q, 10, 5)
     for dev in (False, True):
         r = givf.shard_search_batch(torch.from_numpy(Q).cuda() if dev else Q, 10, 5)
+        ctx.sync()   # device-buffer calls are asynchronous on the library stream
         ids_, sc, cn = ((x.cpu().numpy() if dev else np.asarray(x)) for x in (r.doc_ids, r.scores, r.counts))
         assert np.array_equal(cn.astype(np.int64), oc.astype(np.int64))
         for b in range(len(Q)):
             n = int(oc[b])
             assert np.array_equal(ids_[b, :n].view(np.uint64), np.asarray(od[b, :n], dtype=np.uint64)), (dev, b)
             assert _same_f32(sc[b, :n], os_[b, :n]), (dev, b)
+
+
+@pytest.mark.parametrize("k", [33, 64, 100, 257])
+@pytest.mark.parametrize("pq", [None, (8, 8)])
+def test_ivf_large_k_multi_round(M, k, pq):
+    """k > 32 runs several scan rounds (each hides the rows reported so far) and merges their exact results: same ids,
+    order and scores as the reference's bounded heap of size k (index.rs:265-274), through search (doc ids) and
+    search_with_centroids (point ids), with fewer than k rows available for some queries."""
+    X = synth.clustered(3000, 128, n_blobs=8, seed=k)
+    _check_ivf(M, X, nlist=12, nprobe=5, k=k, pq_params=pq, seed=k + 1)
+
+
+def test_ivf_large_k_with_duplicates_and_invalidation(M):
+    """Exact code-word ties, points living in two probed lists (same composite twice) and invalidated ids, k = 48 and 120:
+    the group sharing a round's last composite is carried over to the next round as a whole."""
+    rng = np.random.default_rng(7)
+    base = synth.clustered(300, 256, n_blobs=5, seed=17)
+    X = np.repeat(base, 4, axis=0)[rng.permutation(1200)]
+    inv = np.arange(3, 1200, 11, dtype=np.uint32)
+    _check_ivf(M, X, nlist=6, nprobe=6, k=48, pq_params=(8, 8), max_clusters=2, invalidate=inv, seed=18)
+    _check_ivf(M, X, nlist=6, nprobe=4, k=120, max_clusters=2, invalidate=inv, seed=19)
+
+
+def test_k_above_limit_is_rejected(M):
+    X = synth.clustered(500, 32, n_blobs=3, seed=2)
+    cents = O.kmeans(X, 4, iters=3, seed=1)
+    offsets, ids = O.build_posting_lists(X, cents)
+    givf = M.BlockBasedIvf(cents, offsets, ids, X, M.NoQuantizer(32))
+    with pytest.raises(M.Unsupported):
+        givf.search_batch(X[:4], 5000, 2)

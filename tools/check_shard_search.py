@@ -57,6 +57,7 @@ def main():
     ok = True
 
     def same(r, dev, tag=""):
+        ctx.sync()   # device-buffer calls are asynchronous on the library stream
         ids_, sc, cn = ((x.cpu().numpy() if dev else np.asarray(x)) for x in (r.doc_ids, r.scores, r.counts))
         bad = 0
         for b in range(B):
