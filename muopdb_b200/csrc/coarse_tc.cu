@@ -485,18 +485,34 @@ k_coarse_select_q(const float *__restrict__ Dt, const float *__restrict__ Q, con
     kmin = min(min(kmin, k4.x), min(k4.y, min(k4.z, k4.w)));
     kmax = max(max(kmax, k4.x), max(k4.y, max(k4.z, k4.w)));
   }
+  // Pre-filter: the nprobe-th smallest of the 128 per-thread minima is an upper bound T of tau (nprobe distinct keys are
+  // <= it), and only ~2 % of the keys are <= T.  The histogram passes below then touch ~100 keys instead of all C with
+  // shared-memory atomics (2 cycles per lane: 4096 of them per query and 7 queries per SM were 2/3 of this kernel's time).
+  const uint32_t tmin = kmin;
+  uint32_t *tmins = cand;  // SELW_CAP >= SELQ_THREADS words, free until the classification
+  tmins[tid] = tmin;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
     kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
   }
-  __syncthreads();  // misc / hist initialised
+  __syncthreads();  // misc / hist initialised, tmins published
   if (lane == 0) { atomicMin(&misc[8], kmin); atomicMax(&misc[9], kmax); }
+  if (nprobe <= SELQ_THREADS) {
+    uint32_t r = 0;
+#pragma unroll 8
+    for (int j = 0; j < SELQ_THREADS; j++) {
+      const uint32_t o = tmins[j];
+      r += (o < tmin || (o == tmin && j < tid)) ? 1u : 0u;
+    }
+    if (r == nprobe - 1) misc[11] = tmin;   // exactly one thread
+  }
   __syncthreads();
-  // ---- two histogram levels over [kmin, kmax]: the key interval [lo_key, hi_key] of width range / 2^20 holding tau
+  // ---- two histogram levels over [kmin, T]: the key interval [lo_key, hi_key] of width range / 2^20 holding tau
   uint32_t base = misc[8];
-  uint32_t width_log = 32 - __clz((misc[9] - base) | 1u);
-  uint32_t lo_key = base, hi_key = misc[9];
+  const uint32_t top_key = nprobe <= SELQ_THREADS ? min(misc[11], misc[9]) : misc[9];
+  uint32_t width_log = 32 - __clz((top_key - base) | 1u);
+  uint32_t lo_key = base, hi_key = top_key;
   for (int pass = 0; pass < 2; pass++) {
     const uint32_t shift = width_log > 10 ? width_log - 10 : 0;
 #pragma unroll 4
@@ -737,6 +753,9 @@ int launch_coarse_tc(mgpu_ctx *ctx, const float *dQ, uint32_t B, const float *d_
                      uint32_t *d_overflow, uint32_t *d_flags, int need_order, uint32_t *out_ids, float *out_dist,
                      const uint32_t *chunk_start, uint32_t *d_work, bool *work_done, cudaEvent_t after_gemm) {
   const uint32_t Kp = coarse_tc_kp(dim);
+  // MGPU_FORK=0: side-stream work (the query encode) starts before the GEMM; 1 (default): after it
+  static const int fork_at = getenv("MGPU_FORK") ? atoi(getenv("MGPU_FORK")) : 1;
+  if (after_gemm && fork_at == 0) CUDA_TRY(ctx, cudaEventRecord(after_gemm, ctx->stream));
   MGPU_TRY(launch_split_bf16(ctx, dQ, B, dim, 0, d_qsplit, d_qn));
   CUtensorMap mq, mc;
   MGPU_TRY(make_map(ctx, &mq, d_qsplit, B, Kp, TC_BM));
@@ -749,7 +768,7 @@ int launch_coarse_tc(mgpu_ctx *ctx, const float *dQ, uint32_t B, const float *d_
     k_coarse_gemm<<<grid, TC_THREADS, smem, ctx->stream>>>(mq, mc, d_qn, d_cn, B, C, Kp, d_Dt);
     CUDA_TRY(ctx, cudaGetLastError());
   }
-  if (after_gemm) CUDA_TRY(ctx, cudaEventRecord(after_gemm, ctx->stream));  // fork point for work that may overlap the selection
+  if (after_gemm && fork_at != 0) CUDA_TRY(ctx, cudaEventRecord(after_gemm, ctx->stream));  // fork point for work that may overlap the selection
   uint32_t cap = 1;
   while (cap < C) cap <<= 1;
   size_t ssel = ((dim + 3) & ~3u) * 4 + (size_t)cap * 12 + SEL_BINS * 4 + 64;
