@@ -312,9 +312,11 @@ def main():
         step_device(i)
     barrier()
 
-    # ---- timed: device-resident queries, per-step CUDA events on the library stream, L2 flushed between steps
+    # ---- timed: device-resident queries, per-step CUDA events on the library stream, L2 flushed between steps.  Only the
+    # scan kernel (the roofline kernel) is bracketed by events inside the timed region; the other launches run back to back
+    # as they do in production.  The per-class breakdown comes from a second, untimed pass with every class bracketed.
     ctx.profile_reset()
-    ctx.profile_enable(True)
+    ctx.profile_enable(True, classes=[_lib.K_SCAN])
     launches0 = ctx.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     scan_bytes = 0
@@ -330,7 +332,16 @@ def main():
     launches = ctx.launch_count() - launches0
     ctx.profile_enable(False)
     scan_ms, scan_launches = ctx.profile_get(_lib.K_SCAN)
-    prof = {nme: ctx.profile_get(c)[0] for c, nme in enumerate(_lib.KERNEL_CLASS_NAMES)}
+    ctx.profile_reset()
+    ctx.profile_enable(True)
+    nprof = min(args.steps, 10)
+    with torch.cuda.stream(ext):
+        for i in range(nprof):
+            flush.zero_()
+            step_device(i)
+    barrier()
+    ctx.profile_enable(False)
+    prof = {nme: ctx.profile_get(c)[0] * args.steps / nprof for c, nme in enumerate(_lib.KERNEL_CLASS_NAMES)}
     scan_bytes_per_launch = ivf.last_scan_bytes()  # every batch scans about the same number of rows; this is the last one
     rows_per_launch = ivf.last_scan_rows()
     t = torch.tensor([dev_ms], dtype=torch.float64, device=device)

@@ -83,7 +83,8 @@ int mgpu_device_sm_count(mgpu_ctx *ctx);
 int mgpu_timer_start(mgpu_ctx *ctx);
 int mgpu_timer_stop(mgpu_ctx *ctx, float *elapsed_ms); /* records, synchronises, returns elapsed */
 
-/* Per-kernel-class profiling: when on, every launch of a class is bracketed by events. */
+/* Per-kernel-class profiling: launches of the enabled classes are bracketed by events.  on > 0: all classes; on < 0: -on is
+ * a bit mask of classes (1 << MGPU_K_*); 0: off. */
 int mgpu_profile_enable(mgpu_ctx *ctx, int on);
 int mgpu_profile_reset(mgpu_ctx *ctx);
 int mgpu_profile_get(mgpu_ctx *ctx, int kernel_class, float *total_ms, uint64_t *launches);

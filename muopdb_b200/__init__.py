@@ -139,8 +139,10 @@ class Context:
         _lib.check(self.lib.mgpu_timer_stop(self.h, C.byref(ms)), self.h)
         return ms.value
 
-    def profile_enable(self, on=True):
-        _lib.check(self.lib.mgpu_profile_enable(self.h, int(on)), self.h)
+    def profile_enable(self, on=True, classes=None):
+        """classes: iterable of kernel classes (_lib.K_*) to bracket with events; None = all (when `on`)."""
+        v = int(bool(on)) if classes is None or not on else -sum(1 << c for c in classes)
+        _lib.check(self.lib.mgpu_profile_enable(self.h, v), self.h)
 
     def profile_reset(self):
         _lib.check(self.lib.mgpu_profile_reset(self.h), self.h)

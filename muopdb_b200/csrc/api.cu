@@ -127,7 +127,9 @@ int mgpu_timer_stop(mgpu_ctx *ctx, float *ms) {
 int mgpu_profile_enable(mgpu_ctx *ctx, int on) {
   if (!ctx) return MGPU_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> g(ctx->mu);
-  ctx->profiling = on != 0;
+  // on > 0: every class; on < 0: -on is a bit mask of classes (e.g. -(1 << MGPU_K_SCAN): only the scan kernel, so that the
+  // other launches of a timed region run back to back without event records between them); 0: off
+  ctx->profiling = on > 0 ? 0xFFFFFFFFu : (on < 0 ? (uint32_t)(-on) : 0u);
   return MGPU_OK;
 }
 int mgpu_profile_reset(mgpu_ctx *ctx) {

@@ -31,7 +31,7 @@ struct mgpu_ctx {
   void *pinned = nullptr; size_t pinned_bytes = 0;
   // timing
   cudaEvent_t t0 = nullptr, t1 = nullptr;
-  bool profiling = false;
+  uint32_t profiling = 0;   // bit c set: launches of kernel class c are bracketed by events
   struct Prof { std::vector<cudaEvent_t> ev; uint64_t launches = 0; float done_ms = 0.f; };
   Prof prof[MGPU_K_COUNT];
   uint64_t launches = 0;
@@ -71,10 +71,10 @@ struct LaunchScope {
   mgpu_ctx *ctx; int cls; cudaStream_t st;
   LaunchScope(mgpu_ctx *c, int k, cudaStream_t s = nullptr) : ctx(c), cls(k), st(s ? s : c->stream) {
     ctx->launches++; ctx->prof[cls].launches++;
-    if (ctx->profiling) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ctx->prof[cls].ev.push_back(e); }
+    if (ctx->profiling >> cls & 1u) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ctx->prof[cls].ev.push_back(e); }
   }
   ~LaunchScope() {
-    if (ctx->profiling) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ctx->prof[cls].ev.push_back(e); }
+    if (ctx->profiling >> cls & 1u) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ctx->prof[cls].ev.push_back(e); }
   }
 };
 
