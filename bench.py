@@ -381,7 +381,7 @@ def main():
     e2e_blocking_s = float(t.item())
     e2e_s, e2e_mode = e2e_blocking_s, "blocking call per batch (mgpu_ivf_search, MGPU_HOST), L2 flushed + synchronised between calls"
 
-    if world == 1:
+    if True:
         # pipelined form of the same host-buffer call (mgpu_ivf_search_submit / mgpu_search_wait): two batches in flight, so
         # batch i+1's H2D and batch i-1's D2H overlap batch i's kernels.  Every step still uploads its queries from pinned
         # memory and downloads its results.  The L2 flush runs on the library stream between batches; its event-timed
@@ -399,7 +399,10 @@ def main():
                     flush.zero_()
                     if timed:
                         fev[i][1].record(ext)
-                tk = ivf.search_batch_submit(Qh[i % nbatches], k, nprobe, outs[i & 1])
+                if world > 1:
+                    tk = ivf.shard_search_batch_submit(Qh[i % nbatches], k, nprobe, outs[i & 1], shared_codebook=True)
+                else:
+                    tk = ivf.search_batch_submit(Qh[i % nbatches], k, nprobe, outs[i & 1])
                 if prev is not None:
                     ivf.search_wait(prev)
                 prev = tk
@@ -413,11 +416,16 @@ def main():
         barrier()
         flush_s = sum(a.elapsed_time(b) for a, b in fev) / 1e3
         e2e_s = wall - flush_s
-        e2e_mode = ("pipelined host-buffer calls (mgpu_ivf_search_submit/mgpu_search_wait, 2 batches in flight); wall clock of "
-                    "%d steps minus the event-timed L2 flushes (%.3f ms/step) that run between batches" % (args.steps, flush_s * 1e3 / args.steps))
+        if world > 1:   # the job is as slow as its slowest rank
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e_mode = ("pipelined host-buffer calls (mgpu_%sivf_search_submit/mgpu_search_wait, 2 batches in flight); wall clock of "
+                    "%d steps minus the event-timed L2 flushes (%.3f ms/step) that run between batches"
+                    % ("shard_" if world > 1 else "", args.steps, flush_s * 1e3 / args.steps))
         # the pipelined results are the blocking call's results
         last = args.steps - 1
-        ref = ivf.search_batch(Qh[last % nbatches], k, nprobe)
+        ref = ivf.shard_search_batch(Qh[last % nbatches], k, nprobe) if world > 1 else ivf.search_batch(Qh[last % nbatches], k, nprobe)
         got_ids = outs[last & 1][0].numpy()
         if not os.environ.get("MGPU_SCAN_DBG"):  # (experiment builds of the scan kernel return garbage on purpose)
             assert np.array_equal(np.asarray(ref.doc_ids).view(np.int64).reshape(got_ids.shape), got_ids), "pipelined != blocking"

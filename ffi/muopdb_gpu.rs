@@ -47,6 +47,9 @@ extern "C" {
     /// sharded search in one collective call (query encode split across ranks when the codebook is shared)
     pub fn mgpu_shard_ivf_search(ivf: *mut mgpu_ivf, q: *const c_float, b: u32, k: u32, nprobe: u32, shared_codebook: c_int,
                                  out_doc_ids: *mut mgpu_u128, out_scores: *mut c_float, out_counts: *mut u32, mem: c_int) -> c_int;
+    pub fn mgpu_shard_ivf_search_submit(ivf: *mut mgpu_ivf, q: *const c_float, b: u32, k: u32, nprobe: u32, shared_codebook: c_int,
+                                        out_doc_ids: *mut mgpu_u128, out_scores: *mut c_float, out_counts: *mut u32,
+                                        ticket: *mut u64) -> c_int;
     pub fn mgpu_hnsw_search(h: *mut mgpu_hnsw, q: *const c_float, b: u32, k: u32, ef: u32, out_doc_ids: *mut mgpu_u128,
                             out_scores: *mut c_float, out_counts: *mut u32, out_stats: *mut u64, mem: c_int) -> c_int;
     pub fn mgpu_spann_search(s: *mut mgpu_spann, q: *const c_float, b: u32, top_k: u32, ef: u32, num_explored_centroids: u32,

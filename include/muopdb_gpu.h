@@ -242,6 +242,10 @@ int mgpu_shard_allgather_merge(mgpu_ctx *ctx, const mgpu_u128 *local_doc_ids, co
  * Collective: all ranks must call it with the same B, k.  Buffers in `mem` space. */
 int mgpu_shard_ivf_search(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, int shared_codebook,
                           mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, int mem);
+/* Pipelined form over page-locked HOST buffers (see mgpu_ivf_search_submit): returns a ticket, mgpu_search_wait completes it.
+ * Still a collective: every rank submits the same sequence of batches. */
+int mgpu_shard_ivf_search_submit(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, int shared_codebook,
+                                 mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, uint64_t *ticket);
 
 /* ---- Readers of the reference's on-disk formats -------------- */
 /* One Elias-Fano posting-list payload (rs/compression/src/elias_fano/ef.rs:197-215; decode rule

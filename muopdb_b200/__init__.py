@@ -588,6 +588,20 @@ class BlockBasedIvf:
                                                       q.mem), self.ctx.h)
         return BatchResult(ids, scores, cnt)
 
+    def shard_search_batch_submit(self, Q, k: int, num_probes: int, out, shared_codebook: bool = True) -> int:
+        """Pipelined shard_search_batch over page-locked HOST buffers (mgpu_shard_ivf_search_submit); `search_wait(ticket)`
+        completes it.  Collective: every rank submits the same batches in the same order."""
+        q = _Buf(Q, np.float32, (None, self.dim))
+        if q.mem != HOST:
+            raise ValueError("shard_search_batch_submit takes host buffers")
+        ip, sp, cp = (x.data_ptr() if _is_torch(x) else x.ctypes.data for x in out)
+        t = C.c_uint64(0)
+        _lib.check(self.ctx.lib.mgpu_shard_ivf_search_submit(self.handle, q.ptr, q.shape[0], k, num_probes, 1 if shared_codebook else 0,
+                                                             ip, sp, cp, C.byref(t)), self.ctx.h)
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[t.value] = (Q, out)
+        return int(t.value)
+
     def search_batch_submit(self, Q, k: int, num_probes: int, out) -> int:
         """Pipelined search_batch over page-locked HOST buffers (mgpu_ivf_search_submit): returns a ticket at once; `out`
         = (ids, scores, counts) is valid after `search_wait(ticket)`.  Two batches may be in flight, so the next batch's

@@ -105,6 +105,7 @@ SIGNATURES = {
     "mgpu_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mgpu_comm_destroy": (C.c_int, [C.c_void_p]),
     "mgpu_shard_ivf_search": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _vp, _f32p, _u32p, C.c_int]),
+    "mgpu_shard_ivf_search_submit": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _vp, _f32p, _u32p, C.POINTER(C.c_uint64)]),
     "mgpu_shard_allgather_merge": (C.c_int, [C.c_void_p, _vp, _f32p, _u32p, C.c_uint32, C.c_uint32, _vp, _f32p, _u32p]),
     "mgpu_ef_decode": (C.c_int64, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "mgpu_pq_load": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),

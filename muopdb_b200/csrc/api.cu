@@ -603,6 +603,31 @@ static int pipe_prepare(mgpu_ctx *ctx, mgpu_ctx::Pipe *pp, size_t q_bytes, size_
   return MGPU_OK;
 }
 
+// first half of a pipelined host-buffer call: claims the slot, uploads Q on the H2D stream, makes the main stream wait for it
+static int pipe_begin(mgpu_ctx *ctx, const void *Q, size_t q_bytes, size_t out_bytes, mgpu_ctx::Pipe **out_pp) {
+  mgpu_ctx::Pipe *pp = &ctx->pipe[ctx->pipe_seq & 1];
+  MGPU_TRY(pipe_prepare(ctx, pp, q_bytes, out_bytes));
+  if (pp->used) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->h2d_stream, pp->ev_done, 0));  // the previous user of the buffer has read it
+  CUDA_TRY(ctx, cudaMemcpyAsync(pp->q, Q, q_bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
+  CUDA_TRY(ctx, cudaEventRecord(pp->ev_h2d, ctx->h2d_stream));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, pp->ev_h2d, 0));
+  *out_pp = pp;
+  return MGPU_OK;
+}
+// second half: results leave on the D2H stream; the ticket completes when they have landed in the caller's buffers
+static int pipe_end(mgpu_ctx *ctx, mgpu_ctx::Pipe *pp, uint32_t B, uint32_t k, const mgpu_u128 *dD, const float *dS, const uint32_t *dC,
+                    mgpu_u128 *out_docs, float *out_scores, uint32_t *out_counts, uint64_t *ticket) {
+  CUDA_TRY(ctx, cudaEventRecord(pp->ev_done, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->d2h_stream, pp->ev_done, 0));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_docs, dD, (size_t)B * k * 16, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_scores, dS, (size_t)B * k * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_counts, dC, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  CUDA_TRY(ctx, cudaEventRecord(pp->ev_out, ctx->d2h_stream));
+  pp->seq = ++ctx->pipe_seq; pp->pending = true; pp->used = true;
+  *ticket = pp->seq;
+  return MGPU_OK;
+}
+
 // shared implementation of scan / scan_remap / search
 static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint32_t *probe_ids, uint32_t max_probes,
                            const uint32_t *probe_counts, uint32_t nprobe_coarse, uint32_t k, uint32_t *out_pids,
@@ -672,12 +697,7 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
   mgpu_ctx::Pipe *pp = nullptr;
   if (ticket) {
     // pipelined call: queries go through this slot's own staging buffer on the H2D stream
-    pp = &ctx->pipe[ctx->pipe_seq & 1];
-    MGPU_TRY(pipe_prepare(ctx, pp, bQ, (size_t)B * k * 24 + (size_t)B * 4 + 768));
-    if (pp->used) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->h2d_stream, pp->ev_done, 0));  // the previous user of the buffer has read it
-    CUDA_TRY(ctx, cudaMemcpyAsync(pp->q, Q, bQ, cudaMemcpyHostToDevice, ctx->h2d_stream));
-    CUDA_TRY(ctx, cudaEventRecord(pp->ev_h2d, ctx->h2d_stream));
-    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, pp->ev_h2d, 0));
+    MGPU_TRY(pipe_begin(ctx, Q, bQ, (size_t)B * k * 24 + (size_t)B * 4 + 768, &pp));
     dQ = pp->q;
   } else {
     MGPU_TRY(stage_in(ctx, Q, bQ, mem, sQ, &dQ));
@@ -717,16 +737,7 @@ static int ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, const uint
   MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, dP, max_probes, dPC, k, d_qcodes_ext ? (uint8_t *)d_qcodes_ext : dQC, dCK, dCS, dOrd, oP, oD,
                         oS, oC, qcodes_on_aux, dF, filter_stride, have_work, d_qcodes_ext != nullptr));
   if (pp) {
-    // results leave on the D2H stream; the ticket completes when they have landed in the caller's buffers
-    CUDA_TRY(ctx, cudaEventRecord(pp->ev_done, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->d2h_stream, pp->ev_done, 0));
-    CUDA_TRY(ctx, cudaMemcpyAsync(out_docs, oD, (size_t)B * k * 16, cudaMemcpyDeviceToHost, ctx->d2h_stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(out_scores, oS, (size_t)B * k * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(out_counts, oC, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
-    CUDA_TRY(ctx, cudaEventRecord(pp->ev_out, ctx->d2h_stream));
-    pp->seq = ++ctx->pipe_seq; pp->pending = true; pp->used = true;
-    *ticket = pp->seq;
-    return MGPU_OK;
+    return pipe_end(ctx, pp, B, k, oD, oS, oC, out_docs, out_scores, out_counts, ticket);
   }
   if (mem == MGPU_HOST) {
     MGPU_TRY(stage_out(ctx, out_pids, oP, (size_t)B * k * 4, mem));
@@ -1004,10 +1015,11 @@ int mgpu_shard_allgather_merge(mgpu_ctx *ctx, const mgpu_u128 *local_doc_ids, co
 // every rank returns the merged result.  With a codebook shared by all shards (shared_codebook != 0) the query encode
 // (index.rs:193) -- per-query work that does not shrink with the shard -- is split across the ranks: rank r encodes
 // queries [r*ceil(B/N), (r+1)*ceil(B/N)) and one all-gather of B x m code bytes replaces N-1 redundant encodes per query.
-int mgpu_shard_ivf_search(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, int shared_codebook,
-                          mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, int mem) {
+static int shard_ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, int shared_codebook,
+                                 mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, int mem, uint64_t *ticket) {
   if (!ivf) return MGPU_ERR_INVALID_ARG;
   mgpu_ctx *ctx = ivf->ctx;
+  if (ticket) *ticket = 0;
   if (!ctx->nccl_comm) return mgpu_fail(ctx, MGPU_ERR_NCCL, "shard_ivf_search: communicator not initialised (mgpu_comm_init_rank)");
   if (B && (!Q || !out_doc_ids || !out_scores || !out_counts)) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "shard_ivf_search: null buffer");
   if (nprobe == 0 || nprobe > ivf->nlist) return mgpu_fail(ctx, MGPU_ERR_OUT_OF_RANGE, "num_probes %u out of range 1..%u (the reference panics)", nprobe, ivf->nlist);
@@ -1048,7 +1060,13 @@ int mgpu_shard_ivf_search(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k,
   float *outS = w.get<float>(mem == MGPU_HOST ? (size_t)B * k : 0);
   uint32_t *outC = w.get<uint32_t>(mem == MGPU_HOST ? B : 0);
   const void *dQv;
-  MGPU_TRY(stage_in(ctx, Q, (size_t)B * ivf->dim * 4, mem, sQ, &dQv));
+  mgpu_ctx::Pipe *pp = nullptr;
+  if (ticket) {   // pipelined: this slot's staging for the queries and the merged results, copies on the side streams
+    MGPU_TRY(pipe_begin(ctx, Q, (size_t)B * ivf->dim * 4, (size_t)B * k * 24 + (size_t)B * 4 + 768, &pp));
+    dQv = pp->q;
+  } else {
+    MGPU_TRY(stage_in(ctx, Q, (size_t)B * ivf->dim * 4, mem, sQ, &dQv));
+  }
   const float *dQ = (const float *)dQv;
   const uint8_t *ext = nullptr;
   if (split_encode) {
@@ -1063,7 +1081,12 @@ int mgpu_shard_ivf_search(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k,
   mgpu_u128 *oD = mem == MGPU_DEVICE ? out_doc_ids : outD;
   float *oS = mem == MGPU_DEVICE ? out_scores : outS;
   uint32_t *oC = mem == MGPU_DEVICE ? out_counts : outC;
+  if (pp) {
+    WsAlloc wo(pp->out, pp->out_bytes);
+    oD = wo.get<mgpu_u128>((size_t)B * k); oS = wo.get<float>((size_t)B * k); oC = wo.get<uint32_t>(B);
+  }
   MGPU_TRY(shard_allgather_merge_impl(ctx, locD, locS, locC, B, k, oD, oS, oC, true));
+  if (pp) return pipe_end(ctx, pp, B, k, oD, oS, oC, out_doc_ids, out_scores, out_counts, ticket);
   if (mem == MGPU_HOST) {
     MGPU_TRY(stage_out(ctx, out_doc_ids, oD, (size_t)B * k * 16, mem));
     MGPU_TRY(stage_out(ctx, out_scores, oS, (size_t)B * k * 4, mem));
@@ -1071,6 +1094,22 @@ int mgpu_shard_ivf_search(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k,
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return MGPU_OK;
+}
+
+int mgpu_shard_ivf_search(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, int shared_codebook,
+                          mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, int mem) {
+  return shard_ivf_search_impl(ivf, Q, B, k, nprobe, shared_codebook, out_doc_ids, out_scores, out_counts, mem, nullptr);
+}
+
+/* Pipelined form for page-locked host buffers (mgpu_search_wait completes it); collective like the blocking call. */
+int mgpu_shard_ivf_search_submit(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, int shared_codebook,
+                                 mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, uint64_t *ticket) {
+  if (!ivf || !ticket) return MGPU_ERR_INVALID_ARG;
+  if (B == 0 || k == 0) {
+    *ticket = 0;
+    return shard_ivf_search_impl(ivf, Q, B, k, nprobe, shared_codebook, out_doc_ids, out_scores, out_counts, MGPU_HOST, nullptr);
+  }
+  return shard_ivf_search_impl(ivf, Q, B, k, nprobe, shared_codebook, out_doc_ids, out_scores, out_counts, MGPU_HOST, ticket);
 }
 
 }  // extern "C"

@@ -76,6 +76,15 @@ def main():
 
     for dev in (False, True):
         ok &= same(givf.shard_search_batch(torch.from_numpy(Q).cuda() if dev else Q, k, nprobe, shared_codebook=True), dev, 'split')
+    # pipelined submit/wait over pinned buffers, two batches in flight
+    Qp = torch.from_numpy(Q).pin_memory()
+    outs = [(torch.zeros((B, k, 2), dtype=torch.int64).pin_memory(), torch.zeros((B, k), dtype=torch.float32).pin_memory(),
+             torch.zeros((B,), dtype=torch.int32).pin_memory()) for _ in range(3)]
+    tks = [givf.shard_search_batch_submit(Qp, k, nprobe, o) for o in outs]
+    for t in tks:
+        givf.search_wait(t)
+    for o in outs:
+        ok &= same(M.BatchResult(o[0].numpy(), o[1].numpy(), o[2].numpy()), False, 'pipelined')
     # and without the split encode (every rank encodes every query): same answer
     ok &= same(givf.shard_search_batch(Q, k, nprobe, shared_codebook=False), False, 'nosplit')
     t = torch.tensor([1 if ok else 0])
