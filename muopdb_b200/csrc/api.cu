@@ -925,6 +925,7 @@ typedef int (*fn_ncclCommInitRank)(void **, int, nccl_uid_t, int);
 typedef int (*fn_ncclCommDestroy)(void *);
 typedef int (*fn_ncclAllGather)(const void *, void *, size_t, int, void *, cudaStream_t);
 typedef const char *(*fn_ncclGetErrorString)(int);
+typedef int (*fn_ncclGroup)(void);
 
 static void *g_nccl = nullptr;
 static void *nccl_sym(const char *name) {
@@ -995,10 +996,15 @@ static int shard_allgather_merge_impl(mgpu_ctx *ctx, const mgpu_u128 *local_doc_
   MGPU_TRY(mgpu_ws_reserve(ctx, need));
   WsAlloc w(ctx->ws, ctx->ws_bytes);
   mgpu_u128 *gD = w.get<mgpu_u128>(S * nloc); float *gS = w.get<float>(S * nloc); uint32_t *gC = w.get<uint32_t>((size_t)S * B);
-  // ncclChar = 0; three small all-gathers over NVLink (B*k*20 + B*4 bytes per rank)
+  // ncclChar = 0; three small all-gathers over NVLink (B*k*20 + B*4 bytes per rank), grouped so that NCCL issues them as one
+  // launch (the exchange is latency bound: three separate collectives cost three launch + handshake latencies)
+  auto gs = (fn_ncclGroup)nccl_sym("ncclGroupStart");
+  auto ge = (fn_ncclGroup)nccl_sym("ncclGroupEnd");
+  const bool grouped = gs && ge && gs() == 0;
   int r = ag(local_doc_ids, gD, nloc * 16, 0, ctx->nccl_comm, ctx->stream);
   if (r == 0) r = ag(local_scores, gS, nloc * 4, 0, ctx->nccl_comm, ctx->stream);
   if (r == 0) r = ag(local_counts, gC, (size_t)B * 4, 0, ctx->nccl_comm, ctx->stream);
+  if (grouped) { const int r2 = ge(); if (r == 0) r = r2; }
   if (r != 0) return mgpu_fail(ctx, MGPU_ERR_NCCL, "ncclAllGather failed (%d)", r);
   ctx->launches += 3;
   return launch_merge_topk(ctx, gD, gS, gC, S, B, k, out_doc_ids, out_scores, out_counts);
