@@ -132,7 +132,7 @@ int mgpu_batcher_create(mgpu_ivf *ivf, uint32_t max_batch, uint32_t max_wait_us,
   if (!ivf || !out) return MGPU_ERR_INVALID_ARG;
   *out = nullptr;
   if (max_batch == 0 || k == 0) return mgpu_fail(ivf->ctx, MGPU_ERR_INVALID_ARG, "batcher: max_batch and k must be positive");
-  if (k > MGPU_NCAND) return mgpu_fail(ivf->ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported yet", k, MGPU_NCAND);
+  if (k > MGPU_MAX_K) return mgpu_fail(ivf->ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported", k, MGPU_MAX_K);
   if (nprobe == 0 || nprobe > ivf->nlist) return mgpu_fail(ivf->ctx, MGPU_ERR_OUT_OF_RANGE, "num_probes %u out of range 1..%u (the reference panics)", nprobe, ivf->nlist);
   mgpu_batcher *b = new mgpu_batcher();
   b->ivf = ivf; b->max_batch = max_batch; b->max_wait_us = max_wait_us; b->k = k; b->nprobe = nprobe; b->dim = ivf->dim;
@@ -145,7 +145,7 @@ int mgpu_batcher_create_spann(mgpu_spann *sp, uint32_t max_batch, uint32_t max_w
   if (!sp || !out) return MGPU_ERR_INVALID_ARG;
   *out = nullptr;
   if (max_batch == 0 || top_k == 0) return mgpu_fail(sp->ctx, MGPU_ERR_INVALID_ARG, "batcher: max_batch and top_k must be positive");
-  if (top_k > MGPU_NCAND) return mgpu_fail(sp->ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported yet", top_k, MGPU_NCAND);
+  if (top_k > MGPU_MAX_K) return mgpu_fail(sp->ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported", top_k, MGPU_MAX_K);
   mgpu_batcher *b = new mgpu_batcher();
   b->spann = sp; b->max_batch = max_batch; b->max_wait_us = max_wait_us; b->k = top_k; b->ef = ef; b->nexp = num_explored_centroids;
   b->ratio = centroid_distance_ratio; b->dim = sp->lists->dim; b->words = (sp->lists->n + 31) / 32;

@@ -644,3 +644,21 @@ def test_k_above_limit_is_rejected(M):
     givf = M.BlockBasedIvf(cents, offsets, ids, X, M.NoQuantizer(32))
     with pytest.raises(M.Unsupported):
         givf.search_batch(X[:4], 5000, 2)
+
+
+def test_micro_batcher_large_k(M):
+    """The per-request front door accepts k > 32 as well (multi-round top-k behind it)."""
+    X = synth.clustered(2500, 64, n_blobs=6, seed=41)
+    cents = O.kmeans(X, 10, iters=4, seed=1)
+    offsets, ids = O.build_posting_lists(X, cents)
+    oivf = O.Ivf(cents, offsets, ids, X)
+    givf = M.BlockBasedIvf(cents, offsets, ids, X, M.NoQuantizer(64))
+    mb = M.MicroBatcher(givf, k=40, num_probes=4, max_batch=8, max_wait_us=1000)
+    Q = (X[:5] + 0.01).astype(np.float32)
+    for i in range(len(Q)):
+        r = mb.search(Q[i])
+        od, os_, oc = oivf.search_batch(Q[i:i + 1], 40, 4)
+        n = int(oc[0])
+        assert [x.doc_id for x in r.id_with_scores] == [int(lo) | (int(hi) << 64) for lo, hi in od[0, :n]], i
+        assert _same_f32(np.array([x.score for x in r.id_with_scores], dtype=np.float32), os_[0, :n])
+    mb.close()
