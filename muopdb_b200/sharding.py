@@ -23,6 +23,15 @@ def split_probes(nprobe: int, nlist: int, world: int):
     return max(nlist // world, 1), max(nprobe // world, 1)
 
 
+def encode_slice(B: int, world: int, rank: int):
+    """Queries rank `rank` encodes when the codebook is shared (mgpu_shard_ivf_search, api.cu): (first, count).  Every rank
+    all-gathers ceil(B / world) code rows, so rank r's slice starts at r * ceil(B / world); the last slices may be short or
+    empty when B is not a multiple of the world size."""
+    per = (B + world - 1) // world
+    lo = min(B, rank * per)
+    return lo, min(B, lo + per) - lo
+
+
 def init_comm(ctx, dist=None):
     """Create the NCCL communicator of `ctx` across the torch.distributed world (any backend is fine for the
     rendezvous)."""

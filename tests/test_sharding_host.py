@@ -75,3 +75,18 @@ def test_shard_helpers():
     assert sharding.split_probes(64, 4096, 1) == (4096, 64)
     lo = np.arange(10, dtype=np.uint64)
     assert sharding.shard_of(lo, 4).tolist() == [0, 1, 2, 3, 0, 1, 2, 3, 0, 1]
+
+
+def test_encode_slices_tile_the_batch():
+    """Split query encode of the sharded search: the ranks' slices are disjoint, ordered and cover the batch, with the gathered
+    buffer holding query q at row q (slices are ceil(B / world) apart)."""
+    from muopdb_b200 import sharding
+    for B in (0, 1, 7, 203, 1024, 8192):
+        for world in (1, 2, 3, 8):
+            per = (B + world - 1) // world
+            covered = []
+            for r in range(world):
+                lo, cnt = sharding.encode_slice(B, world, r)
+                assert lo == min(B, r * per) and 0 <= cnt <= per
+                covered.extend(range(lo, lo + cnt))
+            assert covered == list(range(B)), (B, world)
