@@ -474,7 +474,7 @@ k_coarse_select_q(const float *__restrict__ Dt, const float *__restrict__ Q, con
   // ---- the row, one burst; every thread converts the pieces it fetched itself (no barrier needed in between)
   for (uint32_t i = tid; i < C4; i += SELQ_THREADS) selw_cp_async16((uint4 *)keys + i, row4 + i);
   for (int i = tid; i < SELW_BINS / 4; i += SELQ_THREADS) ((uint4 *)hist)[i] = make_uint4(0, 0, 0, 0);
-  if (tid == 0) { misc[0] = 0; misc[1] = 0; misc[3] = nprobe - 1; misc[8] = 0xFFFFFFFFu; misc[9] = 0u; misc[10] = 0u; }
+  if (tid == 0) { misc[0] = 0; misc[1] = 0; misc[3] = nprobe - 1; misc[8] = 0xFFFFFFFFu; misc[9] = 0u; misc[10] = 0u; misc[11] = 0u; }
   selw_cp_async_wait();
   uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
 #pragma unroll 4
@@ -485,28 +485,28 @@ k_coarse_select_q(const float *__restrict__ Dt, const float *__restrict__ Q, con
     kmin = min(min(kmin, k4.x), min(k4.y, min(k4.z, k4.w)));
     kmax = max(max(kmax, k4.x), max(k4.y, max(k4.z, k4.w)));
   }
-  // Pre-filter: the nprobe-th smallest of the 128 per-thread minima is an upper bound T of tau (nprobe distinct keys are
-  // <= it), and only ~2 % of the keys are <= T.  The histogram passes below then touch ~100 keys instead of all C with
-  // shared-memory atomics (2 cycles per lane: 4096 of them per query and 7 queries per SM were 2/3 of this kernel's time).
-  const uint32_t tmin = kmin;
-  uint32_t *tmins = cand;  // SELW_CAP >= SELQ_THREADS words, free until the classification
-  tmins[tid] = tmin;
+  // Pre-filter: every warp sorts its 32 per-thread minima (shuffle bitonic network) and takes the ceil(nprobe/4)-th smallest;
+  // the maximum of the four is an upper bound T of tau (4 x ceil(nprobe/4) >= nprobe distinct keys are <= it), and only a few
+  // percent of the keys are <= T.  The histogram passes below then touch ~100 keys instead of all C with shared-memory
+  // atomics (2 cycles per lane each).
+  uint32_t tsort = kmin;
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      const uint32_t other = __shfl_xor_sync(0xffffffffu, tsort, j);
+      const bool up = (lane & k2) == 0, lower = (lane & j) == 0;
+      tsort = (lower == up) ? min(tsort, other) : max(tsort, other);
+    }
+  }
+  const uint32_t twarp = __shfl_sync(0xffffffffu, tsort, (int)min((nprobe + 3) / 4, 32u) - 1);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
     kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
   }
-  __syncthreads();  // misc / hist initialised, tmins published
-  if (lane == 0) { atomicMin(&misc[8], kmin); atomicMax(&misc[9], kmax); }
-  if (nprobe <= SELQ_THREADS) {
-    uint32_t r = 0;
-#pragma unroll 8
-    for (int j = 0; j < SELQ_THREADS; j++) {
-      const uint32_t o = tmins[j];
-      r += (o < tmin || (o == tmin && j < tid)) ? 1u : 0u;
-    }
-    if (r == nprobe - 1) misc[11] = tmin;   // exactly one thread
-  }
+  __syncthreads();  // misc / hist initialised
+  if (lane == 0) { atomicMin(&misc[8], kmin); atomicMax(&misc[9], kmax); atomicMax(&misc[11], twarp); }
   __syncthreads();
   // ---- two histogram levels over [kmin, T]: the key interval [lo_key, hi_key] of width range / 2^20 holding tau
   uint32_t base = misc[8];
