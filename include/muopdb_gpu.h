@@ -77,6 +77,12 @@ const char *mgpu_last_error(mgpu_ctx *ctx);
 const char *mgpu_version(void);
 int mgpu_sync(mgpu_ctx *ctx);                    /* wait for everything enqueued on the ctx stream */
 void *mgpu_stream(mgpu_ctx *ctx);                /* the cudaStream_t all kernels of this ctx run on */
+/* The ctx stream is created non-blocking: it is NOT ordered against the legacy default stream or any other stream.  A caller
+ * that produces MGPU_DEVICE inputs (or pre-fills outputs) on its own stream orders them with mgpu_stream_wait (ctx stream waits
+ * for the work enqueued on `other` so far) and consumes results with mgpu_stream_signal (`other` waits for the work enqueued on
+ * the ctx streams so far) -- or simply calls mgpu_sync.  `other` is a cudaStream_t (NULL = legacy default stream). */
+int mgpu_stream_wait(mgpu_ctx *ctx, void *other);
+int mgpu_stream_signal(mgpu_ctx *ctx, void *other);
 int mgpu_device_sm_count(mgpu_ctx *ctx);
 
 /* CUDA-event timing on the ctx stream (bench.py times device work with these). */
@@ -97,6 +103,13 @@ uint64_t mgpu_launch_count(mgpu_ctx *ctx);       /* kernels launched by this ctx
 int mgpu_distance_batch(mgpu_ctx *ctx, const float *A, uint64_t nA, const float *B, uint64_t nB, uint32_t dim,
                         int metric, int squared, float *out, int mem);
 
+/* LaneConformingDistanceCalculator<LANES, D>::calculate_squared (rs/utils/src/distance/lane_conforming.rs:16-27), all pairs:
+ * LANES accumulators over the whole vector (dim % lanes == 0, lanes in {1,2,4,8,16}), one ordered reduce_sum, then
+ * D::outermost_op (L2: identity => squared distance; dot: negation).  Equals mgpu_distance_batch(squared) when dim % 16 == 0
+ * and lanes == 16, differs in summation order otherwise.  k-means picks it by dimension (kmeans_builder.rs:126-136). */
+int mgpu_distance_batch_lanes(mgpu_ctx *ctx, const float *A, uint64_t nA, const float *B, uint64_t nB, uint32_t dim, int metric,
+                              int lanes, float *out, int mem);
+
 /* ---- ProductQuantizer (rs/quantization/src/pq/mod.rs:23-286, Quantizer trait quantization.rs:6-38) */
 /* codebook: m * 2^nbits * dsub floats laid out [subspace][centroid][dsub] (pq/mod.rs:155-167), host memory. */
 int mgpu_pq_create(mgpu_ctx *ctx, uint32_t dim, uint32_t dsub, uint32_t nbits, const float *codebook, int metric,
@@ -106,6 +119,10 @@ void mgpu_pq_destroy(mgpu_pq *pq);
 int mgpu_pq_quantize_batch(mgpu_pq *pq, const float *X, uint64_t n, uint8_t *codes, int mem);
 /* Quantizer::distance(a[i], b[i], StreamingSIMD) for n code-word pairs (pq/mod.rs:231-266). */
 int mgpu_pq_distance_batch(mgpu_pq *pq, const uint8_t *a, const uint8_t *b, uint64_t n, float *out, int mem);
+
+/* ProductQuantizer::original_vector (pq/mod.rs:184-200) for n code words: out[i] = concatenation of the codebook centroids the
+ * code word names (n x dim floats). */
+int mgpu_pq_original_vector(mgpu_pq *pq, const uint8_t *codes, uint64_t n, float *out, int mem);
 
 /* ---- BlockBasedIvf<Q> (rs/index/src/ivf/block_based/index.rs:22-471) ---------------------- */
 /* Arrays are what BlockBasedIvf::new reads from `index` + `vectors` (ivf/writer.rs:300-353):
@@ -125,6 +142,20 @@ uint32_t mgpu_ivf_num_clusters(mgpu_ivf *ivf); /* index.rs:334-336 */
 /* invalidate_batch by point id (index.rs:430-471 family): skipped before any distance work (index.rs:198-200). */
 int mgpu_ivf_invalidate(mgpu_ivf *ivf, const uint32_t *point_ids, uint32_t n);
 int mgpu_ivf_is_invalidated(mgpu_ivf *ivf, uint32_t point_id, int *out);
+
+/* The reference's doc-id keyed forms.  invalidate / invalidate_batch (index.rs:417-452): doc id -> point id through
+ * doc_id_to_point_id (built in point-id order, a repeated doc id keeps its last point: index.rs:67-73); unknown doc ids are
+ * skipped; out_ok[i] (may be NULL) = 1 when doc_ids[i] was newly invalidated, *out_num_ok (may be NULL) their number.
+ * is_invalidated(doc_id) (index.rs:454-459): unknown doc ids report 0.  HOST pointers. */
+int mgpu_ivf_invalidate_docs(mgpu_ivf *ivf, const mgpu_u128 *doc_ids, uint32_t n, uint8_t *out_ok, uint32_t *out_num_ok);
+int mgpu_ivf_is_doc_invalidated(mgpu_ivf *ivf, const mgpu_u128 *doc_id, int *out);
+/* get_point_id (index.rs:469-471): *found = 0 encodes None. */
+int mgpu_ivf_get_point_id(mgpu_ivf *ivf, const mgpu_u128 *doc_id, int *found, uint32_t *point_id);
+/* get_doc_id / get_doc_ids (index.rs:350-366): doc ids of n point ids in input order; an id >= num_vectors is an error. */
+int mgpu_ivf_get_doc_ids(mgpu_ivf *ivf, const uint32_t *point_ids, uint32_t n, mgpu_u128 *out_doc_ids);
+/* get_vector (index.rs:372-384) for n point ids: the stored rows, n x quantized_dimension of u8 (PQ) or f32 (NoQuantizer),
+ * read back out of the HBM scan layout. */
+int mgpu_ivf_get_vectors(mgpu_ivf *ivf, const uint32_t *point_ids, uint32_t n, void *out_rows);
 
 /* find_nearest_centroids (index.rs:147-163) for B queries: the nprobe smallest sqrt-L2 centroid distances,
  * nearest first, ties by centroid index.  out_ids: B x nprobe; out_dist (may be NULL): B x nprobe. */
@@ -172,6 +203,14 @@ uint64_t mgpu_ivf_last_scan_rows(mgpu_ivf *ivf);
  * out_cids: n x max_clusters (UINT32_MAX padded), out_counts: n. */
 int mgpu_ivf_assign(mgpu_ctx *ctx, const float *X, uint64_t n, const float *centroids, uint32_t nlist, uint32_t dim,
                     uint32_t max_clusters, float threshold, uint32_t *out_cids, uint32_t *out_counts, int mem);
+
+/* Assignment step of KMeansBuilder::run_lloyd (rs/utils/src/kmeans_builder/kmeans_builder.rs:199-221): per row of X
+ * argmin_c (T::calculate_squared(x, c) + penalties[c]), folded from (0, f32::MAX) with a strict '<' (first minimum wins).
+ * T follows the dimension as in kmeans_builder.rs:126-136: LaneConforming<16|8|4, D> for dim % 16|8|4 == 0, else D.
+ * penalties: nlist floats or NULL (= 0); out_labels: n; out_costs (may be NULL): n winning costs (distance + penalty).
+ * Large L2 problems run the tensor-core estimate + exact re-score of the band (same labels and costs, bit for bit). */
+int mgpu_kmeans_assign(mgpu_ctx *ctx, const float *X, uint64_t n, const float *centroids, uint32_t nlist, uint32_t dim, int metric,
+                       const float *penalties, uint32_t *out_labels, float *out_costs, int mem);
 
 /* ---- BlockBasedHnsw<Q> (rs/index/src/hnsw/block_based/index.rs:55-298) --------------------- */
 /* Graph arrays exactly as in the `hnsw/index` file (hnsw/block_based/graph_storage.rs:122-193):
@@ -247,6 +286,26 @@ int mgpu_shard_ivf_search(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k,
 int mgpu_shard_ivf_search_submit(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, int shared_codebook,
                                  mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, uint64_t *ticket);
 
+/* The result exchange of the sharded calls (all-gather + merge) runs on its own stream (and communicator), so in the pipelined
+ * *_submit forms batch i's exchange always overlaps batch i+1's kernels.  For DEVICE buffers the default keeps the ctx stream
+ * ordered after the exchange (work enqueued on mgpu_stream() afterwards sees the merged result).  on != 0 drops that wait:
+ * consecutive sharded calls then overlap the same way, and results are complete after mgpu_sync (which waits for both
+ * streams) -- the caller must not reuse an output buffer before that. */
+int mgpu_shard_overlap(mgpu_ctx *ctx, int on);
+
+/* Config 5: every rank holds the SPANN index of one doc-shard (centroid HNSW + posting lists), all ranks pass
+ * the same replicated batch; per rank Spann::search (spann/index.rs:211-266), then the per-shard results are all-gathered over
+ * NVLink and merged by (score, doc_id) (collection/snapshot.rs:49-63; fan-out model rs/aggregator/src/aggregator.rs:81-132).
+ * A shard that answers None (out_counts == UINT32_MAX) contributes nothing; the merged count is UINT32_MAX only if every shard
+ * answered None.  shared_codebook as in mgpu_shard_ivf_search.  Collective; buffers in `mem` space. */
+int mgpu_shard_spann_search(mgpu_spann *s, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef, uint32_t num_explored_centroids,
+                            float centroid_distance_ratio, int shared_codebook, mgpu_u128 *out_doc_ids, float *out_scores,
+                            uint32_t *out_counts, int mem);
+/* Pipelined form over page-locked HOST buffers (ticket completed by mgpu_search_wait), as mgpu_shard_ivf_search_submit. */
+int mgpu_shard_spann_search_submit(mgpu_spann *s, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef,
+                                   uint32_t num_explored_centroids, float centroid_distance_ratio, int shared_codebook,
+                                   mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, uint64_t *ticket);
+
 /* ---- Readers of the reference's on-disk formats -------------- */
 /* One Elias-Fano posting-list payload (rs/compression/src/elias_fano/ef.rs:197-215; decode rule
  * block_based_decoder.rs:162-179,257-266) -> ascending values.  Host-only (no device needed).
@@ -263,6 +322,31 @@ int mgpu_ivf_load(mgpu_ctx *ctx, const char *base_dir, uint64_t index_offset, ui
  * `{base}/hnsw/vector_storage` (hnsw/writer.rs:206-265, graph_storage.rs:122-193).  dim = original dimension. */
 int mgpu_hnsw_load(mgpu_ctx *ctx, const char *base_dir, uint64_t index_offset, uint64_t vector_offset, uint32_t dim, int quant,
                    int metric, mgpu_pq *pq, mgpu_hnsw **out);
+/* Multi-user SPANN files (rs/index/src/multi_spann/{writer,reader,index}.rs): all users' sections are packed into
+ * {base}/centroids/hnsw/{index,vector_storage} and {base}/ivf/{index,vectors,raw_vectors,quantizer/codebook}; the file
+ * {base}/user_index_info maps user id -> byte offsets (UserIndexInfo, multi_spann/user_index_info.rs:4-14). */
+typedef struct {
+  mgpu_u128 user_id;
+  uint64_t centroid_vector_offset, centroid_vector_len, centroid_index_offset, centroid_index_len;
+  uint64_t ivf_vectors_offset, ivf_vectors_len, ivf_raw_vectors_offset, ivf_raw_vectors_len;
+  uint64_t ivf_index_offset, ivf_index_len, ivf_pq_codebook_offset, ivf_pq_codebook_len;
+} mgpu_user_index_info;
+/* UserIndexInfo::from_le_bytes / to_le_bytes (user_index_info.rs:26-83): the 112-byte record. */
+int mgpu_user_index_info_decode(const uint8_t bytes[112], mgpu_user_index_info *out);
+int mgpu_user_index_info_encode(const mgpu_user_index_info *info, uint8_t out_bytes[112]);
+/* Every record of a `user_index_info` table file (an odht 0.3.1 HashTableOwned<HashConfig> image: 32-byte header, slot_count
+ * entries of 16-byte key + 112-byte value, then slot_count + 16 control bytes whose top bit marks an empty slot).  odht is a
+ * third-party crate absent from the reference checkout: its layout is restated from the published format and checked by the
+ * header's own item count and by key == value.user_id.  Returns the number of records (up to `cap` are stored), -1 on
+ * malformed input. */
+int64_t mgpu_user_index_info_read(const char *path, mgpu_user_index_info *out, uint64_t cap);
+/* MultiSpannIndex::get_or_create_index (multi_spann/index.rs:100-128) -> SpannReader::new_with_offsets(...).read
+ * (spann/reader.rs:43-82): opens one user's centroid HNSW (NoQuantizer<L2>) and posting lists at the recorded offsets.
+ * quant == MGPU_QUANT_PQ reads {base}/ivf/quantizer/product_quantizer_config.yaml and the user's slice of `codebook`
+ * (ivf_pq_codebook_offset/len); *out_pq then owns that quantizer (NULL otherwise).  Free with mgpu_spann_destroy,
+ * mgpu_ivf_destroy, mgpu_hnsw_destroy, mgpu_pq_destroy. */
+int mgpu_spann_load_user(mgpu_ctx *ctx, const char *base_dir, const mgpu_user_index_info *info, uint32_t dim, int quant, int metric,
+                         mgpu_pq **out_pq, mgpu_hnsw **out_centroids, mgpu_ivf **out_lists, mgpu_spann **out_spann);
 /* sizes = {num_layers, n_edges, n_points, n_edge_offsets, n, entry_point}; copy_graph reads the resident arrays back. */
 int mgpu_hnsw_info(mgpu_hnsw *h, uint64_t sizes[6]);
 int mgpu_hnsw_copy_graph(mgpu_hnsw *h, uint32_t *edges, uint32_t *points, uint64_t *edge_offsets, uint64_t *level_offsets);

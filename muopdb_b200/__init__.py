@@ -29,7 +29,8 @@ from . import _lib
 from ._lib import (DEVICE, DOT, HOST, L2, QUANT_NONE, QUANT_PQ, InvalidArgument, MuopdbGpuError, NoDevice, OutOfRange,
                    Unsupported)
 
-__all__ = ["Context", "default_context", "L2DistanceCalculator", "DotProductDistanceCalculator", "NoQuantizer",
+__all__ = ["Context", "default_context", "L2DistanceCalculator", "DotProductDistanceCalculator",
+           "LaneConformingDistanceCalculator", "kmeans_assign", "UserIndexInfo", "MultiSpannIndex", "NoQuantizer",
            "ProductQuantizer", "BlockBasedIvf", "BlockBasedHnsw", "Spann", "SearchParams", "IdWithScore", "SearchResult",
            "Planner", "MicroBatcher", "merge_topk", "assign_to_centroids", "elias_fano_decode", "L2", "DOT", "MuopdbGpuError", "OutOfRange", "InvalidArgument", "Unsupported",
            "NoDevice"]
@@ -123,6 +124,15 @@ class Context:
     def sync(self):
         _lib.check(self.lib.mgpu_sync(self.h), self.h)
 
+    def order(self, mem):
+        """Context manager around one C-ABI call with DEVICE buffers: the library stream is non-blocking, so torch's current
+        stream and the library stream are ordered explicitly -- before the call the library stream waits for torch's stream
+        (inputs computed by earlier torch ops, the zero-fill of freshly allocated outputs), after it torch's stream waits for
+        the library streams (so `.cpu()`, indexing, ... see the results).  No-op for host buffers and when torch's current
+        stream IS the library stream.  With shard_overlap(True) the trailing wait is skipped (it would chain consecutive
+        sharded calls through torch's stream); results are then complete after sync()."""
+        return _StreamOrder(self, mem == DEVICE)
+
     @property
     def sm_count(self) -> int:
         return self.lib.mgpu_device_sm_count(self.h)
@@ -166,11 +176,38 @@ class Context:
         _lib.check(_lib.load().mgpu_comm_unique_id(C.addressof(buf)))
         return bytes(buf)
 
+    _overlap = False
+
+    def shard_overlap(self, on: bool = True):
+        """mgpu_shard_overlap: device-buffer sharded calls return with their result exchange still in flight on the
+        exchange stream (the next batch's kernels run next to it); `sync()` completes both streams."""
+        _lib.check(self.lib.mgpu_shard_overlap(self.h, int(bool(on))), self.h)
+        self._overlap = bool(on)
+
     def shard_allgather_merge(self, local_doc_ids, local_scores, local_counts, B, k, out_doc_ids, out_scores, out_counts):
         """All device tensors: doc ids (B,k,2) int64, scores (B,k) f32, counts (B,) int32."""
         _lib.check(self.lib.mgpu_shard_allgather_merge(self.h, local_doc_ids.data_ptr(), local_scores.data_ptr(),
                                                        local_counts.data_ptr(), B, k, out_doc_ids.data_ptr(),
                                                        out_scores.data_ptr(), out_counts.data_ptr()), self.h)
+
+
+class _StreamOrder:
+    def __init__(self, ctx, active):
+        self.ctx, self.active, self.stream = ctx, active, None
+
+    def __enter__(self):
+        if self.active:
+            import torch
+            st = torch.cuda.current_stream(self.ctx.device).cuda_stream
+            if st != (self.ctx.stream or 0):
+                self.stream = st
+                _lib.check(self.ctx.lib.mgpu_stream_wait(self.ctx.h, st), self.ctx.h)
+        return self
+
+    def __exit__(self, et, ev, tb):
+        if self.active and self.stream is not None and et is None and not self.ctx._overlap:
+            _lib.check(self.ctx.lib.mgpu_stream_signal(self.ctx.h, self.stream), self.ctx.h)
+        return False
 
 
 _default_ctx = {}
@@ -204,7 +241,8 @@ class _DistanceCalculator:
         else:
             out = np.empty((nA, nB), dtype=np.float32)
             optr = out.ctypes.data
-        _lib.check(ctx.lib.mgpu_distance_batch(ctx.h, a.ptr, nA, b.ptr, nB, dim, cls.METRIC, int(squared), optr, a.mem), ctx.h)
+        with ctx.order(a.mem):
+            _lib.check(ctx.lib.mgpu_distance_batch(ctx.h, a.ptr, nA, b.ptr, nB, dim, cls.METRIC, int(squared), optr, a.mem), ctx.h)
         return out
 
     @classmethod
@@ -230,6 +268,63 @@ class L2DistanceCalculator(_DistanceCalculator):
 class DotProductDistanceCalculator(_DistanceCalculator):
     """rs/utils/src/distance/dot_product.rs:7-99 (negated dot; calculate_squared forwards to calculate)"""
     METRIC = DOT
+
+
+class LaneConformingDistanceCalculator:
+    """rs/utils/src/distance/lane_conforming.rs:9-28: LaneConformingDistanceCalculator<LANES, D> -- only CalculateSquared;
+    the dimension must be a multiple of LANES."""
+
+    def __init__(self, lanes: int, distance=L2DistanceCalculator):
+        self.lanes, self.calculator, self.METRIC = lanes, distance, distance.METRIC
+
+    def calculate_squared_batch(self, A, B, ctx: Optional[Context] = None):
+        ctx = ctx or default_context()
+        a, b = _Buf(A, np.float32), _Buf(B, np.float32)
+        if len(a.shape) != 2 or len(b.shape) != 2 or a.shape[1] != b.shape[1] or a.mem != b.mem:
+            raise InvalidArgument(_lib.ERR_INVALID_ARG, "calculate_squared_batch expects (nA, dim) and (nB, dim) in one memory space")
+        nA, dim = a.shape
+        nB = b.shape[0]
+        if a.mem == DEVICE:
+            import torch
+            out = torch.empty((nA, nB), dtype=torch.float32, device=A.device)
+            optr = out.data_ptr()
+        else:
+            out = np.empty((nA, nB), dtype=np.float32)
+            optr = out.ctypes.data
+        with ctx.order(a.mem):
+            _lib.check(ctx.lib.mgpu_distance_batch_lanes(ctx.h, a.ptr, nA, b.ptr, nB, dim, self.METRIC, self.lanes, optr, a.mem), ctx.h)
+        return out
+
+    def calculate_squared(self, a, b) -> float:
+        a = np.asarray(a, dtype=np.float32).reshape(1, -1)
+        b = np.asarray(b, dtype=np.float32).reshape(1, -1)
+        return float(self.calculate_squared_batch(a, b)[0, 0])
+
+
+def kmeans_assign(X, centroids, penalties=None, distance=L2DistanceCalculator, with_costs=False, ctx: Optional[Context] = None):
+    """Assignment step of KMeansBuilder::run_lloyd (rs/utils/src/kmeans_builder/kmeans_builder.rs:199-221): per row the first
+    minimum of T::calculate_squared(x, c) + penalties[c], T chosen by the dimension (kmeans_builder.rs:126-136).
+    -> labels (n,) [, costs (n,)]"""
+    ctx = ctx or default_context()
+    x, c = _Buf(X, np.float32), _Buf(centroids, np.float32)
+    p = _Buf(penalties, np.float32, allow_none=True)
+    if x.mem != c.mem or (p.mem is not None and p.mem != x.mem):
+        raise InvalidArgument(_lib.ERR_INVALID_ARG, "X, centroids and penalties must live in the same memory space")
+    n, dim = x.shape
+    if c.shape[1] != dim or (p.ptr is not None and p.shape[0] != c.shape[0]):
+        raise InvalidArgument(_lib.ERR_INVALID_ARG, "shape mismatch")
+    if x.mem == DEVICE:
+        import torch
+        labels = torch.zeros((n,), dtype=torch.int32, device=X.device)
+        costs = torch.zeros((n,), dtype=torch.float32, device=X.device)
+        lp, cp = labels.data_ptr(), costs.data_ptr()
+    else:
+        labels = np.zeros((n,), dtype=np.uint32)
+        costs = np.zeros((n,), dtype=np.float32)
+        lp, cp = labels.ctypes.data, costs.ctypes.data
+    with ctx.order(x.mem):
+        _lib.check(ctx.lib.mgpu_kmeans_assign(ctx.h, x.ptr, n, c.ptr, c.shape[0], dim, distance.METRIC, p.ptr, lp, cp, x.mem), ctx.h)
+    return (labels, costs) if with_costs else labels
 
 
 # ---- Quantizers (rs/quantization/src/quantization.rs:6-38) ----------------------------------------------------------------
@@ -318,14 +413,25 @@ class ProductQuantizer:
         else:
             out = np.empty((n, m), dtype=np.uint8)
             optr = out.ctypes.data
-        _lib.check(self.ctx.lib.mgpu_pq_quantize_batch(self.handle, x.ptr, n, optr, x.mem), self.ctx.h)
+        with self.ctx.order(x.mem):
+            _lib.check(self.ctx.lib.mgpu_pq_quantize_batch(self.handle, x.ptr, n, optr, x.mem), self.ctx.h)
         return out[0] if single else out
 
     def original_vector(self, quantized):
-        """pq/mod.rs:184-200 -- a gather from the codebook (no arithmetic)."""
-        q = np.asarray(quantized, dtype=np.uint8)
-        cb = self.codebook.reshape(self.quantized_dimension(), 1 << self.num_bits, self.subvector_dimension)
-        return cb[np.arange(q.size), q].reshape(-1).copy()
+        """pq/mod.rs:184-200 -- the codebook centroids a code word names; one code word (m,) or a batch (n, m)."""
+        single = (not _is_torch(quantized)) and np.ndim(quantized) == 1
+        q = _Buf(np.asarray(quantized, dtype=np.uint8).reshape(1, -1) if single else quantized, np.uint8, (None, self.quantized_dimension()))
+        n = q.shape[0]
+        if q.mem == DEVICE:
+            import torch
+            out = torch.empty((n, self.dimension), dtype=torch.float32, device=quantized.device)
+            optr = out.data_ptr()
+        else:
+            out = np.empty((n, self.dimension), dtype=np.float32)
+            optr = out.ctypes.data
+        with self.ctx.order(q.mem):
+            _lib.check(self.ctx.lib.mgpu_pq_original_vector(self.handle, q.ptr, n, optr, q.mem), self.ctx.h)
+        return out[0] if single else out
 
     def distance(self, a, b):
         """Quantizer::distance(a, b, StreamingSIMD); a and b are code words (m,) or batches (n, m) -> (n,)."""
@@ -468,10 +574,11 @@ class BlockBasedIvf:
         if docs is not None and docs.shape[0] != n:
             raise InvalidArgument(_lib.ERR_INVALID_ARG, "doc_ids must have one entry per row")
         h = C.c_void_p()
-        _lib.check(self.ctx.lib.mgpu_ivf_create(self.ctx.h, self.dim, self.nlist, cent.ctypes.data, lo.ctypes.data,
-                                                ids.ctypes.data if ids.size else None, quantizer.QUANT, quantizer.metric,
-                                                quantizer.handle, r.ptr, r.mem, n,
-                                                docs.ctypes.data if docs is not None else None, C.byref(h)), self.ctx.h)
+        with self.ctx.order(r.mem):
+            _lib.check(self.ctx.lib.mgpu_ivf_create(self.ctx.h, self.dim, self.nlist, cent.ctypes.data, lo.ctypes.data,
+                                                    ids.ctypes.data if ids.size else None, quantizer.QUANT, quantizer.metric,
+                                                    quantizer.handle, r.ptr, r.mem, n,
+                                                    docs.ctypes.data if docs is not None else None, C.byref(h)), self.ctx.h)
         self.handle = h
 
     def __del__(self):
@@ -502,17 +609,64 @@ class BlockBasedIvf:
     def num_vectors(self) -> int:
         return int(self.ctx.lib.mgpu_ivf_num_vectors(self.handle))
 
-    def invalidate_batch(self, point_ids: Sequence[int]):
+    # -- invalidation.  The reference's methods are keyed by DOC id (index.rs:417-459); the scan tests point ids.
+    def invalidate_points(self, point_ids: Sequence[int]):
+        """invalid_point_ids.insert for a batch of point ids (what invalidate does after resolving the doc id)."""
         a = np.ascontiguousarray(point_ids, dtype=np.uint32)
         _lib.check(self.ctx.lib.mgpu_ivf_invalidate(self.handle, a.ctypes.data, a.size), self.ctx.h)
 
-    def invalidate(self, point_id: int):
-        self.invalidate_batch([point_id])
-
-    def is_invalidated(self, point_id: int) -> bool:
+    def is_point_invalidated(self, point_id: int) -> bool:
         o = C.c_int()
         _lib.check(self.ctx.lib.mgpu_ivf_is_invalidated(self.handle, point_id, C.byref(o)), self.ctx.h)
         return bool(o.value)
+
+    def invalidate_batch(self, doc_ids) -> list:
+        """index.rs:439-452: -> the doc ids that were successfully (newly) invalidated, in input order."""
+        d = _ints_to_pairs(list(doc_ids) if not isinstance(doc_ids, np.ndarray) else doc_ids)
+        n = d.shape[0]
+        ok = np.zeros(max(n, 1), dtype=np.uint8)
+        num = C.c_uint32()
+        _lib.check(self.ctx.lib.mgpu_ivf_invalidate_docs(self.handle, d.ctypes.data, n, ok.ctypes.data, C.byref(num)), self.ctx.h)
+        ints = _pairs_to_ints(d)
+        return [ints[i] for i in range(n) if ok[i]]
+
+    def invalidate(self, doc_id: int) -> bool:
+        """index.rs:417-429: true if the document was found and newly marked invalid."""
+        return len(self.invalidate_batch([int(doc_id)])) == 1
+
+    def is_invalidated(self, doc_id: int) -> bool:
+        """index.rs:454-459"""
+        d = _ints_to_pairs([int(doc_id)])
+        o = C.c_int()
+        _lib.check(self.ctx.lib.mgpu_ivf_is_doc_invalidated(self.handle, d.ctypes.data, C.byref(o)), self.ctx.h)
+        return bool(o.value)
+
+    # -- accessors (index.rs:350-384,469-471)
+    def get_point_id(self, doc_id: int) -> Optional[int]:
+        d = _ints_to_pairs([int(doc_id)])
+        found, pid = C.c_int(), C.c_uint32()
+        _lib.check(self.ctx.lib.mgpu_ivf_get_point_id(self.handle, d.ctypes.data, C.byref(found), C.byref(pid)), self.ctx.h)
+        return int(pid.value) if found.value else None
+
+    def get_doc_ids(self, point_ids: Sequence[int]) -> list:
+        a = np.ascontiguousarray(point_ids, dtype=np.uint32)
+        out = np.zeros((max(a.size, 1), 2), dtype=np.uint64)
+        _lib.check(self.ctx.lib.mgpu_ivf_get_doc_ids(self.handle, a.ctypes.data, a.size, out.ctypes.data), self.ctx.h)
+        return _pairs_to_ints(out[:a.size])
+
+    def get_doc_id(self, point_id: int) -> int:
+        return self.get_doc_ids([point_id])[0]
+
+    def get_vectors(self, point_ids: Sequence[int]) -> np.ndarray:
+        a = np.ascontiguousarray(point_ids, dtype=np.uint32)
+        qd = self.quantizer.quantized_dimension()
+        out = np.zeros((max(a.size, 1), qd), dtype=np.uint8 if self.quantizer.QUANT == QUANT_PQ else np.float32)
+        _lib.check(self.ctx.lib.mgpu_ivf_get_vectors(self.handle, a.ctypes.data, a.size, out.ctypes.data), self.ctx.h)
+        return out[:a.size]
+
+    def get_vector(self, point_id: int) -> np.ndarray:
+        """index.rs:372-384: the stored (quantized) row of a point."""
+        return self.get_vectors([point_id])[0]
 
     # -- batched entry points
     def find_nearest_centroids_batch(self, Q, num_probes: int, with_distances=False):
@@ -528,7 +682,8 @@ class BlockBasedIvf:
             ids = np.zeros((B, p), dtype=np.uint32)
             ds = np.zeros((B, p), dtype=np.float32)
             ip, dp = ids.ctypes.data, ds.ctypes.data
-        _lib.check(self.ctx.lib.mgpu_ivf_coarse(self.handle, q.ptr, B, num_probes, ip, dp, q.mem), self.ctx.h)
+        with self.ctx.order(q.mem):
+            _lib.check(self.ctx.lib.mgpu_ivf_coarse(self.handle, q.ptr, B, num_probes, ip, dp, q.mem), self.ctx.h)
         return (ids, ds) if with_distances else ids
 
     def search_with_centroids_batch(self, Q, centroid_ids, k: int, counts=None, remap=True, planner=None):
@@ -545,13 +700,15 @@ class BlockBasedIvf:
             if not remap:
                 raise Unsupported(_lib.ERR_UNSUPPORTED, "the planner filter is only wired into the remapping search (index.rs:298-332)")
             fp, fstride, _keep = _filter_arg(planner, B, self.num_vectors(), Q if q.mem == DEVICE else None)
-            _lib.check(self.ctx.lib.mgpu_ivf_scan_remap_filtered(self.handle, q.ptr, B, pr.ptr, P, pc.ptr, k, fp, fstride, ip, sp, cp,
-                                                                 q.mem), self.ctx.h)
+            with self.ctx.order(q.mem):
+                _lib.check(self.ctx.lib.mgpu_ivf_scan_remap_filtered(self.handle, q.ptr, B, pr.ptr, P, pc.ptr, k, fp, fstride, ip, sp, cp,
+                                                                     q.mem), self.ctx.h)
             if _keep is not None and q.mem == DEVICE:
                 self.ctx.sync()  # the bitmap tensor must outlive the asynchronous scan
             return BatchResult(ids, scores, cnt)
         f = self.ctx.lib.mgpu_ivf_scan_remap if remap else self.ctx.lib.mgpu_ivf_scan
-        _lib.check(f(self.handle, q.ptr, B, pr.ptr, P, pc.ptr, k, ip, sp, cp, q.mem), self.ctx.h)
+        with self.ctx.order(q.mem):
+            _lib.check(f(self.handle, q.ptr, B, pr.ptr, P, pc.ptr, k, ip, sp, cp, q.mem), self.ctx.h)
         return BatchResult(ids, scores, cnt)
 
     def search_batch(self, Q, k: int, num_probes: int, out=None, planner=None) -> BatchResult:
@@ -566,12 +723,14 @@ class BlockBasedIvf:
             ip, sp, cp = (x.data_ptr() if _is_torch(x) else x.ctypes.data for x in out)
         if planner is not None:
             fp, fstride, _keep = _filter_arg(planner, B, self.num_vectors(), Q if q.mem == DEVICE else None)
-            _lib.check(self.ctx.lib.mgpu_ivf_search_filtered(self.handle, q.ptr, B, k, num_probes, fp, fstride, ip, sp, cp, q.mem),
-                       self.ctx.h)
+            with self.ctx.order(q.mem):
+                _lib.check(self.ctx.lib.mgpu_ivf_search_filtered(self.handle, q.ptr, B, k, num_probes, fp, fstride, ip, sp, cp, q.mem),
+                           self.ctx.h)
             if _keep is not None and q.mem == DEVICE:
                 self.ctx.sync()  # the bitmap tensor must outlive the asynchronous scan
             return BatchResult(ids, scores, cnt)
-        _lib.check(self.ctx.lib.mgpu_ivf_search(self.handle, q.ptr, B, k, num_probes, ip, sp, cp, q.mem), self.ctx.h)
+        with self.ctx.order(q.mem):
+            _lib.check(self.ctx.lib.mgpu_ivf_search(self.handle, q.ptr, B, k, num_probes, ip, sp, cp, q.mem), self.ctx.h)
         return BatchResult(ids, scores, cnt)
 
     def shard_search_batch(self, Q, k: int, num_probes: int, out=None, shared_codebook: bool = True) -> BatchResult:
@@ -584,8 +743,9 @@ class BlockBasedIvf:
         else:
             ids, scores, cnt = out
             ip, sp, cp = (x.data_ptr() if _is_torch(x) else x.ctypes.data for x in out)
-        _lib.check(self.ctx.lib.mgpu_shard_ivf_search(self.handle, q.ptr, B, k, num_probes, 1 if shared_codebook else 0, ip, sp, cp,
-                                                      q.mem), self.ctx.h)
+        with self.ctx.order(q.mem):
+            _lib.check(self.ctx.lib.mgpu_shard_ivf_search(self.handle, q.ptr, B, k, num_probes, 1 if shared_codebook else 0, ip, sp, cp,
+                                                          q.mem), self.ctx.h)
         return BatchResult(ids, scores, cnt)
 
     def shard_search_batch_submit(self, Q, k: int, num_probes: int, out, shared_codebook: bool = True) -> int:
@@ -666,11 +826,12 @@ class BlockBasedHnsw:
         self.dim = quantizer.dimension
         docs = _ints_to_pairs(doc_ids)
         h = C.c_void_p()
-        _lib.check(self.ctx.lib.mgpu_hnsw_create(self.ctx.h, self.dim, int(num_layers), e.ctypes.data if e.size else None,
-                                                 e.size, p.ctypes.data if p.size else None, p.size, eo.ctypes.data, eo.size,
-                                                 lo.ctypes.data, quantizer.QUANT, quantizer.metric, quantizer.handle, r.ptr,
-                                                 r.mem, n, docs.ctypes.data if docs is not None else None, C.byref(h)),
-                   self.ctx.h)
+        with self.ctx.order(r.mem):
+            _lib.check(self.ctx.lib.mgpu_hnsw_create(self.ctx.h, self.dim, int(num_layers), e.ctypes.data if e.size else None,
+                                                     e.size, p.ctypes.data if p.size else None, p.size, eo.ctypes.data, eo.size,
+                                                     lo.ctypes.data, quantizer.QUANT, quantizer.metric, quantizer.handle, r.ptr,
+                                                     r.mem, n, docs.ctypes.data if docs is not None else None, C.byref(h)),
+                       self.ctx.h)
         self.handle = h
 
     def __del__(self):
@@ -720,7 +881,8 @@ class BlockBasedHnsw:
             else:
                 stats = np.zeros((B, 2), dtype=np.uint64)
                 stp = stats.ctypes.data
-        _lib.check(self.ctx.lib.mgpu_hnsw_search(self.handle, q.ptr, B, k, ef, ip, sp, cp, stp, q.mem), self.ctx.h)
+        with self.ctx.order(q.mem):
+            _lib.check(self.ctx.lib.mgpu_hnsw_search(self.handle, q.ptr, B, k, ef, ip, sp, cp, stp, q.mem), self.ctx.h)
         r = BatchResult(ids, scores, cnt)
         return (r, stats) if with_stats else r
 
@@ -761,20 +923,191 @@ class Spann:
         ids, scores, cnt, ip, sp, cp = _alloc_out(B, params.top_k, Q if q.mem == DEVICE else None)
         if planner is not None:
             fp, fstride, _keep = _filter_arg(planner, B, self.posting_lists.num_vectors(), Q if q.mem == DEVICE else None)
-            _lib.check(self.ctx.lib.mgpu_spann_search_filtered(self.handle, q.ptr, B, params.top_k, params.ef_construction,
-                                                               params.explored(), float(params.centroid_distance_ratio), fp,
-                                                               fstride, ip, sp, cp, q.mem), self.ctx.h)
+            with self.ctx.order(q.mem):
+                _lib.check(self.ctx.lib.mgpu_spann_search_filtered(self.handle, q.ptr, B, params.top_k, params.ef_construction,
+                                                                   params.explored(), float(params.centroid_distance_ratio), fp,
+                                                                   fstride, ip, sp, cp, q.mem), self.ctx.h)
             if _keep is not None and q.mem == DEVICE:
                 self.ctx.sync()
             return BatchResult(ids, scores, cnt)
-        _lib.check(self.ctx.lib.mgpu_spann_search(self.handle, q.ptr, B, params.top_k, params.ef_construction,
-                                                  params.explored(), float(params.centroid_distance_ratio), ip, sp, cp,
-                                                  q.mem), self.ctx.h)
+        with self.ctx.order(q.mem):
+            _lib.check(self.ctx.lib.mgpu_spann_search(self.handle, q.ptr, B, params.top_k, params.ef_construction,
+                                                      params.explored(), float(params.centroid_distance_ratio), ip, sp, cp,
+                                                      q.mem), self.ctx.h)
         return BatchResult(ids, scores, cnt)
+
+    def shard_search_batch(self, Q, params: SearchParams, out=None, shared_codebook: bool = True) -> BatchResult:
+        """Config 5 (mgpu_shard_spann_search): Spann::search on this rank's doc-shard for the replicated batch Q, then the
+        all-gather + (score, doc_id) merge over the context's ranks.  Collective."""
+        q = _Buf(Q, np.float32, (None, self.posting_lists.dim))
+        B = q.shape[0]
+        if out is None:
+            ids, scores, cnt, ip, sp, cp = _alloc_out(B, params.top_k, Q if q.mem == DEVICE else None)
+        else:
+            ids, scores, cnt = out
+            ip, sp, cp = (x.data_ptr() if _is_torch(x) else x.ctypes.data for x in out)
+        with self.ctx.order(q.mem):
+            _lib.check(self.ctx.lib.mgpu_shard_spann_search(self.handle, q.ptr, B, params.top_k, params.ef_construction, params.explored(),
+                                                            float(params.centroid_distance_ratio), 1 if shared_codebook else 0, ip, sp, cp,
+                                                            q.mem), self.ctx.h)
+        return BatchResult(ids, scores, cnt)
+
+    def shard_search_batch_submit(self, Q, params: SearchParams, out, shared_codebook: bool = True) -> int:
+        """Pipelined form over page-locked HOST buffers; `search_wait(ticket)` completes it."""
+        q = _Buf(Q, np.float32, (None, self.posting_lists.dim))
+        if q.mem != HOST:
+            raise ValueError("shard_search_batch_submit takes host buffers")
+        ip, sp, cp = (x.data_ptr() if _is_torch(x) else x.ctypes.data for x in out)
+        t = C.c_uint64(0)
+        _lib.check(self.ctx.lib.mgpu_shard_spann_search_submit(self.handle, q.ptr, q.shape[0], params.top_k, params.ef_construction,
+                                                               params.explored(), float(params.centroid_distance_ratio),
+                                                               1 if shared_codebook else 0, ip, sp, cp, C.byref(t)), self.ctx.h)
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[t.value] = (Q, out)
+        return int(t.value)
+
+    def search_wait(self, ticket: int) -> None:
+        _lib.check(self.ctx.lib.mgpu_search_wait(self.ctx.h, ticket), self.ctx.h)
+        getattr(self, "_inflight", {}).pop(ticket, None)
+
+    def invalidate(self, doc_id: int) -> bool:
+        """spann/index.rs: Spann::invalidate forwards to the posting lists."""
+        return self.posting_lists.invalidate(doc_id)
+
+    def invalidate_batch(self, doc_ids) -> list:
+        return self.posting_lists.invalidate_batch(doc_ids)
+
+    def is_invalidated(self, doc_id: int) -> bool:
+        return self.posting_lists.is_invalidated(doc_id)
 
     def search(self, query, params: SearchParams, planner: Optional[Planner] = None) -> Optional[SearchResult]:
         """spann/index.rs:211-266"""
         return self.search_batch(np.asarray(query, dtype=np.float32).reshape(1, -1), params, planner=planner).to_results()[0]
+
+
+# ---- multi-user SPANN files (rs/index/src/multi_spann) ------------------------------------------------------------------------
+class _UserIndexInfoC(C.Structure):
+    _fields_ = [("user_lo", C.c_uint64), ("user_hi", C.c_uint64)] + [(n, C.c_uint64) for n in (
+        "centroid_vector_offset", "centroid_vector_len", "centroid_index_offset", "centroid_index_len", "ivf_vectors_offset",
+        "ivf_vectors_len", "ivf_raw_vectors_offset", "ivf_raw_vectors_len", "ivf_index_offset", "ivf_index_len",
+        "ivf_pq_codebook_offset", "ivf_pq_codebook_len")]
+
+
+@dataclass
+class UserIndexInfo:
+    """rs/index/src/multi_spann/user_index_info.rs:4-18"""
+    user_id: int
+    centroid_vector_offset: int = 0
+    centroid_vector_len: int = 0
+    centroid_index_offset: int = 0
+    centroid_index_len: int = 0
+    ivf_vectors_offset: int = 0
+    ivf_vectors_len: int = 0
+    ivf_raw_vectors_offset: int = 0
+    ivf_raw_vectors_len: int = 0
+    ivf_index_offset: int = 0
+    ivf_index_len: int = 0
+    ivf_pq_codebook_offset: int = 0
+    ivf_pq_codebook_len: int = 0
+
+    def _c(self) -> _UserIndexInfoC:
+        c = _UserIndexInfoC()
+        c.user_lo, c.user_hi = self.user_id & 0xFFFFFFFFFFFFFFFF, self.user_id >> 64
+        for n, _ in _UserIndexInfoC._fields_[2:]:
+            setattr(c, n, getattr(self, n))
+        return c
+
+    @classmethod
+    def _from_c(cls, c: _UserIndexInfoC):
+        return cls(int(c.user_lo) | (int(c.user_hi) << 64), **{n: int(getattr(c, n)) for n, _ in _UserIndexInfoC._fields_[2:]})
+
+    def to_le_bytes(self) -> bytes:
+        """user_index_info.rs:26-42"""
+        buf = (C.c_uint8 * 112)()
+        c = self._c()
+        _lib.check(_lib.load().mgpu_user_index_info_encode(C.addressof(c), C.addressof(buf)))
+        return bytes(buf)
+
+    @classmethod
+    def from_le_bytes(cls, data: bytes):
+        """user_index_info.rs:59-83"""
+        buf = (C.c_uint8 * 112).from_buffer_copy(data[:112])
+        c = _UserIndexInfoC()
+        _lib.check(_lib.load().mgpu_user_index_info_decode(C.addressof(buf), C.addressof(c)))
+        return cls._from_c(c)
+
+    @classmethod
+    def read_table(cls, path: str) -> dict:
+        """All records of a `user_index_info` file (odht table image) -> {user_id: UserIndexInfo}."""
+        lib = _lib.load()
+        n = lib.mgpu_user_index_info_read(path.encode(), None, 0)
+        if n < 0:
+            raise InvalidArgument(_lib.ERR_INVALID_ARG, f"{path}: not a user_index_info table")
+        arr = (_UserIndexInfoC * max(n, 1))()
+        lib.mgpu_user_index_info_read(path.encode(), C.addressof(arr), n)
+        out = {}
+        for i in range(n):
+            u = cls._from_c(arr[i])
+            out[u.user_id] = u
+        return out
+
+
+class MultiSpannIndex:
+    """rs/index/src/multi_spann/index.rs: one Spann per user inside shared files, opened lazily by user id
+    (get_or_create_index :100-128) at the byte offsets of `{base}/user_index_info`."""
+
+    def __init__(self, base_directory: str, num_features: int, quantizer_kind: int = QUANT_NONE, distance=L2DistanceCalculator,
+                 ctx: Optional[Context] = None):
+        import os
+        self.base, self.dim, self.quant, self.metric = base_directory, num_features, quantizer_kind, distance.METRIC
+        self.ctx = ctx or default_context()
+        self.user_index_infos = UserIndexInfo.read_table(os.path.join(base_directory, "user_index_info"))
+        self.user_to_spann = {}
+
+    def user_ids(self) -> list:
+        return sorted(self.user_index_infos)
+
+    def get_or_create_index(self, user_id: int) -> "Spann":
+        if user_id in self.user_to_spann:
+            return self.user_to_spann[user_id]
+        info = self.user_index_infos.get(user_id)
+        if info is None:
+            raise InvalidArgument(_lib.ERR_INVALID_ARG, "User not found")   # index.rs:108
+        c = info._c()
+        pq, hn, iv, sp = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _lib.check(self.ctx.lib.mgpu_spann_load_user(self.ctx.h, self.base.encode(), C.addressof(c), self.dim, self.quant, self.metric,
+                                                     C.byref(pq), C.byref(hn), C.byref(iv), C.byref(sp)), self.ctx.h)
+        s = Spann.__new__(Spann)
+        s.ctx, s.handle = self.ctx, sp
+        noq = NoQuantizer(self.dim)
+        hnsw = BlockBasedHnsw.__new__(BlockBasedHnsw)
+        hnsw.ctx, hnsw.quantizer, hnsw.dim, hnsw.handle = self.ctx, noq, self.dim, hn
+        ivf = BlockBasedIvf.__new__(BlockBasedIvf)
+        ivf.ctx, ivf.handle, ivf.dim = self.ctx, iv, self.dim
+        ivf.nlist = int(self.ctx.lib.mgpu_ivf_num_clusters(iv))
+        if self.quant == QUANT_PQ:
+            q = ProductQuantizer.__new__(ProductQuantizer)
+            q.ctx, q.handle, q.metric, q.dimension = self.ctx, pq, self.metric, self.dim
+            import os
+            cfg = {}
+            for line in open(os.path.join(self.base, "ivf", "quantizer", "product_quantizer_config.yaml")):
+                if ":" in line:
+                    k, v = line.split(":", 1)
+                    cfg[k.strip()] = int(v)
+            q.subvector_dimension, q.num_bits = cfg["subvector_dimension"], cfg["num_bits"]
+            q.codebook = None
+            ivf.quantizer = q
+        else:
+            ivf.quantizer = noq
+        s.centroids, s.posting_lists = hnsw, ivf
+        self.user_to_spann[user_id] = s
+        return s
+
+    def search_for_user(self, user_id: int, query, params: SearchParams, planner: Optional[Planner] = None) -> Optional[SearchResult]:
+        """multi_spann/index.rs: search_for_user -> Spann::search of that user's index (None for an unknown user)."""
+        if user_id not in self.user_index_infos:
+            return None
+        return self.get_or_create_index(user_id).search(query, params, planner)
 
 
 # ---- micro-batcher ------------------------------------------------------------------------------------------------------------
@@ -855,7 +1188,8 @@ def merge_topk(doc_ids, scores, counts, k: int, ctx: Optional[Context] = None) -
     if kk != k:
         raise InvalidArgument(_lib.ERR_INVALID_ARG, "partial results must have stride k")
     ids, sc, cnt, ip, sp, cp = _alloc_out(B, k, doc_ids if d.mem == DEVICE else None)
-    _lib.check(ctx.lib.mgpu_merge_topk(ctx.h, d.ptr, s.ptr, c.ptr, S, B, k, ip, sp, cp, d.mem), ctx.h)
+    with ctx.order(d.mem):
+        _lib.check(ctx.lib.mgpu_merge_topk(ctx.h, d.ptr, s.ptr, c.ptr, S, B, k, ip, sp, cp, d.mem), ctx.h)
     return BatchResult(ids, sc, cnt)
 
 
@@ -877,5 +1211,6 @@ def assign_to_centroids(X, centroids, max_clusters_per_vector=1, distance_thresh
         cids = np.zeros((n, r), dtype=np.uint32)
         cnt = np.zeros((n,), dtype=np.uint32)
         ip, cp = cids.ctypes.data, cnt.ctypes.data
-    _lib.check(ctx.lib.mgpu_ivf_assign(ctx.h, x.ptr, n, c.ptr, c.shape[0], dim, r, float(distance_threshold), ip, cp, x.mem), ctx.h)
+    with ctx.order(x.mem):
+        _lib.check(ctx.lib.mgpu_ivf_assign(ctx.h, x.ptr, n, c.ptr, c.shape[0], dim, r, float(distance_threshold), ip, cp, x.mem), ctx.h)
     return cids, cnt

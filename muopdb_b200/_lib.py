@@ -52,6 +52,8 @@ SIGNATURES = {
     "mgpu_version": (C.c_char_p, []),
     "mgpu_sync": (C.c_int, [C.c_void_p]),
     "mgpu_stream": (C.c_void_p, [C.c_void_p]),
+    "mgpu_stream_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mgpu_stream_signal": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mgpu_device_sm_count": (C.c_int, [C.c_void_p]),
     "mgpu_timer_start": (C.c_int, [C.c_void_p]),
     "mgpu_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
@@ -60,10 +62,12 @@ SIGNATURES = {
     "mgpu_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     "mgpu_launch_count": (C.c_uint64, [C.c_void_p]),
     "mgpu_distance_batch": (C.c_int, [C.c_void_p, _f32p, C.c_uint64, _f32p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, _f32p, C.c_int]),
+    "mgpu_distance_batch_lanes": (C.c_int, [C.c_void_p, _f32p, C.c_uint64, _f32p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, _f32p, C.c_int]),
     "mgpu_pq_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _f32p, C.c_int, C.POINTER(C.c_void_p)]),
     "mgpu_pq_destroy": (None, [C.c_void_p]),
     "mgpu_pq_quantize_batch": (C.c_int, [C.c_void_p, _f32p, C.c_uint64, _u8p, C.c_int]),
     "mgpu_pq_distance_batch": (C.c_int, [C.c_void_p, _u8p, _u8p, C.c_uint64, _f32p, C.c_int]),
+    "mgpu_pq_original_vector": (C.c_int, [C.c_void_p, _u8p, C.c_uint64, _f32p, C.c_int]),
     "mgpu_ivf_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _f32p, _u64p, _u32p, C.c_int, C.c_int, C.c_void_p,
                                   _vp, C.c_int, C.c_uint64, _vp, C.POINTER(C.c_void_p)]),
     "mgpu_ivf_destroy": (None, [C.c_void_p]),
@@ -71,6 +75,11 @@ SIGNATURES = {
     "mgpu_ivf_num_clusters": (C.c_uint32, [C.c_void_p]),
     "mgpu_ivf_invalidate": (C.c_int, [C.c_void_p, _u32p, C.c_uint32]),
     "mgpu_ivf_is_invalidated": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_int)]),
+    "mgpu_ivf_invalidate_docs": (C.c_int, [C.c_void_p, _vp, C.c_uint32, _u8p, C.POINTER(C.c_uint32)]),
+    "mgpu_ivf_is_doc_invalidated": (C.c_int, [C.c_void_p, _vp, C.POINTER(C.c_int)]),
+    "mgpu_ivf_get_point_id": (C.c_int, [C.c_void_p, _vp, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]),
+    "mgpu_ivf_get_doc_ids": (C.c_int, [C.c_void_p, _u32p, C.c_uint32, _vp]),
+    "mgpu_ivf_get_vectors": (C.c_int, [C.c_void_p, _u32p, C.c_uint32, _vp]),
     "mgpu_ivf_coarse": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, _u32p, _f32p, C.c_int]),
     "mgpu_ivf_scan": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, _u32p, C.c_uint32, _u32p, C.c_uint32, _u32p, _f32p, _u32p, C.c_int]),
     "mgpu_ivf_scan_remap": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, _u32p, C.c_uint32, _u32p, C.c_uint32, _vp, _f32p, _u32p, C.c_int]),
@@ -84,6 +93,7 @@ SIGNATURES = {
     "mgpu_ivf_last_scan_bytes": (C.c_uint64, [C.c_void_p]),
     "mgpu_ivf_last_scan_rows": (C.c_uint64, [C.c_void_p]),
     "mgpu_ivf_assign": (C.c_int, [C.c_void_p, _f32p, C.c_uint64, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, _u32p, _u32p, C.c_int]),
+    "mgpu_kmeans_assign": (C.c_int, [C.c_void_p, _f32p, C.c_uint64, _f32p, C.c_uint32, C.c_uint32, C.c_int, _f32p, _u32p, _f32p, C.c_int]),
     "mgpu_hnsw_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _u32p, C.c_uint64, _u32p, C.c_uint64, _u64p, C.c_uint64,
                                    _u64p, C.c_int, C.c_int, C.c_void_p, _vp, C.c_int, C.c_uint64, _vp, C.POINTER(C.c_void_p)]),
     "mgpu_hnsw_destroy": (None, [C.c_void_p]),
@@ -106,12 +116,22 @@ SIGNATURES = {
     "mgpu_comm_destroy": (C.c_int, [C.c_void_p]),
     "mgpu_shard_ivf_search": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _vp, _f32p, _u32p, C.c_int]),
     "mgpu_shard_ivf_search_submit": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _vp, _f32p, _u32p, C.POINTER(C.c_uint64)]),
+    "mgpu_shard_spann_search": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_int, _vp, _f32p,
+                                          _u32p, C.c_int]),
+    "mgpu_shard_spann_search_submit": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_int, _vp,
+                                                 _f32p, _u32p, C.POINTER(C.c_uint64)]),
+    "mgpu_shard_overlap": (C.c_int, [C.c_void_p, C.c_int]),
     "mgpu_shard_allgather_merge": (C.c_int, [C.c_void_p, _vp, _f32p, _u32p, C.c_uint32, C.c_uint32, _vp, _f32p, _u32p]),
     "mgpu_ef_decode": (C.c_int64, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "mgpu_pq_load": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "mgpu_ivf_load": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "mgpu_hnsw_load": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_void_p,
                                  C.POINTER(C.c_void_p)]),
+    "mgpu_user_index_info_decode": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mgpu_user_index_info_encode": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mgpu_user_index_info_read": (C.c_int64, [C.c_char_p, C.c_void_p, C.c_uint64]),
+    "mgpu_spann_load_user": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "mgpu_hnsw_info": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mgpu_hnsw_copy_graph": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -88,6 +88,12 @@ void mgpu_destroy(mgpu_ctx *ctx) {
     if (pp.ev_out) cudaEventDestroy(pp.ev_out);
   }
   if (ctx->shard_ws) cudaFree(ctx->shard_ws);
+  for (auto &sl : ctx->shard_slot) {
+    if (sl.buf) cudaFree(sl.buf);
+    if (sl.ev_local) cudaEventDestroy(sl.ev_local);
+    if (sl.ev_xdone) cudaEventDestroy(sl.ev_xdone);
+  }
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
   if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
   if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   if (ctx->ws) cudaFree(ctx->ws);
@@ -106,9 +112,44 @@ const char *mgpu_last_error(mgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "nu
 int mgpu_sync(mgpu_ctx *ctx) {
   if (!ctx) return MGPU_ERR_INVALID_ARG;
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->comm_stream) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->comm_stream));   // a sharded call's exchange may still be in flight
   return MGPU_OK;
 }
 void *mgpu_stream(mgpu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+// Ordering against a caller-owned stream (the ctx stream is non-blocking: it does not synchronise with the legacy stream or
+// with any other stream implicitly).  wait: the ctx stream waits for everything enqueued on `other` so far (inputs produced
+// there, e.g. a zero-fill of the output buffers); signal: `other` waits for everything enqueued on the ctx streams so far
+// (results).  The events are created per call: two calls may be in flight from different threads of one ctx user.
+int mgpu_stream_wait(mgpu_ctx *ctx, void *other) {
+  if (!ctx) return MGPU_ERR_INVALID_ARG;
+  if ((cudaStream_t)other == ctx->stream) return MGPU_OK;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaEvent_t e;
+  CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  cudaError_t r = cudaEventRecord(e, (cudaStream_t)other);
+  if (r == cudaSuccess) r = cudaStreamWaitEvent(ctx->stream, e, 0);
+  cudaEventDestroy(e);   // released once the wait has consumed it
+  CUDA_TRY(ctx, r);
+  return MGPU_OK;
+}
+int mgpu_stream_signal(mgpu_ctx *ctx, void *other) {
+  if (!ctx) return MGPU_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStream_t srcs[2] = {ctx->stream, ctx->comm_stream};
+  for (cudaStream_t st : srcs) {
+    if (!st || st == (cudaStream_t)other) continue;
+    cudaEvent_t e;
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaError_t r = cudaEventRecord(e, st);
+    if (r == cudaSuccess) r = cudaStreamWaitEvent((cudaStream_t)other, e, 0);
+    cudaEventDestroy(e);
+    CUDA_TRY(ctx, r);
+  }
+  return MGPU_OK;
+}
 int mgpu_device_sm_count(mgpu_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 
 int mgpu_timer_start(mgpu_ctx *ctx) {
@@ -387,7 +428,8 @@ void mgpu_ivf_destroy(mgpu_ivf *ivf) {
   cudaStreamSynchronize(ivf->ctx->stream);
   cudaFree(ivf->d_centroids); cudaFree(ivf->d_csplit); cudaFree(ivf->d_cn); cudaFree(ivf->d_chunk_start); cudaFree(ivf->d_list_len); cudaFree(ivf->d_slot_pid);
   cudaFree(ivf->d_codes); cudaFree(ivf->d_rows); cudaFree(ivf->d_doc_ids); cudaFree(ivf->d_invalid); cudaFree(ivf->d_scan_rows);
-  cudaFree(ivf->d_scan_overflow);
+  cudaFree(ivf->d_scan_overflow); cudaFree(ivf->d_pid_slot);
+  ivf_free_doc_map(ivf);
   delete ivf;
 }
 
@@ -532,38 +574,64 @@ static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32
   FinalizeArgs f;
   memset(&f, 0, sizeof(f));
   f.cand_key = d_ckey; f.cand_slot = d_cslot; f.B = B; f.k = k; f.slot_pid = ivf->d_slot_pid; f.metric = ivf->metric;
-  if (k > MGPU_NCAND) {
-    // ---- k > 32: multi-round top-k.  Every round is the ordinary scan restricted to rows whose composite (ranking key,
-    // point id) is not below the bound left by the previous round, followed by the exact re-score of its (up to) 31 newly
-    // reported candidates; the rounds' exact results are merged with the reference's ordering.  Rounds = ceil((k+16)/31):
-    // 16 spare candidates cover swaps between the fixed-point ranking and the exact scores at the k boundary.
+  // PQ ranks by a fixed-point key and re-scores exactly, so it wants spare candidates beyond k: one round gives 32 - k of
+  // them; from k > 16 on the multi-round path keeps the same MGPU_ROUND_SPARE margin as for k > 32
+  if (k > MGPU_NCAND || (ivf->quant == MGPU_QUANT_PQ && k > MGPU_NCAND - MGPU_ROUND_SPARE)) {
+    // ---- multi-round top-k.  Every round is the ordinary scan restricted to rows whose composite (ranking key, point id)
+    // is not below the bound left by the previous round, followed by the exact re-score of its (up to) 31 newly reported
+    // candidates; the rounds' exact results are merged with the reference's ordering.  Rounds run until every query has
+    // either seen a short round (all of its rows reported) or holds k + MGPU_ROUND_SPARE reported candidates: a round that
+    // ends inside a group of equal composites (a point living in several probed lists) reports fewer than 31, so the count
+    // is tracked per query on the device instead of assuming 31 per round.  The spare candidates cover swaps between the
+    // fixed-point ranking and the exact scores at the k boundary.
     if (k > MGPU_MAX_K) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported", k, MGPU_MAX_K);
-    const uint32_t R = (k + 16 + 30) / 31;
+    const uint32_t want = k + MGPU_ROUND_SPARE;
+    const uint32_t R0 = (want + 30) / 31;
+    // hard cap: twice the nominal count (covers every point sitting in up to 16 probed lists), bounded by what the merge
+    // kernel can hold in shared memory
+    const uint32_t Rcap = std::min<uint32_t>(2 * R0 + 2, (uint32_t)(ctx->smem_optin / (MGPU_NCAND * 28)));
     const size_t per = (size_t)B * MGPU_NCAND;
     size_t need = 0;
-    need = ws_need(need, (size_t)B * 8); need = ws_need(need, R * per * 4); need = ws_need(need, R * per * 4);
-    need = ws_need(need, (size_t)R * B * 4);
+    need = ws_need(need, (size_t)B * 8); need = ws_need(need, Rcap * per * 4); need = ws_need(need, Rcap * per * 4);
+    need = ws_need(need, (size_t)Rcap * B * 4); need = ws_need(need, (size_t)B * 4); need = ws_need(need, 16);
     uint8_t *priv = nullptr;
     CUDA_TRY(ctx, cudaMallocAsync((void **)&priv, need + 256, ctx->stream));
     WsAlloc pw(priv, need + 256);
     uint64_t *lb = pw.get<uint64_t>(B);
-    uint32_t *rP = pw.get<uint32_t>(R * per); float *rS = pw.get<float>(R * per); uint32_t *rC = pw.get<uint32_t>((size_t)R * B);
+    uint32_t *rP = pw.get<uint32_t>(Rcap * per); float *rS = pw.get<float>(Rcap * per); uint32_t *rC = pw.get<uint32_t>((size_t)Rcap * B);
+    uint32_t *reported = pw.get<uint32_t>(B); uint32_t *unfinished = pw.get<uint32_t>(4);
     int st = MGPU_OK;
     if (cudaMemsetAsync(lb, 0, (size_t)B * 8, ctx->stream) != cudaSuccess) st = mgpu_fail(ctx, MGPU_ERR_CUDA, "memset failed");
+    if (st == MGPU_OK && cudaMemsetAsync(reported, 0, (size_t)B * 4, ctx->stream) != cudaSuccess) st = mgpu_fail(ctx, MGPU_ERR_CUDA, "memset failed");
     a.lower_bound = lb;
     if (ivf->quant == MGPU_QUANT_PQ) {
       f.cb = ivf->pq->d_cb; f.codes = ivf->d_codes; f.qcodes = d_qcodes; f.m = ivf->pq->m; f.K = ivf->pq->K;
       f.dsub = ivf->pq->dsub; f.ng = ivf->ng; f.pq_fast = ivf->pq_fast;
     }
     f.doc_ids = nullptr; f.k = MGPU_NCAND; f.prune = false;
-    for (uint32_t r = 0; r < R && st == MGPU_OK; r++) {
-      st = launch_scan(ivf, a);
-      if (st == MGPU_OK) st = launch_round_prepare(ctx, d_ckey, d_cslot, B, lb);
-      f.out_docs = nullptr; f.out_pids = rP + r * per; f.out_scores = rS + r * per; f.out_counts = rC + (size_t)r * B;
-      if (st == MGPU_OK) st = launch_finalize(ctx, f);
+    uint32_t r = 0, target = R0;
+    while (st == MGPU_OK) {
+      for (; r < target && st == MGPU_OK; r++) {
+        st = launch_scan(ivf, a);
+        if (st == MGPU_OK && cudaMemsetAsync(unfinished, 0, 4, ctx->stream) != cudaSuccess) st = mgpu_fail(ctx, MGPU_ERR_CUDA, "memset failed");
+        if (st == MGPU_OK) st = launch_round_prepare(ctx, d_ckey, d_cslot, B, lb, reported, want, unfinished);
+        f.out_docs = nullptr; f.out_pids = rP + r * per; f.out_scores = rS + r * per; f.out_counts = rC + (size_t)r * B;
+        if (st == MGPU_OK) st = launch_finalize(ctx, f);
+      }
+      if (st != MGPU_OK) break;
+      uint32_t left = 0;   // queries whose last round was full and that still hold fewer than `want` reported candidates
+      if (cudaMemcpyAsync(&left, unfinished, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+          cudaStreamSynchronize(ctx->stream) != cudaSuccess) { st = mgpu_fail(ctx, MGPU_ERR_CUDA, "multi-round top-k: reading the round status failed"); break; }
+      if (left == 0) break;
+      if (r >= Rcap) {
+        st = mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "multi-round top-k: %u rounds did not yield k + %d candidates for %u queries "
+                                                   "(a point living in more than 16 probed lists?)", r, MGPU_ROUND_SPARE, left);
+        break;
+      }
+      target = std::min(Rcap, r + std::max<uint32_t>(1, R0 / 8));
     }
     // the k smallest by (distance, point_id) over all rounds, then (remap variants) doc ids ordered by (score, doc_id)
-    if (st == MGPU_OK) st = launch_merge_rounds(ctx, rP, rS, rC, R, B, k, ivf->d_doc_ids, d_out_pids, d_out_docs, d_out_scores, d_out_counts);
+    if (st == MGPU_OK) st = launch_merge_rounds(ctx, rP, rS, rC, r, B, k, ivf->d_doc_ids, d_out_pids, d_out_docs, d_out_scores, d_out_counts);
     cudaFreeAsync(priv, ctx->stream);
     return st;
   }
@@ -615,10 +683,12 @@ static int pipe_begin(mgpu_ctx *ctx, const void *Q, size_t q_bytes, size_t out_b
   return MGPU_OK;
 }
 // second half: results leave on the D2H stream; the ticket completes when they have landed in the caller's buffers
+// results_ready (optional): the event after which the results are complete when they are produced off the main stream (the
+// sharded calls' exchange stream); ev_done still marks the point after which the slot's query staging may be overwritten
 static int pipe_end(mgpu_ctx *ctx, mgpu_ctx::Pipe *pp, uint32_t B, uint32_t k, const mgpu_u128 *dD, const float *dS, const uint32_t *dC,
-                    mgpu_u128 *out_docs, float *out_scores, uint32_t *out_counts, uint64_t *ticket) {
+                    mgpu_u128 *out_docs, float *out_scores, uint32_t *out_counts, uint64_t *ticket, cudaEvent_t results_ready = nullptr) {
   CUDA_TRY(ctx, cudaEventRecord(pp->ev_done, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->d2h_stream, pp->ev_done, 0));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->d2h_stream, results_ready ? results_ready : pp->ev_done, 0));
   CUDA_TRY(ctx, cudaMemcpyAsync(out_docs, dD, (size_t)B * k * 16, cudaMemcpyDeviceToHost, ctx->d2h_stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(out_scores, dS, (size_t)B * k * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(out_counts, dC, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
@@ -951,6 +1021,8 @@ int mgpu_comm_unique_id(uint8_t out_id[128]) {
   return MGPU_OK;
 }
 
+typedef int (*fn_ncclCommSplit)(void *, int, int, void **, void *);
+
 int mgpu_comm_init(mgpu_ctx *ctx, int nranks, int rank, const uint8_t id[128]) {
   if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return MGPU_ERR_INVALID_ARG;
   auto f = (fn_ncclCommInitRank)nccl_sym("ncclCommInitRank");
@@ -965,81 +1037,147 @@ int mgpu_comm_init(mgpu_ctx *ctx, int nranks, int rank, const uint8_t id[128]) {
     return mgpu_fail(ctx, MGPU_ERR_NCCL, "ncclCommInitRank failed: %s", es ? es(r) : "?");
   }
   ctx->nranks = nranks; ctx->rank = rank;
+  // a second communicator for the result exchange, so that it can run on its own stream next to the query-code all-gather
+  // of the following batch (collectives of ONE communicator are ordered, whatever stream they are given)
+  static const bool no_split = getenv("MGPU_COMM_SPLIT") && getenv("MGPU_COMM_SPLIT")[0] == '0';
+  auto split = (fn_ncclCommSplit)nccl_sym("ncclCommSplit");
+  ctx->nccl_comm_x = nullptr;
+  if (split && !no_split && split(ctx->nccl_comm, 0, rank, &ctx->nccl_comm_x, nullptr) != 0) ctx->nccl_comm_x = nullptr;
+  if (!ctx->comm_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
   return MGPU_OK;
 }
 
 int mgpu_comm_destroy(mgpu_ctx *ctx) {
   if (!ctx) return MGPU_ERR_INVALID_ARG;
-  if (ctx->nccl_comm) {
-    auto f = (fn_ncclCommDestroy)nccl_sym("ncclCommDestroy");
-    if (f) f(ctx->nccl_comm);
-    ctx->nccl_comm = nullptr;
-  }
+  auto f = (fn_ncclCommDestroy)nccl_sym("ncclCommDestroy");
+  if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
+  if (ctx->nccl_comm_x) { if (f) f(ctx->nccl_comm_x); ctx->nccl_comm_x = nullptr; }
+  if (ctx->nccl_comm) { if (f) f(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
   return MGPU_OK;
 }
 
-static int shard_allgather_merge_impl(mgpu_ctx *ctx, const mgpu_u128 *local_doc_ids, const float *local_scores,
-                                      const uint32_t *local_counts, uint32_t B, uint32_t k, mgpu_u128 *out_doc_ids,
-                                      float *out_scores, uint32_t *out_counts, bool caller_holds_lock) {
+int mgpu_shard_overlap(mgpu_ctx *ctx, int on) {
   if (!ctx) return MGPU_ERR_INVALID_ARG;
-  if (!ctx->nccl_comm) return mgpu_fail(ctx, MGPU_ERR_NCCL, "shard_allgather_merge: communicator not initialised");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->shard_overlap = on != 0;
+  return MGPU_OK;
+}
+
+// ---- result exchange --------------------------------------------------------------------------------------------------------
+// One slot of exchange buffers: this rank's local top-k (docs | scores | counts), the gathered lists of all ranks, and (host
+// callers) the merged result before its D2H copy.
+struct ShardBufs {
+  mgpu_u128 *locD; float *locS; uint32_t *locC;
+  mgpu_u128 *gD; float *gS; uint32_t *gC;
+  mgpu_u128 *outD; float *outS; uint32_t *outC;
+};
+
+// Claims the next slot.  The main stream waits until the slot's previous exchange has consumed its buffers.
+static int shard_slot_begin(mgpu_ctx *ctx, uint32_t B, uint32_t k, mgpu_ctx::ShardSlot **out_slot, ShardBufs *b) {
+  if (!ctx->comm_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  mgpu_ctx::ShardSlot *sl = &ctx->shard_slot[ctx->shard_seq++ & 1];
+  if (!sl->ev_local) {
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl->ev_local, cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl->ev_xdone, cudaEventDisableTiming));
+  }
+  const uint32_t S = (uint32_t)ctx->nranks;
+  const size_t nloc = (size_t)B * k;
+  size_t need = 0;
+  need = ws_need(need, nloc * 16); need = ws_need(need, nloc * 4); need = ws_need(need, (size_t)B * 4);
+  need = ws_need(need, S * nloc * 16); need = ws_need(need, S * nloc * 4); need = ws_need(need, (size_t)S * B * 4);
+  need = ws_need(need, nloc * 16); need = ws_need(need, nloc * 4); need = ws_need(need, (size_t)B * 4);
+  need += 256;
+  if (sl->used) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, sl->ev_xdone, 0));
+  if (sl->bytes < need) {
+    if (sl->buf) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->comm_stream)); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(sl->buf); sl->buf = nullptr; sl->bytes = 0; }
+    CUDA_TRY(ctx, cudaMalloc(&sl->buf, need + need / 4));
+    sl->bytes = need + need / 4;
+  }
+  WsAlloc w(sl->buf, sl->bytes);
+  b->locD = w.get<mgpu_u128>(nloc); b->locS = w.get<float>(nloc); b->locC = w.get<uint32_t>(B);
+  b->gD = w.get<mgpu_u128>(S * nloc); b->gS = w.get<float>(S * nloc); b->gC = w.get<uint32_t>((size_t)S * B);
+  b->outD = w.get<mgpu_u128>(nloc); b->outS = w.get<float>(nloc); b->outC = w.get<uint32_t>(B);
+  *out_slot = sl;
+  return MGPU_OK;
+}
+
+// All-gather of the per-shard top-k over NVLink + merge (snapshot.rs:60-61,105-106), on the exchange stream: it starts when
+// the local search of this batch is done and does not hold up the main stream.
+static int shard_exchange(mgpu_ctx *ctx, mgpu_ctx::ShardSlot *sl, const ShardBufs &b, const mgpu_u128 *locD, const float *locS,
+                          const uint32_t *locC, uint32_t B, uint32_t k, mgpu_u128 *oD, float *oS, uint32_t *oC) {
   auto ag = (fn_ncclAllGather)nccl_sym("ncclAllGather");
   if (!ag) return mgpu_fail(ctx, MGPU_ERR_NCCL, "ncclAllGather not found");
-  std::unique_lock<std::mutex> g(ctx->mu, std::defer_lock);
-  if (!caller_holds_lock) g.lock();
-  cudaSetDevice(ctx->device);
-  if (B == 0 || k == 0) return MGPU_OK;
+  void *comm = ctx->nccl_comm_x ? ctx->nccl_comm_x : ctx->nccl_comm;
   const uint32_t S = (uint32_t)ctx->nranks;
-  size_t nloc = (size_t)B * k;
-  size_t need = 0;
-  need = ws_need(need, S * nloc * 16); need = ws_need(need, S * nloc * 4); need = ws_need(need, (size_t)S * B * 4);
-  MGPU_TRY(mgpu_ws_reserve(ctx, need));
-  WsAlloc w(ctx->ws, ctx->ws_bytes);
-  mgpu_u128 *gD = w.get<mgpu_u128>(S * nloc); float *gS = w.get<float>(S * nloc); uint32_t *gC = w.get<uint32_t>((size_t)S * B);
-  // ncclChar = 0; three small all-gathers over NVLink (B*k*20 + B*4 bytes per rank), grouped so that NCCL issues them as one
-  // launch (the exchange is latency bound: three separate collectives cost three launch + handshake latencies)
+  const size_t nloc = (size_t)B * k;
+  CUDA_TRY(ctx, cudaEventRecord(sl->ev_local, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->comm_stream, sl->ev_local, 0));
+  // ncclChar = 0; three small all-gathers (B*k*20 + B*4 bytes per rank), grouped so that NCCL issues them as one launch (the
+  // exchange is latency bound: three separate collectives cost three launch + handshake latencies)
   auto gs = (fn_ncclGroup)nccl_sym("ncclGroupStart");
   auto ge = (fn_ncclGroup)nccl_sym("ncclGroupEnd");
   const bool grouped = gs && ge && gs() == 0;
-  int r = ag(local_doc_ids, gD, nloc * 16, 0, ctx->nccl_comm, ctx->stream);
-  if (r == 0) r = ag(local_scores, gS, nloc * 4, 0, ctx->nccl_comm, ctx->stream);
-  if (r == 0) r = ag(local_counts, gC, (size_t)B * 4, 0, ctx->nccl_comm, ctx->stream);
+  int r = ag(locD, b.gD, nloc * 16, 0, comm, ctx->comm_stream);
+  if (r == 0) r = ag(locS, b.gS, nloc * 4, 0, comm, ctx->comm_stream);
+  if (r == 0) r = ag(locC, b.gC, (size_t)B * 4, 0, comm, ctx->comm_stream);
   if (grouped) { const int r2 = ge(); if (r == 0) r = r2; }
   if (r != 0) return mgpu_fail(ctx, MGPU_ERR_NCCL, "ncclAllGather failed (%d)", r);
   ctx->launches += 3;
-  return launch_merge_topk(ctx, gD, gS, gC, S, B, k, out_doc_ids, out_scores, out_counts);
+  MGPU_TRY(launch_merge_topk(ctx, b.gD, b.gS, b.gC, S, B, k, oD, oS, oC, ctx->comm_stream));
+  CUDA_TRY(ctx, cudaEventRecord(sl->ev_xdone, ctx->comm_stream));
+  sl->used = true;
+  return MGPU_OK;
 }
 
 int mgpu_shard_allgather_merge(mgpu_ctx *ctx, const mgpu_u128 *local_doc_ids, const float *local_scores,
                                const uint32_t *local_counts, uint32_t B, uint32_t k, mgpu_u128 *out_doc_ids,
                                float *out_scores, uint32_t *out_counts) {
-  return shard_allgather_merge_impl(ctx, local_doc_ids, local_scores, local_counts, B, k, out_doc_ids, out_scores, out_counts, false);
+  if (!ctx) return MGPU_ERR_INVALID_ARG;
+  if (!ctx->nccl_comm) return mgpu_fail(ctx, MGPU_ERR_NCCL, "shard_allgather_merge: communicator not initialised");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (B == 0 || k == 0) return MGPU_OK;
+  mgpu_ctx::ShardSlot *sl;
+  ShardBufs b;
+  MGPU_TRY(shard_slot_begin(ctx, B, k, &sl, &b));
+  MGPU_TRY(shard_exchange(ctx, sl, b, local_doc_ids, local_scores, local_counts, B, k, out_doc_ids, out_scores, out_counts));
+  if (!ctx->shard_overlap) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, sl->ev_xdone, 0));
+  return MGPU_OK;
 }
 
+static int spann_search_impl(mgpu_spann *sp, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef,
+                             uint32_t num_explored_centroids, float ratio, const uint32_t *filter_bits, uint64_t filter_stride,
+                             mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, int mem, bool caller_holds_lock = false,
+                             const uint8_t *d_qcodes_ext = nullptr);
+
 // The whole sharded query path in one call: every rank passes the SAME replicated batch and searches its own
-// doc-shard; the per-shard top-k lists are all-gathered and merged with the leaf ordering (snapshot.rs:60-61,105-106), so
-// every rank returns the merged result.  With a codebook shared by all shards (shared_codebook != 0) the query encode
-// (index.rs:193) -- per-query work that does not shrink with the shard -- is split across the ranks: rank r encodes
-// queries [r*ceil(B/N), (r+1)*ceil(B/N)) and one all-gather of B x m code bytes replaces N-1 redundant encodes per query.
-static int shard_ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, int shared_codebook,
-                                 mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, int mem, uint64_t *ticket) {
-  if (!ivf) return MGPU_ERR_INVALID_ARG;
+// doc-shard -- BlockBasedIvf::search (ivf != null) or Spann::search (sp != null, config 5); the per-shard top-k lists are
+// all-gathered and merged with the leaf ordering (snapshot.rs:60-61,105-106), so every rank returns the merged result.  With
+// a codebook shared by all shards (shared_codebook != 0) the query encode (index.rs:193) -- per-query work that does not
+// shrink with the shard -- is split across the ranks: rank r encodes queries [r*ceil(B/N), (r+1)*ceil(B/N)) and one
+// all-gather of B x m code bytes replaces N-1 redundant encodes per query.
+static int shard_search_impl(mgpu_ivf *ivf, mgpu_spann *sp, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, uint32_t ef,
+                             uint32_t num_explored, float ratio, int shared_codebook, mgpu_u128 *out_doc_ids, float *out_scores,
+                             uint32_t *out_counts, int mem, uint64_t *ticket) {
+  if (!ivf && !sp) return MGPU_ERR_INVALID_ARG;
+  if (sp) ivf = sp->lists;
   mgpu_ctx *ctx = ivf->ctx;
   if (ticket) *ticket = 0;
-  if (!ctx->nccl_comm) return mgpu_fail(ctx, MGPU_ERR_NCCL, "shard_ivf_search: communicator not initialised (mgpu_comm_init_rank)");
-  if (B && (!Q || !out_doc_ids || !out_scores || !out_counts)) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "shard_ivf_search: null buffer");
-  if (nprobe == 0 || nprobe > ivf->nlist) return mgpu_fail(ctx, MGPU_ERR_OUT_OF_RANGE, "num_probes %u out of range 1..%u (the reference panics)", nprobe, ivf->nlist);
+  if (!ctx->nccl_comm) return mgpu_fail(ctx, MGPU_ERR_NCCL, "shard search: communicator not initialised (mgpu_comm_init)");
+  if (B && (!Q || !out_doc_ids || !out_scores || !out_counts)) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "shard search: null buffer");
+  if (!sp && (nprobe == 0 || nprobe > ivf->nlist)) return mgpu_fail(ctx, MGPU_ERR_OUT_OF_RANGE, "num_probes %u out of range 1..%u (the reference panics)", nprobe, ivf->nlist);
   if (k > MGPU_MAX_K) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported", k, MGPU_MAX_K);
   auto ag = (fn_ncclAllGather)nccl_sym("ncclAllGather");
   if (!ag) return mgpu_fail(ctx, MGPU_ERR_NCCL, "ncclAllGather not found");
   std::lock_guard<std::mutex> g(ctx->mu);
   cudaSetDevice(ctx->device);
   if (B == 0) return MGPU_OK;
-  if (k == 0) {
+  if (k == 0 && !sp) {
     if (mem == MGPU_HOST) memset(out_counts, 0, (size_t)B * 4);
     else CUDA_TRY(ctx, cudaMemsetAsync(out_counts, 0, (size_t)B * 4, ctx->stream));
     return MGPU_OK;
   }
+  const uint32_t kk = std::max<uint32_t>(k, 1);   // Spann with top_k = 0 still reports None / empty per query
   const uint32_t N = (uint32_t)ctx->nranks, r = (uint32_t)ctx->rank;
   const bool split_encode = shared_codebook && ivf->quant == MGPU_QUANT_PQ && N > 1;
   const uint32_t m = ivf->pq ? ivf->pq->m : 0;
@@ -1048,27 +1186,22 @@ static int shard_ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, uint
   need = ws_need(need, mem == MGPU_HOST ? (size_t)B * ivf->dim * 4 : 0);
   need = ws_need(need, split_encode ? (size_t)N * slice * m : 0);
   need = ws_need(need, split_encode ? (size_t)slice * m : 0);
-  need = ws_need(need, (size_t)B * k * 16); need = ws_need(need, (size_t)B * k * 4); need = ws_need(need, (size_t)B * 4);
-  need = ws_need(need, mem == MGPU_HOST ? (size_t)B * k * 16 : 0);
-  need = ws_need(need, mem == MGPU_HOST ? (size_t)B * k * 4 : 0);
-  need = ws_need(need, mem == MGPU_HOST ? (size_t)B * 4 : 0);
   if (ctx->shard_ws_bytes < need) {
     if (ctx->shard_ws) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->shard_ws); ctx->shard_ws = nullptr; ctx->shard_ws_bytes = 0; }
-    CUDA_TRY(ctx, cudaMalloc(&ctx->shard_ws, need + need / 4));
-    ctx->shard_ws_bytes = need + need / 4;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->shard_ws, need + need / 4 + 256));
+    ctx->shard_ws_bytes = need + need / 4 + 256;
   }
   WsAlloc w(ctx->shard_ws, ctx->shard_ws_bytes);
   float *sQ = w.get<float>(mem == MGPU_HOST ? (size_t)B * ivf->dim : 0);
   uint8_t *codes_all = w.get<uint8_t>(split_encode ? (size_t)N * slice * m : 0);
   uint8_t *codes_mine = w.get<uint8_t>(split_encode ? (size_t)slice * m : 0);
-  mgpu_u128 *locD = w.get<mgpu_u128>((size_t)B * k); float *locS = w.get<float>((size_t)B * k); uint32_t *locC = w.get<uint32_t>(B);
-  mgpu_u128 *outD = w.get<mgpu_u128>(mem == MGPU_HOST ? (size_t)B * k : 0);
-  float *outS = w.get<float>(mem == MGPU_HOST ? (size_t)B * k : 0);
-  uint32_t *outC = w.get<uint32_t>(mem == MGPU_HOST ? B : 0);
+  mgpu_ctx::ShardSlot *sl;
+  ShardBufs b;
+  MGPU_TRY(shard_slot_begin(ctx, B, kk, &sl, &b));
   const void *dQv;
   mgpu_ctx::Pipe *pp = nullptr;
   if (ticket) {   // pipelined: this slot's staging for the queries and the merged results, copies on the side streams
-    MGPU_TRY(pipe_begin(ctx, Q, (size_t)B * ivf->dim * 4, (size_t)B * k * 24 + (size_t)B * 4 + 768, &pp));
+    MGPU_TRY(pipe_begin(ctx, Q, (size_t)B * ivf->dim * 4, (size_t)B * kk * 24 + (size_t)B * 4 + 768, &pp));
     dQv = pp->q;
   } else {
     MGPU_TRY(stage_in(ctx, Q, (size_t)B * ivf->dim * 4, mem, sQ, &dQv));
@@ -1083,39 +1216,64 @@ static int shard_ivf_search_impl(mgpu_ivf *ivf, const float *Q, uint32_t B, uint
     ctx->launches += 1;
     ext = codes_all;  // rank j's slice starts at j*slice*m = (first query of the slice)*m: query q sits at q*m
   }
-  MGPU_TRY(ivf_search_impl(ivf, dQ, B, nullptr, 0, nullptr, nprobe, k, nullptr, locD, locS, locC, MGPU_DEVICE, nullptr, 0, nullptr, ext, true));
-  mgpu_u128 *oD = mem == MGPU_DEVICE ? out_doc_ids : outD;
-  float *oS = mem == MGPU_DEVICE ? out_scores : outS;
-  uint32_t *oC = mem == MGPU_DEVICE ? out_counts : outC;
+  if (sp) MGPU_TRY(spann_search_impl(sp, dQ, B, k, ef, num_explored, ratio, nullptr, 0, b.locD, b.locS, b.locC, MGPU_DEVICE, true, ext));
+  else MGPU_TRY(ivf_search_impl(ivf, dQ, B, nullptr, 0, nullptr, nprobe, k, nullptr, b.locD, b.locS, b.locC, MGPU_DEVICE, nullptr, 0, nullptr, ext, true));
+  mgpu_u128 *oD = mem == MGPU_DEVICE ? out_doc_ids : b.outD;
+  float *oS = mem == MGPU_DEVICE ? out_scores : b.outS;
+  uint32_t *oC = mem == MGPU_DEVICE ? out_counts : b.outC;
   if (pp) {
     WsAlloc wo(pp->out, pp->out_bytes);
-    oD = wo.get<mgpu_u128>((size_t)B * k); oS = wo.get<float>((size_t)B * k); oC = wo.get<uint32_t>(B);
+    oD = wo.get<mgpu_u128>((size_t)B * kk); oS = wo.get<float>((size_t)B * kk); oC = wo.get<uint32_t>(B);
   }
-  MGPU_TRY(shard_allgather_merge_impl(ctx, locD, locS, locC, B, k, oD, oS, oC, true));
-  if (pp) return pipe_end(ctx, pp, B, k, oD, oS, oC, out_doc_ids, out_scores, out_counts, ticket);
-  if (mem == MGPU_HOST) {
-    MGPU_TRY(stage_out(ctx, out_doc_ids, oD, (size_t)B * k * 16, mem));
-    MGPU_TRY(stage_out(ctx, out_scores, oS, (size_t)B * k * 4, mem));
-    MGPU_TRY(stage_out(ctx, out_counts, oC, (size_t)B * 4, mem));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  MGPU_TRY(shard_exchange(ctx, sl, b, b.locD, b.locS, b.locC, B, kk, oD, oS, oC));
+  if (pp) return pipe_end(ctx, pp, B, k, oD, oS, oC, out_doc_ids, out_scores, out_counts, ticket, sl->ev_xdone);
+  if (mem == MGPU_DEVICE) {
+    // stream-ordered contract: later work on the ctx stream sees the merged result -- unless the caller opted into overlap
+    // (mgpu_shard_overlap), in which case the next batch's kernels run next to this exchange and mgpu_sync completes both
+    if (!ctx->shard_overlap) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, sl->ev_xdone, 0));
+    return MGPU_OK;
   }
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, sl->ev_xdone, 0));
+  MGPU_TRY(stage_out(ctx, out_doc_ids, oD, (size_t)B * k * 16, mem));
+  MGPU_TRY(stage_out(ctx, out_scores, oS, (size_t)B * k * 4, mem));
+  MGPU_TRY(stage_out(ctx, out_counts, oC, (size_t)B * 4, mem));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return MGPU_OK;
 }
 
 int mgpu_shard_ivf_search(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, int shared_codebook,
                           mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, int mem) {
-  return shard_ivf_search_impl(ivf, Q, B, k, nprobe, shared_codebook, out_doc_ids, out_scores, out_counts, mem, nullptr);
+  if (!ivf) return MGPU_ERR_INVALID_ARG;
+  return shard_search_impl(ivf, nullptr, Q, B, k, nprobe, 0, 0, 0.f, shared_codebook, out_doc_ids, out_scores, out_counts, mem, nullptr);
 }
 
 /* Pipelined form for page-locked host buffers (mgpu_search_wait completes it); collective like the blocking call. */
 int mgpu_shard_ivf_search_submit(mgpu_ivf *ivf, const float *Q, uint32_t B, uint32_t k, uint32_t nprobe, int shared_codebook,
                                  mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, uint64_t *ticket) {
   if (!ivf || !ticket) return MGPU_ERR_INVALID_ARG;
-  if (B == 0 || k == 0) {
-    *ticket = 0;
-    return shard_ivf_search_impl(ivf, Q, B, k, nprobe, shared_codebook, out_doc_ids, out_scores, out_counts, MGPU_HOST, nullptr);
-  }
-  return shard_ivf_search_impl(ivf, Q, B, k, nprobe, shared_codebook, out_doc_ids, out_scores, out_counts, MGPU_HOST, ticket);
+  const bool inflight = B != 0 && k != 0;
+  if (!inflight) *ticket = 0;
+  return shard_search_impl(ivf, nullptr, Q, B, k, nprobe, 0, 0, 0.f, shared_codebook, out_doc_ids, out_scores, out_counts, MGPU_HOST,
+                           inflight ? ticket : nullptr);
+}
+
+/* Config 5: Spann::search per doc-shard + exchange. */
+int mgpu_shard_spann_search(mgpu_spann *s, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef, uint32_t num_explored_centroids,
+                            float centroid_distance_ratio, int shared_codebook, mgpu_u128 *out_doc_ids, float *out_scores,
+                            uint32_t *out_counts, int mem) {
+  if (!s) return MGPU_ERR_INVALID_ARG;
+  return shard_search_impl(nullptr, s, Q, B, top_k, 0, ef, num_explored_centroids, centroid_distance_ratio, shared_codebook, out_doc_ids,
+                           out_scores, out_counts, mem, nullptr);
+}
+
+int mgpu_shard_spann_search_submit(mgpu_spann *s, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef,
+                                   uint32_t num_explored_centroids, float centroid_distance_ratio, int shared_codebook,
+                                   mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, uint64_t *ticket) {
+  if (!s || !ticket) return MGPU_ERR_INVALID_ARG;
+  const bool inflight = B != 0 && top_k != 0;
+  if (!inflight) *ticket = 0;
+  return shard_search_impl(nullptr, s, Q, B, top_k, 0, ef, num_explored_centroids, centroid_distance_ratio, shared_codebook, out_doc_ids,
+                           out_scores, out_counts, MGPU_HOST, inflight ? ticket : nullptr);
 }
 
 }  // extern "C"
@@ -1135,8 +1293,18 @@ int mgpu_hnsw_create(mgpu_ctx *ctx, uint32_t dim, uint32_t num_layers, const uin
   if (n_edges && !edges) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "hnsw_create: null edges");
   // edge_offsets = one entry per upper-layer node, then n layer-0 entries, then one terminal entry (hnsw/writer.rs:100-140);
   // level_offsets[num_layers] is n_upper + n in our builders and n_upper + n + 1 in files written by the reference
-  if (level_offsets[num_layers - 1] + n + 1 > n_edge_offsets || level_offsets[num_layers - 1] > n_points)
+  if (level_offsets[num_layers - 1] > n_points || level_offsets[num_layers - 1] >= n_edge_offsets ||
+      n > n_edge_offsets - 1 - level_offsets[num_layers - 1])
     return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "hnsw_create: level_offsets inconsistent with points/edge_offsets");
+  for (uint32_t li = 0; li + 1 < num_layers; li++)
+    if (level_offsets[li + 1] < level_offsets[li]) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "hnsw_create: level_offsets not monotone");
+  // the kernels index `edges` with these: every offset inside the edge array, ascending
+  for (uint64_t i = 0; i < n_edge_offsets; i++)
+    if (edge_offsets[i] > n_edges || (i && edge_offsets[i] < edge_offsets[i - 1]))
+      return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "hnsw_create: edge_offsets[%llu] = %llu is out of order or beyond the %llu edges",
+                       (unsigned long long)i, (unsigned long long)edge_offsets[i], (unsigned long long)n_edges);
+  for (uint64_t i = 0; i < n_edges; i++)
+    if (edges[i] >= n) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "hnsw_create: edge %llu points at %u >= %llu points", (unsigned long long)i, edges[i], (unsigned long long)n);
   std::lock_guard<std::mutex> g(ctx->mu);
   cudaSetDevice(ctx->device);
   mgpu_hnsw *h = new mgpu_hnsw();
@@ -1297,14 +1465,16 @@ __global__ void k_spann_mark_none(const uint32_t *__restrict__ ccounts, uint32_t
 
 static int spann_search_impl(mgpu_spann *sp, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef,
                              uint32_t num_explored_centroids, float ratio, const uint32_t *filter_bits, uint64_t filter_stride,
-                             mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, int mem) {
+                             mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, int mem, bool caller_holds_lock,
+                             const uint8_t *d_qcodes_ext) {
   if (!sp) return MGPU_ERR_INVALID_ARG;
   mgpu_ctx *ctx = sp->ctx;
   mgpu_ivf *ivf = sp->lists;
   mgpu_hnsw *hn = sp->centroids;
   if (B && (!Q || !out_doc_ids || !out_scores || !out_counts)) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "spann_search: null buffer");
   if (top_k > MGPU_MAX_K) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported", top_k, MGPU_MAX_K);
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::unique_lock<std::mutex> g(ctx->mu, std::defer_lock);
+  if (!caller_holds_lock) g.lock();
   cudaSetDevice(ctx->device);
   if (B == 0) return MGPU_OK;
   const uint32_t ne = num_explored_centroids;
@@ -1350,7 +1520,8 @@ static int spann_search_impl(mgpu_spann *sp, const float *Q, uint32_t B, uint32_
   float *oS = mem == MGPU_DEVICE ? out_scores : sS;
   uint32_t *oC = mem == MGPU_DEVICE ? out_counts : sC;
   if (top_k == 0) CUDA_TRY(ctx, cudaMemsetAsync(oC, 0, (size_t)B * 4, ctx->stream));
-  else MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, pr, ne, pc, top_k, dQC, dCK, dCS, nullptr, nullptr, oD, oS, oC, false, dF, filter_stride));
+  else MGPU_TRY(ivf_scan_dev(ivf, (const float *)dQ, B, pr, ne, pc, top_k, d_qcodes_ext ? (uint8_t *)d_qcodes_ext : dQC, dCK, dCS, nullptr, nullptr,
+                             oD, oS, oC, false, dF, filter_stride, false, d_qcodes_ext != nullptr));
   {
     LaunchScope ls(ctx, MGPU_K_OTHER);
     k_spann_mark_none<<<(B + 127) / 128, 128, 0, ctx->stream>>>(cC, B, oC);

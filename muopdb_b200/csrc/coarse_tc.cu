@@ -747,27 +747,33 @@ int launch_split_bf16(mgpu_ctx *ctx, const float *dX, uint64_t n, uint32_t dim, 
   return MGPU_OK;
 }
 
+// Tensor-core squared-L2 estimates D~ (B x C) of B rows against the pre-split centroids: split the rows, then the K = 3*dim
+// bf16 GEMM with the norm terms fused in the epilogue.  d_xsplit: B x Kp bf16; d_xn: B floats (|x|^2).
+int launch_tc_distances(mgpu_ctx *ctx, const float *dX, uint32_t B, const void *d_csplit, const float *d_cn, uint32_t C, uint32_t dim,
+                        void *d_xsplit, float *d_xn, float *d_Dt) {
+  const uint32_t Kp = coarse_tc_kp(dim);
+  MGPU_TRY(launch_split_bf16(ctx, dX, B, dim, 0, d_xsplit, d_xn));
+  CUtensorMap mq, mc;
+  MGPU_TRY(make_map(ctx, &mq, d_xsplit, B, Kp, TC_BM));
+  MGPU_TRY(make_map(ctx, &mc, d_csplit, C, Kp, TC_BN));
+  size_t smem = sizeof(TcSmem) + 1024;
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k_coarse_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((C + TC_BN - 1) / TC_BN, (B + TC_BM - 1) / TC_BM);
+  LaunchScope ls(ctx, MGPU_K_COARSE);
+  k_coarse_gemm<<<grid, TC_THREADS, smem, ctx->stream>>>(mq, mc, d_xn, d_cn, B, C, Kp, d_Dt);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return MGPU_OK;
+}
+
 // d_Dt: B x C floats of workspace; d_qsplit: B x Kp bf16; d_qn: B floats
 int launch_coarse_tc(mgpu_ctx *ctx, const float *dQ, uint32_t B, const float *d_centroids, const void *d_csplit, const float *d_cn,
                      float cn_max, uint32_t C, uint32_t dim, uint32_t nprobe, void *d_qsplit, float *d_qn, float *d_Dt,
                      uint32_t *d_overflow, uint32_t *d_flags, int need_order, uint32_t *out_ids, float *out_dist,
                      const uint32_t *chunk_start, uint32_t *d_work, bool *work_done, cudaEvent_t after_gemm) {
-  const uint32_t Kp = coarse_tc_kp(dim);
   // MGPU_FORK=0: side-stream work (the query encode) starts before the GEMM; 1 (default): after it
   static const int fork_at = getenv("MGPU_FORK") ? atoi(getenv("MGPU_FORK")) : 1;
   if (after_gemm && fork_at == 0) CUDA_TRY(ctx, cudaEventRecord(after_gemm, ctx->stream));
-  MGPU_TRY(launch_split_bf16(ctx, dQ, B, dim, 0, d_qsplit, d_qn));
-  CUtensorMap mq, mc;
-  MGPU_TRY(make_map(ctx, &mq, d_qsplit, B, Kp, TC_BM));
-  MGPU_TRY(make_map(ctx, &mc, d_csplit, C, Kp, TC_BN));
-  size_t smem = sizeof(TcSmem) + 1024;
-  CUDA_TRY(ctx, cudaFuncSetAttribute(k_coarse_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  {
-    dim3 grid((C + TC_BN - 1) / TC_BN, (B + TC_BM - 1) / TC_BM);
-    LaunchScope ls(ctx, MGPU_K_COARSE);
-    k_coarse_gemm<<<grid, TC_THREADS, smem, ctx->stream>>>(mq, mc, d_qn, d_cn, B, C, Kp, d_Dt);
-    CUDA_TRY(ctx, cudaGetLastError());
-  }
+  MGPU_TRY(launch_tc_distances(ctx, dQ, B, d_csplit, d_cn, C, dim, d_qsplit, d_qn, d_Dt));
   if (after_gemm && fork_at != 0) CUDA_TRY(ctx, cudaEventRecord(after_gemm, ctx->stream));  // fork point for work that may overlap the selection
   uint32_t cap = 1;
   while (cap < C) cap <<= 1;

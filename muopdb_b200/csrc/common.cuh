@@ -48,6 +48,15 @@ struct mgpu_ctx {
   void *shard_ws = nullptr; size_t shard_ws_bytes = 0;  // buffers of mgpu_shard_ivf_search (outlive the nested calls' workspace)
   // nccl
   void *nccl_lib = nullptr; void *nccl_comm = nullptr; int nranks = 1, rank = 0;
+  // Result exchange of the sharded searches (all-gather of the per-shard top-k + merge kernel): runs on its own stream and,
+  // when ncclCommSplit is available, on its own communicator, so that batch i's exchange overlaps batch i+1's coarse
+  // scoring and scan (which stay on `stream`; the query-code all-gather of the split encode keeps `nccl_comm`).  Two slots of
+  // per-batch buffers alternate.  ev_local: the shard's local top-k is ready; ev_xdone: the merged result is ready.
+  void *nccl_comm_x = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  struct ShardSlot { void *buf = nullptr; size_t bytes = 0; cudaEvent_t ev_local = nullptr, ev_xdone = nullptr; bool used = false; } shard_slot[2];
+  uint64_t shard_seq = 0;
+  bool shard_overlap = false;   // mgpu_shard_overlap: device-buffer sharded calls return with the exchange still in flight
 };
 
 int mgpu_fail(mgpu_ctx *ctx, int code, const char *fmt, ...);

@@ -243,6 +243,8 @@ int launch_finalize(mgpu_ctx *ctx, const FinalizeArgs &a) {
 
 // ---- merge of S partial top-k lists per query ------------------------------------------------------------------------
 // Concatenate, order by IdWithScore::cmp, truncate to k.  One block per query, rank-by-counting in shared memory.
+// A partial count of UINT32_MAX is Spann::search's `None` (spann/index.rs:229-231): it contributes nothing, and the merged
+// count is UINT32_MAX only when every partial result is None.
 __global__ void k_merge_topk(const mgpu_u128 *__restrict__ docs, const float *__restrict__ scores,
                              const uint32_t *__restrict__ counts, uint32_t S, uint32_t B, uint32_t k,
                              mgpu_u128 *__restrict__ out_docs, float *__restrict__ out_scores,
@@ -255,7 +257,8 @@ __global__ void k_merge_topk(const mgpu_u128 *__restrict__ docs, const float *__
   const uint32_t q = blockIdx.x;
   for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
     uint32_t s = e / k, i = e % k;
-    bool valid = i < counts[(size_t)s * B + q];
+    const uint32_t cs = counts[(size_t)s * B + q];
+    bool valid = cs != 0xFFFFFFFFu && i < cs;
     size_t src = ((size_t)s * B + q) * k + i;
     sd[e] = valid ? docs[src] : mgpu_u128{0, 0};
     sk[e] = valid ? f2key(scores[src]) : 0xFFFFFFFFu;
@@ -278,19 +281,24 @@ __global__ void k_merge_topk(const mgpu_u128 *__restrict__ docs, const float *__
       out_scores[(size_t)q * k + rank] = key2f(sk[e]);
     }
   }
-  if (threadIdx.x == 0) out_counts[q] = total < k ? total : k;
+  if (threadIdx.x == 0) {
+    bool all_none = true;
+    for (uint32_t s = 0; s < S; s++) all_none = all_none && counts[(size_t)s * B + q] == 0xFFFFFFFFu;
+    out_counts[q] = all_none ? 0xFFFFFFFFu : (total < k ? total : k);
+  }
 }
 
 int launch_merge_topk(mgpu_ctx *ctx, const mgpu_u128 *docs, const float *scores, const uint32_t *counts, uint32_t S,
-                      uint32_t B, uint32_t k, mgpu_u128 *out_docs, float *out_scores, uint32_t *out_counts) {
+                      uint32_t B, uint32_t k, mgpu_u128 *out_docs, float *out_scores, uint32_t *out_counts, cudaStream_t st) {
   if (B == 0 || k == 0) return MGPU_OK;
   size_t n = (size_t)S * k;
   size_t smem = n * (sizeof(mgpu_u128) + 8);
   if (smem > ctx->smem_optin) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "merge of %zu candidates per query exceeds shared memory", n);
   CUDA_TRY(ctx, cudaFuncSetAttribute(k_merge_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int threads = n >= 256 ? 256 : (int)((n + 31) / 32 * 32);
-  LaunchScope ls(ctx, MGPU_K_MERGE);
-  k_merge_topk<<<B, threads, smem, ctx->stream>>>(docs, scores, counts, S, B, k, out_docs, out_scores, out_counts);
+  if (!st) st = ctx->stream;
+  LaunchScope ls(ctx, MGPU_K_MERGE, st);
+  k_merge_topk<<<B, threads, smem, st>>>(docs, scores, counts, S, B, k, out_docs, out_scores, out_counts);
   CUDA_TRY(ctx, cudaGetLastError());
   return MGPU_OK;
 }
@@ -301,7 +309,8 @@ int launch_merge_topk(mgpu_ctx *ctx, const mgpu_u128 *docs, const float *scores,
 // point in several probed lists share a composite) is left to the next round, whose scan ignores composites < c32.  A short
 // round has seen every remaining row: everything is reported and later rounds find nothing.
 __global__ void k_round_prepare(uint64_t *__restrict__ cand_key, uint32_t *__restrict__ cand_slot, uint32_t B,
-                                uint64_t *__restrict__ lower_bound) {
+                                uint64_t *__restrict__ lower_bound, uint32_t *__restrict__ reported, uint32_t want,
+                                uint32_t *__restrict__ unfinished) {
   const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (q >= B) return;
@@ -311,16 +320,25 @@ __global__ void k_round_prepare(uint64_t *__restrict__ cand_key, uint32_t *__res
   if (valid == 0xffffffffu) {
     const uint64_t c32 = shfl64(key, 31);
     if (key == c32) cand_slot[(size_t)q * MGPU_NCAND + lane] = MGPU_EMPTY_SLOT;
-    if (lane == 0) lower_bound[q] = c32;
+    const uint32_t nrep = __popc(__ballot_sync(0xffffffffu, key != c32));
+    if (lane == 0) {
+      lower_bound[q] = c32;
+      // per-query count of reported candidates: the host keeps adding rounds until every query that has not seen a short
+      // round holds `want` (= k + spare) of them -- a round that ends inside a group of equal composites reports < 31
+      const uint32_t tot = reported[q] + nrep;
+      reported[q] = tot;
+      if (tot < want) atomicAdd(unfinished, 1u);
+    }
   } else if (lane == 0) {
     lower_bound[q] = MGPU_EMPTY_KEY;
   }
 }
 
-int launch_round_prepare(mgpu_ctx *ctx, uint64_t *cand_key, uint32_t *cand_slot, uint32_t B, uint64_t *lower_bound) {
+int launch_round_prepare(mgpu_ctx *ctx, uint64_t *cand_key, uint32_t *cand_slot, uint32_t B, uint64_t *lower_bound,
+                         uint32_t *reported, uint32_t want, uint32_t *unfinished) {
   if (B == 0) return MGPU_OK;
   LaunchScope ls(ctx, MGPU_K_FINALIZE);
-  k_round_prepare<<<(B + 3) / 4, 128, 0, ctx->stream>>>(cand_key, cand_slot, B, lower_bound);
+  k_round_prepare<<<(B + 3) / 4, 128, 0, ctx->stream>>>(cand_key, cand_slot, B, lower_bound, reported, want, unfinished);
   CUDA_TRY(ctx, cudaGetLastError());
   return MGPU_OK;
 }

@@ -51,6 +51,9 @@ struct mgpu_ivf {
   uint32_t scan_overflow_cap = 0;
   uint32_t scan_bound_probes = 0;        // cache: upper bound of chunks any `scan_bound_probes` lists can hold
   uint64_t scan_bound_chunks = 0;
+  // accessors (index.rs:350-384,469-471), built on first use
+  uint32_t *d_pid_slot = nullptr;        // point id -> one slot holding its row (MGPU_EMPTY_SLOT: in no list)
+  void *doc_map = nullptr;               // host std::unordered_map doc id -> point id (doc_id_to_point_id, index.rs:67-73)
 };
 
 struct mgpu_hnsw {
@@ -84,7 +87,8 @@ struct mgpu_spann {
 
 // ---- candidates produced by a scan: per query 32 (composite key, slot) pairs -------------------
 #define MGPU_NCAND 32
-#define MGPU_MAX_K 2048   /* k > 32 runs ceil((k+16)/31) scan rounds (api.cu: ivf_scan_dev) */
+#define MGPU_MAX_K 2048   /* k > 32 (PQ: k > 16) runs scan rounds until k + 16 candidates are reported (api.cu: ivf_scan_dev) */
+#define MGPU_ROUND_SPARE 16
 
 struct ScanArgs {
   // index
@@ -146,9 +150,10 @@ int launch_select_smallest(mgpu_ctx *ctx, const float *dD, uint32_t B, uint32_t 
 int launch_assign_filter(mgpu_ctx *ctx, const uint32_t *sel_ids, const float *sel_vals, uint64_t n, uint32_t r,
                          float threshold, uint32_t *out_cids, uint32_t *out_counts);
 int launch_merge_topk(mgpu_ctx *ctx, const mgpu_u128 *docs, const float *scores, const uint32_t *counts, uint32_t S,
-                      uint32_t B, uint32_t k, mgpu_u128 *out_docs, float *out_scores, uint32_t *out_counts);
+                      uint32_t B, uint32_t k, mgpu_u128 *out_docs, float *out_scores, uint32_t *out_counts, cudaStream_t st = nullptr);
 // multi-round top-k helpers (finalize.cu)
-int launch_round_prepare(mgpu_ctx *ctx, uint64_t *cand_key, uint32_t *cand_slot, uint32_t B, uint64_t *lower_bound);
+int launch_round_prepare(mgpu_ctx *ctx, uint64_t *cand_key, uint32_t *cand_slot, uint32_t B, uint64_t *lower_bound,
+                         uint32_t *reported, uint32_t want, uint32_t *unfinished);
 int launch_merge_rounds(mgpu_ctx *ctx, const uint32_t *pids, const float *scores, const uint32_t *counts, uint32_t R, uint32_t B,
                         uint32_t k, const mgpu_u128 *doc_ids, uint32_t *out_pids, mgpu_u128 *out_docs, float *out_scores,
                         uint32_t *out_counts);
@@ -162,6 +167,24 @@ int launch_coarse_tc(mgpu_ctx *ctx, const float *dQ, uint32_t B, const float *d_
                      uint32_t *d_overflow, uint32_t *d_flags, int need_order, uint32_t *out_ids, float *out_dist,
                      const uint32_t *chunk_start = nullptr, uint32_t *d_work = nullptr, bool *work_done = nullptr,
                      cudaEvent_t after_gemm = nullptr);
+
+int launch_tc_distances(mgpu_ctx *ctx, const float *dX, uint32_t B, const void *d_csplit, const float *d_cn, uint32_t C, uint32_t dim,
+                        void *d_xsplit, float *d_xn, float *d_Dt);
+
+// build-time kernels (assign.cu)
+int launch_distance_lanes(mgpu_ctx *ctx, const float *dA, uint64_t nA, const float *dB, uint64_t nB, uint32_t dim, int metric,
+                          int lanes, float *dout, int kernel_class);
+int launch_kmeans_argmin(mgpu_ctx *ctx, const float *dD, uint64_t n, uint32_t C, const float *d_pen, uint32_t *d_labels, float *d_costs);
+int launch_kmeans_pick_tc(mgpu_ctx *ctx, const float *d_Dt, const float *dX, const float *d_centroids, const float *d_xn,
+                          const float *d_cn_max, uint64_t n, uint32_t C, uint32_t dim, const float *d_pen, uint32_t *d_labels,
+                          float *d_costs);
+int launch_max_f32(mgpu_ctx *ctx, const float *d_v, uint32_t n, float *d_out);
+int launch_pq_original(mgpu_pq *pq, const uint8_t *d_codes, uint64_t n, float *d_out);
+int launch_gather_docs(mgpu_ctx *ctx, const mgpu_u128 *d_doc_ids, const uint32_t *d_pids, uint32_t n, uint64_t nvec, mgpu_u128 *d_out,
+                       uint32_t *d_bad);
+int launch_gather_rows(mgpu_ivf *ivf, const uint32_t *d_pids, uint32_t n, void *d_out, uint32_t *d_bad);
+int ivf_ensure_pid_slot(mgpu_ivf *ivf);
+void ivf_free_doc_map(mgpu_ivf *ivf);
 
 struct HnswSearchArgs {
   const float *Q; uint32_t B, k, ef;

@@ -46,6 +46,8 @@ __host__ __device__ inline ScanSmemLayout scan_layout(int mode, uint32_t dim, ui
 template <int MODE, int NG, int NT>
 __global__ void __launch_bounds__(NT, 1) k_scan(ScanArgs a, ScanSmemLayout L) {
   constexpr int SCAN_THREADS = NT, SCAN_WARPS = NT / 32;
+  // the "max over warps of their 2nd best" threshold bounds the global 32nd best only with >= 16 warps
+  static_assert(2 * SCAN_WARPS >= MGPU_NCAND && SCAN_WARPS <= SCAN_MAX_WARPS, "threshold rule needs 16..32 warps");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *pol = smem;
   float *tmp = (float *)(smem + L.off_tmp);

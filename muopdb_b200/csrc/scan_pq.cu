@@ -86,6 +86,8 @@ struct DbConsumerCtx {
   __device__ __forceinline__ void offer_rows(WarpTop32 &top, bool &first, bool pass, uint32_t key, uint32_t pid, uint32_t slot,
                                              uint32_t thr) {
     constexpr int NCW_ = NCW;
+    // "max over warps of their 2nd best" bounds the global 32nd best only if the warps' two best already are >= 32 rows
+    static_assert(2 * NCW >= MGPU_NCAND && NCW <= 32, "threshold rule needs 16..32 consumer warps");
     uint32_t worst;
 #ifdef MGPU_SCAN_DBG
     { unsigned mm = __ballot_sync(0xffffffffu, pass); if (lane == 0) { atomicAdd(&g_dbg[0], 1ull); atomicAdd(&g_dbg[1], (unsigned long long)__popc(mm)); if (first) atomicAdd(&g_dbg[2], 1ull);} }
@@ -509,8 +511,6 @@ int launch_scan_pq_db(mgpu_ivf *ivf, const ScanArgs &a) {
       // measured on B200 (profiles/): 16 consumer + 4 producer warps (96 registers, no spills) is the best split
       switch (cfg) {
         case 1: return launch_db_t<3, 20, 4>(ivf, a);
-        case 2: return launch_db_t<3, 12, 4>(ivf, a);
-        case 3: return launch_db_t<3, 12, 8>(ivf, a);
         case 4: return launch_db_t<3, 16, 8>(ivf, a);
         default: return launch_db_t<3, 16, 4>(ivf, a);
       }

@@ -44,22 +44,3 @@ def init_comm(ctx, dist=None):
     dist.broadcast_object_list(obj, src=0)
     ctx.comm_init(world, rank, obj[0])
     return world, rank
-
-
-class ShardedSearcher:
-    """Wraps a rank-local index with the all-gather + merge exchange."""
-
-    def __init__(self, local_index, ctx):
-        self.local, self.ctx = local_index, ctx
-
-    def search_batch(self, Q_dev, k: int, local_search, out=None):
-        """local_search(Q_dev) -> BatchResult of device tensors for this shard; returns merged device tensors."""
-        import torch
-        r = local_search(Q_dev)
-        B = Q_dev.shape[0]
-        if out is None:
-            out = (torch.zeros((B, k, 2), dtype=torch.int64, device=Q_dev.device),
-                   torch.zeros((B, k), dtype=torch.float32, device=Q_dev.device),
-                   torch.zeros((B,), dtype=torch.int32, device=Q_dev.device))
-        self.ctx.shard_allgather_merge(r.doc_ids, r.scores, r.counts, B, k, *out)
-        return out

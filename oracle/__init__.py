@@ -94,7 +94,9 @@ def _declare(L):
     L.orc_ivf_assign.restype = None
     L.orc_ivf_assign.argtypes = [_f32p, C.c_uint64, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, _u32p, _u32p]
     L.orc_kmeans_assign.restype = None
-    L.orc_kmeans_assign.argtypes = [_f32p, C.c_uint64, _f32p, C.c_uint32, C.c_uint32, _f32p, _u32p]
+    L.orc_kmeans_assign.argtypes = [_f32p, C.c_uint64, _f32p, C.c_uint32, C.c_uint32, C.c_int, _f32p, _u32p, _f32p]
+    L.orc_lane_conforming_batch.restype = None
+    L.orc_lane_conforming_batch.argtypes = [_f32p, C.c_uint64, _f32p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, _f32p]
     L.orc_hnsw_new.restype = C.c_void_p
     L.orc_hnsw_new.argtypes = [C.c_uint32, C.c_uint32, _u32p, _u32p, _u64p, C.c_uint64, _u64p, C.c_int, C.c_int,
                                C.c_void_p, C.c_uint64, _u64p, _f32p, C.c_uint32, C.c_uint32]
@@ -350,12 +352,22 @@ def build_posting_lists(X, centroids, max_clusters=1, threshold=0.1):
     return offsets, ids
 
 
-def kmeans_assign(X, centroids, penalties=None):
+def kmeans_assign(X, centroids, penalties=None, metric=L2, with_costs=False):
+    """Assignment step of KMeansBuilder::run_lloyd (kmeans_builder.rs:199-221), calculator chosen by dimension (:126-136)."""
     X, centroids = _f32(X), _f32(centroids)
     out = np.empty(X.shape[0], dtype=np.uint32)
+    costs = np.empty(X.shape[0], dtype=np.float32)
     pen = _f32(penalties) if penalties is not None else None
-    lib().orc_kmeans_assign(_p(X, _f32p), X.shape[0], _p(centroids, _f32p), centroids.shape[0], X.shape[1],
-                            _p(pen, _f32p), _p(out, _u32p))
+    lib().orc_kmeans_assign(_p(X, _f32p), X.shape[0], _p(centroids, _f32p), centroids.shape[0], X.shape[1], metric,
+                            _p(pen, _f32p), _p(out, _u32p), _p(costs, _f32p))
+    return (out, costs) if with_costs else out
+
+
+def lane_conforming_batch(A, B, lanes, metric=L2):
+    """All pairs of LaneConformingDistanceCalculator<LANES, D>::calculate_squared (lane_conforming.rs:16-27)."""
+    A, B = _f32(A), _f32(B)
+    out = np.empty((A.shape[0], B.shape[0]), dtype=np.float32)
+    lib().orc_lane_conforming_batch(_p(A, _f32p), A.shape[0], _p(B, _f32p), B.shape[0], A.shape[1], lanes, metric, _p(out, _f32p))
     return out
 
 

@@ -566,20 +566,39 @@ ORC_API void orc_ivf_assign(const float *X, uint64_t n, const float *centroids, 
   }
 }
 
-/* k-means assignment step of KMeansBuilder::run_lloyd (kmeans_builder.rs:199-221):
- * argmin_c (||x-c||^2 + penalty_c), first minimum wins.  penalties may be NULL (=0). */
-ORC_API void orc_kmeans_assign(const float *X, uint64_t n, const float *centroids, uint32_t nlist, uint32_t dim,
-                               const float *penalties, uint32_t *out) {
+/* Assignment step of KMeansBuilder::run_lloyd (kmeans_builder.rs:199-221): per point
+ * argmin_c (T::calculate_squared(x, c) + penalties[c]) folded from (0, f32::MAX) with a strict '<'
+ * (first minimum wins; a NaN cost is never taken).  T is chosen by the dimension (kmeans_builder.rs:126-136):
+ * LaneConformingDistanceCalculator<16|8|4, D> when dim % 16|8|4 == 0, else D itself.
+ * metric: 0 = L2, 1 = dot.  out_costs (may be NULL) = the winning cost (distance + penalty). */
+static inline float kmeans_cost(const float *x, const float *c, uint32_t dim, int metric) {
+  int lanes = dim % 16 == 0 ? 16 : (dim % 8 == 0 ? 8 : (dim % 4 == 0 ? 4 : 0));
+  if (lanes) return orc_lane_conforming(x, c, dim, lanes, metric);
+  return metric == 0 ? orc_l2_squared(x, c, dim) : orc_dot(x, c, dim);
+}
+
+ORC_API void orc_kmeans_assign(const float *X, uint64_t n, const float *centroids, uint32_t nlist, uint32_t dim, int metric,
+                               const float *penalties, uint32_t *out, float *out_costs) {
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < (int64_t)n; i++) {
     float best = 3.40282347e+38f; uint32_t bi = 0;
     for (uint32_t c = 0; c < nlist; c++) {
-      float d = orc_l2_squared(X + (size_t)i * dim, centroids + (size_t)c * dim, dim);
-      if (penalties) d = d + penalties[c];
+      float d = kmeans_cost(X + (size_t)i * dim, centroids + (size_t)c * dim, dim, metric);
+      d = d + (penalties ? penalties[c] : 0.0f);   /* penalties default to 0.0 (kmeans_builder.rs:183-189) */
       if (d < best) { best = d; bi = c; }
     }
     out[i] = bi;
+    if (out_costs) out_costs[i] = best;
   }
+}
+
+/* Batched all-pairs LaneConformingDistanceCalculator<LANES, D>::calculate_squared (what mgpu_distance_batch_lanes computes). */
+ORC_API void orc_lane_conforming_batch(const float *A, uint64_t nA, const float *B, uint64_t nB, uint32_t dim, int lanes,
+                                       int metric, float *out) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)nA; i++)
+    for (uint64_t j = 0; j < nB; j++)
+      out[(size_t)i * nB + j] = orc_lane_conforming(A + (size_t)i * dim, B + j * dim, dim, lanes, metric);
 }
 
 /* ------------------------------------------------------------------------- */

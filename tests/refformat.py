@@ -74,8 +74,26 @@ def write_pq_dir(dirpath, dimension, subvector_dimension, num_bits, codebook):
     np.ascontiguousarray(codebook, dtype="<f4").tofile(os.path.join(dirpath, "codebook"))
 
 
+def ivf_combine_files(num_features, quantized_dimension, num_clusters, num_vectors, doc_id_mapping: bytes, centroids: bytes,
+                      posting_list_metadata: bytes, posting_lists: bytes, lens=None) -> bytes:
+    """IvfWriter::write_header + combine_files (ivf/writer.rs:300-353), byte for byte: 45-byte header, pad to 16,
+    doc_id_mapping, centroids (no padding in between: "doc_id_mapping is always 8-byte aligned"), pad to 8,
+    posting_list_metadata, posting_lists.  `lens` overrides the three section lengths stored in the header (the reference's
+    test_combine_files writes a hand-made header)."""
+    dl, cl, pl = lens or (len(doc_id_mapping), len(centroids), len(posting_list_metadata) + len(posting_lists))
+    out = bytearray(struct.pack("<BIIIQQQQ", 0, num_features, quantized_dimension, num_clusters, num_vectors, dl, cl, pl))
+    assert len(out) == 45
+    _pad(out, 16)
+    out += doc_id_mapping
+    out += centroids
+    _pad(out, 8)
+    out += posting_list_metadata
+    out += posting_lists
+    return bytes(out)
+
+
 def ivf_index_bytes(centroids, list_offsets, list_ids, doc_ids, quantized_dimension) -> bytes:
-    """IvfWriter::combine_files (ivf/writer.rs:300-353)."""
+    """The sections IvfWriter::write produces (ivf/writer.rs:228-298), combined by ivf_combine_files."""
     centroids = np.ascontiguousarray(centroids, dtype="<f4")
     nlist, dim = centroids.shape
     n = len(doc_ids)
@@ -90,15 +108,7 @@ def ivf_index_bytes(centroids, list_offsets, list_ids, doc_ids, quantized_dimens
         enc = ef_encode(ids, ids[-1] if ids else 0)
         meta += struct.pack("<QQ", len(enc), len(payload))
         payload += enc
-    pl = bytes(meta) + bytes(payload)
-    out = bytearray(struct.pack("<BIIIQQQQ", 0, dim, quantized_dimension, nlist, n, len(doc), len(cent), len(pl)))
-    assert len(out) == 45
-    _pad(out, 16)
-    out += doc
-    out += cent
-    _pad(out, 8)
-    out += pl
-    return bytes(out)
+    return ivf_combine_files(dim, quantized_dimension, nlist, n, bytes(doc), cent, bytes(meta), bytes(payload))
 
 
 def write_ivf_dir(base, centroids, list_offsets, list_ids, rows, doc_ids, prefix_bytes=0):
@@ -139,3 +149,85 @@ def write_hnsw_dir(base, num_layers, edges, points, edge_offsets, level_offsets,
     with open(os.path.join(base, "hnsw", "index"), "wb") as f:
         f.write(hnsw_index_bytes(num_layers, edges, points, edge_offsets, level_offsets, doc_ids, rows.shape[1]))
     write_vector_file(os.path.join(base, "hnsw", "vector_storage"), rows)
+
+
+# ---- multi-user SPANN files (rs/index/src/multi_spann/writer.rs:75-260) ---------------------------------------------------------
+def user_index_info_bytes(info: dict) -> bytes:
+    """UserIndexInfo::to_le_bytes (multi_spann/user_index_info.rs:26-42): u128 user id + 12 u64, little endian, 112 bytes."""
+    names = ["centroid_vector_offset", "centroid_vector_len", "centroid_index_offset", "centroid_index_len", "ivf_vectors_offset",
+             "ivf_vectors_len", "ivf_raw_vectors_offset", "ivf_raw_vectors_len", "ivf_index_offset", "ivf_index_len",
+             "ivf_pq_codebook_offset", "ivf_pq_codebook_len"]
+    return _u128(info["user_id"]) + struct.pack("<12Q", *[int(info.get(n, 0)) for n in names])
+
+
+def odht_table_bytes(infos) -> bytes:
+    """An odht 0.3.1 HashTableOwned<HashConfig> image holding the records (layout restated from the crate's published
+    format; odht is not part of the reference checkout, so slot placement does NOT follow its FxHash probing -- the loader
+    under test scans the control bytes and needs no hash).  32-byte header, slot_count x (16-byte key | 112-byte value),
+    slot_count + 16 control bytes (0xFF = empty, 7 hash bits = full)."""
+    n = len(infos)
+    slots = 16
+    while slots * 7 // 8 < n:
+        slots *= 2
+    entries = bytearray(slots * 128)
+    ctrl = bytearray([0xFF] * (slots + 16))
+    for i, info in enumerate(infos):
+        slot = (i * 5 + 3) % slots
+        while ctrl[slot] != 0xFF:
+            slot = (slot + 1) % slots
+        entries[slot * 128:slot * 128 + 16] = _u128(info["user_id"])
+        entries[slot * 128 + 16:slot * 128 + 128] = user_index_info_bytes(info)
+        ctrl[slot] = (info["user_id"] * 0x9E) & 0x7F
+        if slot < 16:
+            ctrl[slots + slot] = ctrl[slot]   # the trailing group mirrors the first 16 control bytes
+    header = b"ODHT" + bytes([1, 16, 112, 32]) + struct.pack("<QQ", n, slots) + struct.pack("<IHH", 0, 0xE000, 0)
+    assert len(header) == 32
+    return header + bytes(entries) + bytes(ctrl)
+
+
+def _append_padded(f, payload: bytes, align: int) -> int:
+    """write_pad + append (multi_spann/writer.rs:151-165): returns the offset the payload starts at."""
+    pos = f.tell()
+    f.write(b"\0" * ((align - pos % align) % align))
+    off = f.tell()
+    f.write(payload)
+    return off
+
+
+def write_multi_spann_dir(base, users, pq=None):
+    """MultiSpannWriter::write's combined layout for `users` = {user_id: dict(hnsw=(num_layers, edges, points, edge_offsets,
+    level_offsets), centroids=(nlist, dim) f32, offsets, ids, rows, doc_ids)}: per-user sections appended to
+    {base}/centroids/hnsw/{index,vector_storage} (16 / 8 byte aligned) and {base}/ivf/{index,vectors} (16 / 8), per-user
+    codebooks appended to {base}/ivf/quantizer/codebook, offsets recorded in {base}/user_index_info.
+    pq = (dimension, subvector_dimension, num_bits, {user_id: codebook})."""
+    os.makedirs(os.path.join(base, "centroids", "hnsw"), exist_ok=True)
+    os.makedirs(os.path.join(base, "ivf", "quantizer"), exist_ok=True)
+    infos = []
+    with open(os.path.join(base, "centroids", "hnsw", "index"), "wb") as f_ci, \
+            open(os.path.join(base, "centroids", "hnsw", "vector_storage"), "wb") as f_cv, \
+            open(os.path.join(base, "ivf", "index"), "wb") as f_ii, open(os.path.join(base, "ivf", "vectors"), "wb") as f_iv, \
+            open(os.path.join(base, "ivf", "quantizer", "codebook"), "wb") as f_cb:
+        for uid in sorted(users):
+            u = users[uid]
+            nl, edges, points, eo, lo = u["hnsw"]
+            cents = np.ascontiguousarray(u["centroids"], dtype="<f4")
+            rows = np.ascontiguousarray(u["rows"])
+            info = {"user_id": uid}
+            b = hnsw_index_bytes(nl, edges, points, eo, lo, list(range(cents.shape[0])), cents.shape[1])
+            info["centroid_index_offset"] = _append_padded(f_ci, b, 16); info["centroid_index_len"] = len(b)
+            b = struct.pack("<Q", cents.shape[0]) + cents.tobytes()
+            info["centroid_vector_offset"] = _append_padded(f_cv, b, 8); info["centroid_vector_len"] = len(b)
+            b = ivf_index_bytes(cents, u["offsets"], u["ids"], u["doc_ids"], rows.shape[1])
+            info["ivf_index_offset"] = _append_padded(f_ii, b, 16); info["ivf_index_len"] = len(b)
+            b = struct.pack("<Q", rows.shape[0]) + rows.tobytes()
+            info["ivf_vectors_offset"] = _append_padded(f_iv, b, 8); info["ivf_vectors_len"] = len(b)
+            if pq:
+                b = np.ascontiguousarray(pq[3][uid], dtype="<f4").tobytes()
+                info["ivf_pq_codebook_offset"] = _append_padded(f_cb, b, 8); info["ivf_pq_codebook_len"] = len(b)
+            infos.append(info)
+    if pq:
+        with open(os.path.join(base, "ivf", "quantizer", "product_quantizer_config.yaml"), "w") as f:
+            f.write(f"dimension: {pq[0]}\nsubvector_dimension: {pq[1]}\nnum_bits: {pq[2]}\n")
+    with open(os.path.join(base, "user_index_info"), "wb") as f:
+        f.write(odht_table_bytes(infos))
+    return infos

@@ -44,6 +44,97 @@ def test_elias_fano_round_trips(n, universe_bits):
     assert M.elias_fano_decode(RF.ef_encode([])).tolist() == []
 
 
+# ---- IVF `index` file layout (CPU) ------------------------------------------------------------------------------------------
+def test_ivf_combine_files_reference_golden_bytes():
+    """rs/index/src/ivf/writer.rs:383-487 (test_combine_files) restated byte for byte: header fields little-endian in the
+    order version u8 | num_features u32 | quantized_dimension u32 | num_clusters u32 | num_vectors u64 | doc_id_mapping_len u64 |
+    centroids_len u64 | posting_lists_and_metadata_len u64, zero padding to the next multiple of 8 (48), then doc_id_mapping,
+    centroids WITHOUT padding in between, zero padding to 8, posting_list_metadata, posting_lists.  tests/refformat.py's IVF
+    writer (which the loader tests read back) is built on this function."""
+    out = RF.ivf_combine_files(10, 10, 5, 4, bytes([100, 101, 102, 103]), bytes([5, 6, 7, 8]), bytes([1, 2, 3, 4]),
+                               bytes([9, 10, 11, 12]), lens=(4, 4, 4))
+    expected_header = [0, 10, 0, 0, 0, 10, 0, 0, 0, 5, 0, 0, 0] + [4, 0, 0, 0, 0, 0, 0, 0] * 4
+    while len(expected_header) % 8:
+        expected_header.append(0)
+    assert list(out[:len(expected_header)]) == expected_header and len(expected_header) == 48
+    off = len(expected_header)
+    assert list(out[off:off + 4]) == [100, 101, 102, 103]
+    assert list(out[off + 4:off + 8]) == [5, 6, 7, 8]
+    nxt = off + 8
+    while nxt % 8:
+        assert out[nxt] == 0
+        nxt += 1
+    assert list(out[nxt:nxt + 4]) == [1, 2, 3, 4]
+    assert list(out[nxt + 4:nxt + 8]) == [9, 10, 11, 12]
+    assert len(out) == nxt + 8   # bytes_written == file length
+
+
+def test_ivf_index_sections_follow_the_reader_offsets():
+    """IvfStorage::new_with_offset (ivf/block_based/storage.rs:52-97) finds the sections of a real file at: doc ids at
+    align16(45); centroids at align8(doc end); posting-list table at align8(centroid end), u64 count first; list i at
+    table end + offset_i.  Checked on a file from the refformat writer, with independent struct arithmetic."""
+    cents = np.arange(15, dtype=np.float32).reshape(3, 5)   # odd nlist * dim: the pad-to-8 after the centroids is real
+    offsets, ids = np.array([0, 2, 2, 5], dtype=np.uint64), np.array([1, 4, 0, 2, 3], dtype=np.uint32)
+    docs = [7, 1 << 70, 9, 11, 13]
+    b = RF.ivf_index_bytes(cents, offsets, ids, docs, 5)
+    ver, nf, qd, nc, nv, dl, cl, pl = struct.unpack_from("<BIIIQQQQ", b, 0)
+    assert (ver, nf, qd, nc, nv) == (0, 5, 5, 3, 5) and dl == 16 * 6 and cl == 8 + 3 * 5 * 4
+    doc_off = 48
+    assert struct.unpack_from("<QQ", b, doc_off) == (5, 0)                       # u128 count
+    assert struct.unpack_from("<QQ", b, doc_off + 16 * 2) == (0, 1 << 6)         # doc id 1 << 70 = hi word 64
+    cent_off = (doc_off + dl + 7) & ~7
+    assert struct.unpack_from("<Q", b, cent_off)[0] == 3
+    assert np.array_equal(np.frombuffer(b, "<f4", 15, cent_off + 8), cents.reshape(-1))
+    meta_off = (cent_off + cl + 7) & ~7
+    assert meta_off != cent_off + cl and struct.unpack_from("<Q", b, meta_off)[0] == 3
+    table = [struct.unpack_from("<QQ", b, meta_off + 8 + 16 * i) for i in range(3)]
+    start = meta_off + 8 + 16 * 3
+    assert len(b) == meta_off + pl
+    import muopdb_b200 as M
+    got = [M.elias_fano_decode(b[start + o:start + o + ln]).tolist() for ln, o in table]
+    assert got == [[1, 4], [], [0, 2, 3]]
+
+
+# ---- multi-user offset table (CPU) ---------------------------------------------------------------------------------------------
+def test_user_index_info_serialization():
+    """rs/index/src/multi_spann/user_index_info.rs:143-203 (test_user_index_info_serialization): to_le_bytes/from_le_bytes
+    round trip, plus the byte layout itself (u128 user id, then the 12 u64 in declaration order)."""
+    import muopdb_b200 as M
+    info = M.UserIndexInfo(1234567890, 100, 200, 300, 400, 500, 600, 700, 800, 900, 1000, 1100, 1200)
+    b = info.to_le_bytes()
+    assert len(b) == 112
+    assert b == struct.pack("<QQ", 1234567890, 0) + struct.pack("<12Q", *range(100, 1300, 100))
+    assert M.UserIndexInfo.from_le_bytes(b) == info
+    wide = M.UserIndexInfo((1 << 100) + 5, ivf_index_offset=1 << 40)
+    assert M.UserIndexInfo.from_le_bytes(wide.to_le_bytes()) == wide
+
+
+def test_user_index_info_table_scan(tmp_path):
+    """`user_index_info` is an odht table image (multi_spann/reader.rs:40-50, index.rs:50,104-108).  odht 0.3.1 is a third-party
+    crate absent from the reference checkout, so this pins the reader against an image built from the crate's published
+    layout (tests/refformat.py:odht_table_bytes), its item count and the key == user_id invariant -- parity UNPINNED."""
+    import muopdb_b200 as M
+    M64 = (1 << 64) - 1
+    infos = [{"user_id": u, "ivf_index_offset": (16 * u) & M64, "centroid_index_offset": (32 * u + 1) & M64, "ivf_pq_codebook_len": u & M64}
+             for u in (3, (1 << 80) + 6, 77, 12, 5000, 9, 10, 11, 13, 14, 15, 16, 17, 18, 19)]
+    p = tmp_path / "user_index_info"
+    p.write_bytes(RF.odht_table_bytes(infos))
+    got = M.UserIndexInfo.read_table(str(p))
+    assert sorted(got) == sorted(i["user_id"] for i in infos)
+    for i in infos:
+        g = got[i["user_id"]]
+        assert (g.ivf_index_offset, g.centroid_index_offset, g.ivf_pq_codebook_len) == \
+            (i["ivf_index_offset"], i["centroid_index_offset"], i["ivf_pq_codebook_len"])
+    raw = bytearray(RF.odht_table_bytes(infos))
+    raw[8] ^= 1                       # item count no longer matches the occupied slots
+    p.write_bytes(bytes(raw))
+    with pytest.raises(M.InvalidArgument):
+        M.UserIndexInfo.read_table(str(p))
+    p.write_bytes(RF.odht_table_bytes(infos)[:200])
+    with pytest.raises(M.InvalidArgument):
+        M.UserIndexInfo.read_table(str(p))
+
+
 # ---- loaders (GPU) ----------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_hnsw_loader_parses_reference_written_file():

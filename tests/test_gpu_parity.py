@@ -110,8 +110,8 @@ def _check_ivf(M, X, nlist, nprobe, k, pq_params=None, max_clusters=1, metric="l
     assert givf.num_clusters() == nlist and givf.num_vectors() == len(X)
     if invalidate is not None:
         oivf.invalidate_batch(invalidate)
-        givf.invalidate_batch(invalidate)
-        assert givf.is_invalidated(int(invalidate[0]))
+        givf.invalidate_points(invalidate)
+        assert givf.is_point_invalidated(int(invalidate[0]))
     Q = queries if queries is not None else np.vstack([X[:nq // 2] + 0.01 * rng.standard_normal((nq // 2, dim)).astype(np.float32),
                                                          rng.random((nq - nq // 2, dim), dtype=np.float32)])
     # coarse: identical probe lists (distances are bit-exact, ties by centroid index on both sides)
@@ -426,7 +426,7 @@ def test_ivf_planner_filter_parity(M, pq, on_device):
     rng = np.random.default_rng(9)
     Q = (X[100:164] + 0.01).astype(np.float32)
     B, n = len(Q), len(X)
-    oivf.invalidate_batch([101, 105, 3000]); givf.invalidate_batch([101, 105, 3000])
+    oivf.invalidate_batch([101, 105, 3000]); givf.invalidate_points([101, 105, 3000])
     Qg = Q
     if on_device:
         import torch
@@ -635,6 +635,35 @@ def test_ivf_large_k_with_duplicates_and_invalidation(M):
     inv = np.arange(3, 1200, 11, dtype=np.uint32)
     _check_ivf(M, X, nlist=6, nprobe=6, k=48, pq_params=(8, 8), max_clusters=2, invalidate=inv, seed=18)
     _check_ivf(M, X, nlist=6, nprobe=4, k=120, max_clusters=2, invalidate=inv, seed=19)
+
+
+@pytest.mark.parametrize("k,pq", [(1000, None), (2048, None), (1000, (8, 8)), (24, (8, 8)), (32, (8, 8))])
+def test_ivf_large_k_every_point_in_two_probed_lists(M, k, pq):
+    """ADVICE r1 (api.cu multi-round top-k): with every point living in two probed lists each composite occurs twice, a
+    round that ends inside a pair reports 30 instead of 31 candidates and a fixed ceil((k+16)/31) rounds came back short
+    (k = 1000 -> 990).  The rounds now run until k + 16 candidates are reported; the reference keeps both copies of a point
+    (no de-dup, index.rs:265-274).  k = 24 / 32 with PQ: the k > 16 PQ searches take the same path (spare candidates for
+    swaps between the fixed-point ranking and the exact scores)."""
+    X = synth.clustered(3200, 64, n_blobs=4, seed=k)
+    cents, offsets, ids = synth.build_ivf_arrays(X, 4, seed=k + 1, max_clusters=2, threshold=1e9)
+    assert offsets[-1] == 2 * len(X)
+    docs = synth.doc_ids_for(len(X), seed=k + 2)
+    if pq:
+        cb = O.train_pq_codebook(X[:1500], pq[0], pq[1], iters=3, seed=k)
+        opq, gq = O.ProductQuantizer(64, pq[0], pq[1], cb), M.ProductQuantizer(64, pq[0], pq[1], cb)
+        rows = opq.quantize(X)
+        oivf = O.Ivf(cents, offsets, ids, rows, doc_ids=docs, pq=opq)
+    else:
+        rows, gq = X, M.NoQuantizer(64)
+        oivf = O.Ivf(cents, offsets, ids, rows, doc_ids=docs)
+    givf = M.BlockBasedIvf(cents, offsets, ids, rows, gq, doc_ids=docs)
+    Q = (X[:6] + 0.01).astype(np.float32)
+    od, os_, oc = oivf.search_batch(Q, k, 4)
+    res = givf.search_batch(Q, k, 4)
+    assert np.array_equal(np.asarray(res.counts, dtype=np.int64), oc.astype(np.int64)) and int(oc.min()) == k
+    for b in range(len(Q)):
+        assert np.array_equal(res.doc_ids[b], od[b]), b
+        assert _same_f32(res.scores[b], os_[b]), b
 
 
 def test_k_above_limit_is_rejected(M):

@@ -5,6 +5,8 @@ k_merge_rounds), checked against a plain sort.  It pins the round rule independe
     its 32 smallest composites (duplicates of one point in several probed lists share a composite and are all kept);
   * a full round REPORTS the entries strictly below its last composite c32 and sets the bound to c32, so the group equal to
     c32 is re-scanned as a whole by the next round; a short round reports everything and ends the search;
+  * rounds continue until k + 16 candidates are reported (a round that ends inside a group of equal composites reports
+    fewer than 31, so the count is tracked instead of assuming 31 per round), up to the hard cap 2 * ceil((k+16)/31) + 2;
   * the union of the reported entries, ordered by (key, point id), is the reference's bounded heap (index.rs:265-274).
 """
 import numpy as np
@@ -13,24 +15,35 @@ import pytest
 NCAND = 32
 
 
-def rounds_needed(k):
-    return (k + 16 + 30) // 31
+SPARE = 16
 
 
-def round_topk(comp, k):
+def rounds_nominal(k):
+    return (k + SPARE + 30) // 31
+
+
+def rounds_cap(k):
+    return 2 * rounds_nominal(k) + 2
+
+
+def round_topk(comp, k, return_rounds=False):
     """comp: 1-d uint64 array of composites (may contain equal values).  Returns the reported composites, sorted."""
     bound = np.uint64(0)
     reported = []
-    for _ in range(rounds_needed(k)):
+    rounds = 0
+    while rounds < rounds_cap(k):
+        rounds += 1
         visible = np.sort(comp[comp >= bound])[:NCAND]
         if len(visible) == NCAND:
             c32 = visible[-1]
             reported.extend(visible[visible < c32].tolist())
             bound = c32
+            if len(reported) >= k + SPARE:
+                break
         else:
             reported.extend(visible.tolist())
-            bound = np.uint64(0xFFFFFFFFFFFFFFFF)
-    return sorted(reported)
+            break
+    return (sorted(reported), rounds) if return_rounds else sorted(reported)
 
 
 @pytest.mark.parametrize("k", [33, 40, 64, 100, 257, 1000])
@@ -44,6 +57,19 @@ def test_rounds_cover_the_k_smallest(k, n):
     got = round_topk(comp, k)
     want = np.sort(comp)[:k].tolist()
     assert got[:min(k, n)] == want[:min(k, n)]
+
+
+@pytest.mark.parametrize("k", [100, 1000, 2048])
+def test_every_point_in_two_probed_lists_still_yields_k(k):
+    """with every composite duplicated a round ending inside a pair reports 30, not 31; a fixed
+    ceil((k+16)/31) rounds then returned fewer than k entries although enough rows exist."""
+    rng = np.random.default_rng(k)
+    n = 3 * k
+    half = (rng.permutation(n).astype(np.uint64) << np.uint64(32)) | np.arange(n, dtype=np.uint64)
+    comp = np.concatenate([half, half])
+    got, rounds = round_topk(comp, k, return_rounds=True)
+    assert got[:k] == np.sort(comp)[:k].tolist()
+    assert rounds_nominal(k) <= rounds <= rounds_cap(k)
 
 
 def test_boundary_group_is_carried_as_a_whole():

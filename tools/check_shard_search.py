@@ -4,8 +4,11 @@
 Every rank builds its doc-shard (doc_id mod N) of one seeded collection with a shared PQ codebook and compares
   (a) mgpu_shard_ivf_search (split query encode + code all-gather + local search + result all-gather + merge), host and
       device buffers, with
-  (b) the CPU oracle: per-shard oracle searches merged with the leaf ordering of snapshot.rs:60-61.
-Bit-exact doc ids and scores are required on every rank."""
+  (b) the CPU oracle: per-shard oracle searches merged with the leaf ordering of snapshot.rs:60-61;
+and the same for mgpu_shard_spann_search (config 5: centroid HNSW -> ratio prune -> PQ lists per shard), including the
+overlapped device-buffer mode (mgpu_shard_overlap) and the pipelined host-buffer form.
+Bit-exact doc ids and scores are required on every rank.  Rank 0 prints one JSON line (kept under profiles/)."""
+import json
 import os
 import sys
 
@@ -87,10 +90,61 @@ def main():
         ok &= same(M.BatchResult(o[0].numpy(), o[1].numpy(), o[2].numpy()), False, 'pipelined')
     # and without the split encode (every rank encodes every query): same answer
     ok &= same(givf.shard_search_batch(Q, k, nprobe, shared_codebook=False), False, 'nosplit')
+    # overlapped device-buffer mode: three calls back to back, their exchanges in flight next to the following searches
+    ctx.shard_overlap(True)
+    Qd = torch.from_numpy(Q).cuda()
+    rs = [givf.shard_search_batch(Qd, k, nprobe, shared_codebook=True) for _ in range(3)]
+    for r in rs:
+        ok &= same(r, True, 'overlap')
+    ctx.shard_overlap(False)
+    ivf_ok = ok
+
+    # ---- config 5: SPANN per shard (centroid HNSW with NoQuantizer<L2> over the shard's centroids + the PQ lists above)
+    ne, ratio, ef = 6, 0.4, 40
+    graphs = [O.hnsw_build(sh[0], 8, 2, 60, seed=3 + r) for r, sh in enumerate(shards)]
+    per = []
+    for (c2, o2, i2, cd2, p2, q2), g in zip(shards, graphs):
+        osp = O.Spann(O.Hnsw(g["num_layers"], g["edges"], g["points"], g["edge_offsets"], g["level_offsets"], c2),
+                      O.Ivf(c2, o2, i2, cd2, doc_ids=p2, pq=q2))
+        per.append(osp.search_batch(Q, k, ef, ne, ratio))
+    merged.clear()
+    n_none = 0
+    for b in range(B):
+        live = [pr for pr in per if int(pr[2][b]) >= 0]          # count -1 == None (spann/index.rs:229-231)
+        n_none += len(per) - len(live)
+        if live:
+            d = np.concatenate([np.asarray(pr[0][b, :int(pr[2][b])]).reshape(-1, 2) for pr in live])
+            sc = np.concatenate([np.asarray(pr[1][b, :int(pr[2][b])], dtype=np.float32) for pr in live])
+            merged.append(O.merge_topk(d, sc, k))
+        else:
+            merged.append(([], np.zeros(0, dtype=np.float32)))
+    g = graphs[rank]
+    ghn = M.BlockBasedHnsw(g["num_layers"], g["edges"], g["points"], g["edge_offsets"], g["level_offsets"], c, M.NoQuantizer(dim), ctx=ctx)
+    gsp = M.Spann(ghn, givf)
+    params = M.SearchParams(k, ef, False, ne, ratio)
+    sp_ok = True
+    for dev in (False, True):
+        sp_ok &= same(gsp.shard_search_batch(torch.from_numpy(Q).cuda() if dev else Q, params), dev, 'spann')
+    sp_ok &= same(gsp.shard_search_batch(Q, params, shared_codebook=False), False, 'spann-nosplit')
+    tks = [gsp.shard_search_batch_submit(Qp, params, o) for o in outs]
+    for t in tks:
+        gsp.search_wait(t)
+    for o in outs:
+        sp_ok &= same(M.BatchResult(o[0].numpy(), o[1].numpy(), o[2].numpy()), False, 'spann-pipelined')
+    ctx.shard_overlap(True)
+    rs = [gsp.shard_search_batch(Qd, params) for _ in range(3)]
+    for r in rs:
+        sp_ok &= same(r, True, 'spann-overlap')
+    ctx.shard_overlap(False)
+    ok = ivf_ok and sp_ok
     t = torch.tensor([1 if ok else 0])
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("shard search check:", "OK" if int(t.item()) == 1 else "MISMATCH", f"(world {world}, B {B})")
+        print(json.dumps({"check": "sharded IVF + SPANN search vs per-shard oracle + oracle merge", "world": world, "queries": B,
+                          "k": k, "modes": ["host", "device", "pipelined", "no split encode", "overlapped exchange"],
+                          "ivf_ok_rank0": bool(ivf_ok), "spann_ok_rank0": bool(sp_ok), "all_ranks_ok": int(t.item()) == 1,
+                          "gpu": torch.cuda.get_device_name(local)}))
     dist.destroy_process_group()
     sys.exit(0 if int(t.item()) == 1 else 1)
 
