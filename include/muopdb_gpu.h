@@ -58,7 +58,8 @@ enum {
   MGPU_K_HNSW = 5,     /* graph beam search */
   MGPU_K_MERGE = 6,    /* shard top-k merge */
   MGPU_K_OTHER = 7,
-  MGPU_K_COUNT = 8
+  MGPU_K_FALLBACK = 8, /* exact re-scan of the queries the 16-bit PQ scan could not certify (normally an empty launch) */
+  MGPU_K_COUNT = 9
 };
 
 typedef struct { uint64_t lo, hi; } mgpu_u128;
@@ -197,6 +198,9 @@ int mgpu_ivf_scan_remap_filtered(mgpu_ivf *ivf, const float *Q, uint32_t B, cons
 /* Algorithmic bytes of the last scan on this index (sum over queries of L(q) x bytes/row + 4). */
 uint64_t mgpu_ivf_last_scan_bytes(mgpu_ivf *ivf);
 uint64_t mgpu_ivf_last_scan_rows(mgpu_ivf *ivf);
+/* Queries of the last PQ search that went through the exact fallback scan (not certified by the 16-bit scan, or too many
+ * chunks for its table); 0 for the other scan kernels. */
+uint64_t mgpu_ivf_last_scan_fallbacks(mgpu_ivf *ivf);
 
 /* ---- Build-time assignment (rs/index/src/ivf/builder.rs:268-366, kmeans_builder.rs:199-221) - */
 /* Squared-L2 to every centroid; the max_clusters nearest; keep those with |d - dmin| <= dmin * threshold.

@@ -784,6 +784,9 @@ class BlockBasedIvf:
     def last_scan_rows(self) -> int:
         return int(self.ctx.lib.mgpu_ivf_last_scan_rows(self.handle))
 
+    def last_scan_fallbacks(self) -> int:
+        return int(self.ctx.lib.mgpu_ivf_last_scan_fallbacks(self.handle))
+
     def last_scan_bytes(self) -> int:
         return int(self.ctx.lib.mgpu_ivf_last_scan_bytes(self.handle))
 

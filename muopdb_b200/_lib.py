@@ -13,8 +13,8 @@ ERR_INVALID_ARG, ERR_OUT_OF_RANGE, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED, ERR_NO_DE
 L2, DOT = 0, 1
 QUANT_NONE, QUANT_PQ = 0, 1
 HOST, DEVICE = 0, 1
-K_COARSE, K_SELECT, K_QUANTIZE, K_SCAN, K_FINALIZE, K_HNSW, K_MERGE, K_OTHER = range(8)
-KERNEL_CLASS_NAMES = ["coarse", "select", "quantize", "scan", "finalize", "hnsw", "merge", "other"]
+K_COARSE, K_SELECT, K_QUANTIZE, K_SCAN, K_FINALIZE, K_HNSW, K_MERGE, K_OTHER, K_FALLBACK = range(9)
+KERNEL_CLASS_NAMES = ["coarse", "select", "quantize", "scan", "finalize", "hnsw", "merge", "other", "fallback"]
 
 
 class MuopdbGpuError(RuntimeError):
@@ -92,6 +92,7 @@ SIGNATURES = {
                                                _vp, _f32p, _u32p, C.c_int]),
     "mgpu_ivf_last_scan_bytes": (C.c_uint64, [C.c_void_p]),
     "mgpu_ivf_last_scan_rows": (C.c_uint64, [C.c_void_p]),
+    "mgpu_ivf_last_scan_fallbacks": (C.c_uint64, [C.c_void_p]),
     "mgpu_ivf_assign": (C.c_int, [C.c_void_p, _f32p, C.c_uint64, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, _u32p, _u32p, C.c_int]),
     "mgpu_kmeans_assign": (C.c_int, [C.c_void_p, _f32p, C.c_uint64, _f32p, C.c_uint32, C.c_uint32, C.c_int, _f32p, _u32p, _f32p, C.c_int]),
     "mgpu_hnsw_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _u32p, C.c_uint64, _u32p, C.c_uint64, _u64p, C.c_uint64,

@@ -261,6 +261,7 @@ int mgpu_pq_create(mgpu_ctx *ctx, uint32_t dim, uint32_t dsub, uint32_t nbits, c
   if (s == MGPU_OK) s = dev_alloc_copy<float>(ctx, &pq->d_rowmin, nullptr, (size_t)pq->m * pq->K);
   if (s == MGPU_OK) s = dev_alloc_copy<float>(ctx, &pq->d_rowmax, nullptr, (size_t)pq->m * pq->K);
   if (s == MGPU_OK) s = launch_pq_build_table(pq);
+  if (s == MGPU_OK) s = launch_pq_build_table16(pq);
   if (s == MGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) s = mgpu_fail(ctx, MGPU_ERR_CUDA, "pq_create: table build failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (s != MGPU_OK) { mgpu_pq_destroy(pq); return s; }
   *out = pq;
@@ -270,7 +271,7 @@ int mgpu_pq_create(mgpu_ctx *ctx, uint32_t dim, uint32_t dsub, uint32_t nbits, c
 void mgpu_pq_destroy(mgpu_pq *pq) {
   if (!pq) return;
   cudaSetDevice(pq->ctx->device);
-  cudaFree(pq->d_cb); cudaFree(pq->d_table); cudaFree(pq->d_rowmin); cudaFree(pq->d_rowmax);
+  cudaFree(pq->d_cb); cudaFree(pq->d_table); cudaFree(pq->d_rowmin); cudaFree(pq->d_rowmax); cudaFree(pq->d_table16);
   delete pq;
 }
 
@@ -407,7 +408,8 @@ int mgpu_ivf_create(mgpu_ctx *ctx, uint32_t dim, uint32_t nlist, const float *ce
       ivf->pq_fast = pq->nbits == 8 && pq->m % 32 == 0 && pq->m / 32 <= 4;
       ivf->ng = ivf->pq_fast ? pq->m / 32 : 0;
       ivf->bytes_per_row = pq->m + 4;
-      s = dev_alloc_copy<uint8_t>(ctx, &ivf->d_codes, nullptr, nslots * pq->m);
+      s = dev_alloc_copy<uint8_t>(ctx, &ivf->d_codes, nullptr,
+                                  ivf->pq_fast ? std::max<uint64_t>(chunks, 1) * pq_fast_chunk_bytes(ivf->ng) : nslots * pq->m);
     } else {
       ivf->bytes_per_row = (uint64_t)dim * 4 + 4;
       s = dev_alloc_copy<float>(ctx, &ivf->d_rows, nullptr, nslots * ivf->dim4 * 4);
@@ -428,7 +430,7 @@ void mgpu_ivf_destroy(mgpu_ivf *ivf) {
   cudaStreamSynchronize(ivf->ctx->stream);
   cudaFree(ivf->d_centroids); cudaFree(ivf->d_csplit); cudaFree(ivf->d_cn); cudaFree(ivf->d_chunk_start); cudaFree(ivf->d_list_len); cudaFree(ivf->d_slot_pid);
   cudaFree(ivf->d_codes); cudaFree(ivf->d_rows); cudaFree(ivf->d_doc_ids); cudaFree(ivf->d_invalid); cudaFree(ivf->d_scan_rows);
-  cudaFree(ivf->d_scan_overflow); cudaFree(ivf->d_pid_slot);
+  cudaFree(ivf->d_scan_overflow); cudaFree(ivf->d_pid_slot); cudaFree(ivf->d_qstate);
   ivf_free_doc_map(ivf);
   delete ivf;
 }
@@ -478,6 +480,15 @@ uint64_t mgpu_ivf_last_scan_rows(mgpu_ivf *ivf) {
   cudaSetDevice(ivf->ctx->device);
   unsigned long long v = 0;
   cudaMemcpyAsync(&v, ivf->d_scan_rows, 8, cudaMemcpyDeviceToHost, ivf->ctx->stream);
+  cudaStreamSynchronize(ivf->ctx->stream);
+  return v;
+}
+uint64_t mgpu_ivf_last_scan_fallbacks(mgpu_ivf *ivf) {
+  if (!ivf || !ivf->d_scan_overflow || !ivf->last_scan_was16) return 0;
+  std::lock_guard<std::mutex> g(ivf->ctx->mu);
+  cudaSetDevice(ivf->ctx->device);
+  uint32_t v = 0;
+  cudaMemcpyAsync(&v, ivf->d_scan_overflow, 4, cudaMemcpyDeviceToHost, ivf->ctx->stream);
   cudaStreamSynchronize(ivf->ctx->stream);
   return v;
 }
@@ -635,15 +646,38 @@ static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32
     cudaFreeAsync(priv, ctx->stream);
     return st;
   }
-  MGPU_TRY(launch_scan(ivf, a));
+  static const bool no_prune = getenv("MGPU_FINALIZE_PRUNE") && getenv("MGPU_FINALIZE_PRUNE")[0] == '0';
   if (ivf->quant == MGPU_QUANT_PQ) {
     f.cb = ivf->pq->d_cb; f.codes = ivf->d_codes; f.qcodes = d_qcodes; f.m = ivf->pq->m; f.K = ivf->pq->K;
     f.dsub = ivf->pq->dsub; f.ng = ivf->ng; f.pq_fast = ivf->pq_fast;
-    static const bool no_prune = getenv("MGPU_FINALIZE_PRUNE") && getenv("MGPU_FINALIZE_PRUNE")[0] == '0';
     f.prune = ivf->metric == MGPU_L2 && !no_prune;
   }
   f.doc_ids = ivf->d_doc_ids;
   f.out_pids = d_out_pids; f.out_docs = d_out_docs; f.out_scores = d_out_scores; f.out_counts = d_out_counts;
+  if (ivf->quant == MGPU_QUANT_PQ && scan_pq16_applicable(ivf, a)) {
+    // ---- 16-bit-LUT scan (scan_pq16.cu) -> exact re-rank + certification -> exact fallback for whatever is left.  The
+    // fallback launch is a no-op when every query was certified (the usual case); its list is filled on the device.
+    if (!ivf->d_scan_overflow || ivf->scan_overflow_cap < B || !ivf->d_qstate) {
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      cudaFree(ivf->d_scan_overflow); cudaFree(ivf->d_qstate);
+      ivf->d_scan_overflow = nullptr; ivf->d_qstate = nullptr; ivf->scan_overflow_cap = 0;
+      CUDA_TRY(ctx, cudaMalloc((void **)&ivf->d_scan_overflow, ((size_t)B + 1) * 4));
+      CUDA_TRY(ctx, cudaMalloc((void **)&ivf->d_qstate, (size_t)B * 4));
+      ivf->scan_overflow_cap = B;
+    }
+    a.overflow_count = ivf->d_scan_overflow;
+    a.overflow_list = ivf->d_scan_overflow + 1;
+    CUDA_TRY(ctx, cudaMemsetAsync(a.overflow_count, 0, 4, ctx->stream));
+    ivf->last_scan_was16 = true;
+    MGPU_TRY(launch_scan_pq16(ivf, a, ivf->d_qstate));
+    static const float cert_slack = getenv("MGPU_CERT_SLACK") ? (float)atof(getenv("MGPU_CERT_SLACK")) : 1.0f;
+    f.key16 = 1; f.gscale = ivf->pq->gscale; f.cert_slack = cert_slack; f.qstate = ivf->d_qstate;
+    f.uncert_count = a.overflow_count; f.uncert_list = a.overflow_list;
+    MGPU_TRY(launch_finalize(ctx, f));
+    return launch_scan_pq_exact_list(ivf, a, f);
+  }
+  ivf->last_scan_was16 = false;
+  MGPU_TRY(launch_scan(ivf, a));
   return launch_finalize(ctx, f);
 }
 

@@ -276,10 +276,8 @@ __global__ void k_gather_rows(const uint32_t *__restrict__ pid_slot, const uint3
   if (out_codes) {
     for (uint32_t s = threadIdx.x; s < m; s += blockDim.x) {
       uint8_t c;
-      if (pq_fast) {
-        const uint32_t g = s >> 5, t = (s & 31) ^ l;
-        c = codes[((chunk * ng + g) * 2 + (t >> 4)) * 512 + l * 16 + (t & 15)];
-      } else c = codes[(size_t)slot * m + s];
+      if (pq_fast) c = codes[pq_fast_code_offset(chunk, ng, l, s)];
+      else c = codes[(size_t)slot * m + s];
       out_codes[(size_t)i * m + s] = c;
     }
   } else {

@@ -5,83 +5,7 @@
 //   Snapshot merge                  rs/index/src/collection/snapshot.rs:49-63,79-108
 #include "internal.cuh"
 #include "pq_device.cuh"
-
-__device__ __forceinline__ float key2f(uint32_t key) {
-  uint32_t u = (key & 0x80000000u) ? (key ^ 0x80000000u) : ~key;
-  return __uint_as_float(u);
-}
-
-struct FastLayoutCode {
-  const uint8_t *codes; uint32_t slot, ng;
-  __device__ __forceinline__ uint32_t operator()(uint32_t s) const {
-    uint32_t g = s >> 5, j = s & 31, l = slot & 31, t = j ^ l;
-    size_t chunk = slot >> 5;
-    return codes[((chunk * ng + g) * 2 + (t >> 4)) * 512 + l * 16 + (t & 15)];
-  }
-};
-
-__device__ __forceinline__ bool doc_less(uint32_t ka, mgpu_u128 a, uint32_t kb, mgpu_u128 b) {
-  if (ka != kb) return ka < kb;
-  if (a.hi != b.hi) return a.hi < b.hi;
-  return a.lo < b.lo;
-}
-
-// Which of a query's 32 candidates can still reach the exact top k (FinalizeArgs::prune)?  Called by one full warp; lane =
-// candidate.  Returns this lane's verdict.
-__device__ __forceinline__ bool prune_keep(uint32_t k, bool valid, uint32_t key, int lane) {
-  const uint32_t nvalid = __popc(__ballot_sync(0xffffffffu, valid));
-  if (nvalid <= k) return valid;
-  // k-th smallest key among the valid candidates, by counting (keys may repeat)
-  uint32_t rank = 0;
-#pragma unroll 8
-  for (int j = 0; j < 32; j++) {
-    const uint32_t kj = __shfl_sync(0xffffffffu, key, j);
-    const bool vj = __shfl_sync(0xffffffffu, (int)valid, j);
-    rank += (vj && (kj < key || (kj == key && j < lane))) ? 1u : 0u;
-  }
-  const unsigned who = __ballot_sync(0xffffffffu, valid && rank == k - 1);
-  const uint32_t kth = __shfl_sync(0xffffffffu, key, __ffs(who) - 1);
-  const uint64_t bound = (uint64_t)kth + (kth >> 12) + 8192u;
-  return valid && (uint64_t)key <= bound;
-}
-
-// Ordering + remap tail shared by both finalize kernels; called by one full warp per query.  `skey` is the exact score
-// key of this lane's candidate, `valid` whether the lane holds one.
-__device__ __forceinline__ void finalize_tail(const FinalizeArgs &a, uint32_t q, int lane, bool valid, uint32_t skey,
-                                              uint32_t pid, uint32_t slot) {
-  WarpTop32 w;
-  w.key = valid ? (((uint64_t)skey << 32) | pid) : MGPU_EMPTY_KEY;
-  w.pay = slot;
-  w.sort();  // ascending (distance, point_id): PointAndDistance::cmp (rs/index/src/utils.rs:71-76)
-  const uint32_t nvalid = __popc(__ballot_sync(0xffffffffu, w.key != MGPU_EMPTY_KEY));
-  const uint32_t count = min(a.k, nvalid);
-  const uint32_t rk = (uint32_t)(w.key >> 32), rpid = (uint32_t)w.key;
-  const float score = key2f(rk);
-  if (a.out_pids && (uint32_t)lane < count) {
-    a.out_pids[(size_t)q * a.k + lane] = rpid;
-    if (!a.out_docs) a.out_scores[(size_t)q * a.k + lane] = score;
-  }
-  if (a.out_docs) {
-    mgpu_u128 doc;
-    if ((uint32_t)lane < count && a.doc_ids) doc = a.doc_ids[rpid];
-    else { doc.lo = rpid; doc.hi = 0; }
-    // IdWithScore::cmp (utils.rs:95-114): (score, doc_id); rank by counting among the kept lanes
-    uint32_t rank = 0;
-    for (uint32_t j = 0; j < count; j++) {
-      uint32_t kj = __shfl_sync(0xffffffffu, rk, j);
-      mgpu_u128 dj;
-      dj.lo = shfl64(doc.lo, j); dj.hi = shfl64(doc.hi, j);
-      bool less = doc_less(kj, dj, rk, doc);
-      bool same = (kj == rk) && dj.lo == doc.lo && dj.hi == doc.hi;
-      rank += (less || (same && j < (uint32_t)lane)) ? 1u : 0u;
-    }
-    if ((uint32_t)lane < count) {
-      a.out_docs[(size_t)q * a.k + rank] = doc;
-      a.out_scores[(size_t)q * a.k + rank] = score;
-    }
-  }
-  if (lane == 0 && a.out_counts) a.out_counts[q] = count;
-}
+#include "finalize_device.cuh"
 
 // generic path: one warp per query, one candidate per lane (any dsub; flat rows arrive with exact keys already)
 template <int METRIC>
@@ -89,12 +13,15 @@ __global__ void __launch_bounds__(128) k_finalize(FinalizeArgs a) {
   const int lane = threadIdx.x & 31;
   const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= a.B) return;
+  if (a.qstate && a.qstate[q]) return;   // deferred by the scan: the exact fallback answers this query
   uint64_t ckey = a.cand_key[(size_t)q * MGPU_NCAND + lane];
   uint32_t slot = a.cand_slot[(size_t)q * MGPU_NCAND + lane];
   bool valid = slot != MGPU_EMPTY_SLOT;
+  const uint32_t nscan = __popc(__ballot_sync(0xffffffffu, valid));
   const uint32_t pid = (uint32_t)ckey;
   uint32_t skey = (uint32_t)(ckey >> 32);
-  if (a.cb != nullptr && a.prune) valid = prune_keep(a.k, valid, skey, lane);
+  const uint32_t fkey = skey;
+  if (a.cb != nullptr && a.prune) valid = prune_keep(a.k, valid, skey, lane, a.key16 != 0, a.m, a.cert_slack);
   if (a.cb != nullptr && valid) {
     // exact Quantizer::distance(quantized_query, row, StreamingSIMD) (index.rs:203-207, pq/mod.rs:231-266)
     float d;
@@ -103,7 +30,7 @@ __global__ void __launch_bounds__(128) k_finalize(FinalizeArgs a) {
     else d = pq_distance_streaming<METRIC>(a.cb, a.m, a.K, a.dsub, qc, RowMajorCode{a.codes + (size_t)slot * a.m});
     skey = f2key(d);
   }
-  finalize_tail(a, q, lane, valid, skey, pid, slot);
+  finalize_tail(a, q, lane, valid, skey, pid, slot, fkey, nscan);
 }
 
 // dsub == 8 (the reference default): one CTA of 128 threads per query.  Staging: the query's own centroids (m x 8 floats) and
@@ -130,9 +57,13 @@ __global__ void __launch_bounds__(FIN8_THREADS) k_finalize_pq8(FinalizeArgs a) {
   float4 *ring = (float4 *)(sslot + MGPU_NCAND);   // FIN8_MLP x 64 gathered centroid halves (16-byte aligned: all sizes above are)
   const uint32_t q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
+  if (a.qstate && a.qstate[q]) return;   // deferred by the scan: the exact fallback answers this query
+  uint32_t nscan = 0, fkey = 0;
   if (tid < MGPU_NCAND) {
     uint32_t slot = a.cand_slot[(size_t)q * MGPU_NCAND + tid];
-    if (a.prune && !prune_keep(a.k, slot != MGPU_EMPTY_SLOT, (uint32_t)(a.cand_key[(size_t)q * MGPU_NCAND + tid] >> 32), lane))
+    fkey = (uint32_t)(a.cand_key[(size_t)q * MGPU_NCAND + tid] >> 32);
+    nscan = __popc(__ballot_sync(0xffffffffu, slot != MGPU_EMPTY_SLOT));
+    if (a.prune && !prune_keep(a.k, slot != MGPU_EMPTY_SLOT, fkey, lane, a.key16 != 0, a.m, a.cert_slack))
       slot = MGPU_EMPTY_SLOT;  // cannot reach the exact top k: treated like an empty candidate from here on
     sslot[tid] = slot;
   }
@@ -150,7 +81,7 @@ __global__ void __launch_bounds__(FIN8_THREADS) k_finalize_pq8(FinalizeArgs a) {
       const uint32_t l = slot & 31;
       // an empty candidate gets code 0 everywhere: it is scored like any other (keeps the warps converged) and ignored later
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (slot != MGPU_EMPTY_SLOT) v = __ldg((const uint4 *)(a.codes + (((size_t)(slot >> 5) * a.ng + g) * 2 + u) * 512 + l * 16));
+      if (slot != MGPU_EMPTY_SLOT) v = __ldg((const uint4 *)(a.codes + (size_t)(slot >> 5) * pq_fast_chunk_bytes(a.ng) + ((size_t)g * 2 + u) * 512 + l * 16));
       const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
       uint8_t *dst = cc + c * mp + 32 * g;
 #pragma unroll
@@ -214,7 +145,7 @@ __global__ void __launch_bounds__(FIN8_THREADS) k_finalize_pq8(FinalizeArgs a) {
     const uint32_t slot = sslot[lane];
     const bool valid = slot != MGPU_EMPTY_SLOT;
     const uint32_t pid = (uint32_t)a.cand_key[(size_t)q * MGPU_NCAND + lane];
-    finalize_tail(a, q, lane, valid, skeys[lane], pid, slot);
+    finalize_tail(a, q, lane, valid, skeys[lane], pid, slot, fkey, nscan);
   }
 }
 

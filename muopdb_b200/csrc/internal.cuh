@@ -11,6 +11,11 @@ struct mgpu_pq {
   float *d_table = nullptr;   // [m][K][K] score contribution of (query code a, row code b): L2 -> ||ca-cb||^2, dot -> -<ca,cb>
   float *d_rowmin = nullptr;  // [m][K] min_b table[m][a][b]
   float *d_rowmax = nullptr;  // [m][K]
+  // 16-bit fixed-point image of the table with ONE scale for the whole quantizer (K == 256 only):
+  //   table16[s][a][b] = rn((table[s][a][b] - rowmin[s][a]) * gscale),  gscale = 65535 / max_{s,a} (rowmax - rowmin)
+  // A query's LUT is then a pure gather of m rows of 512 bytes (no per-query scale, no arithmetic): scan_pq16.cu.
+  uint16_t *d_table16 = nullptr;
+  float gscale = 0.0f;
 };
 
 // ---- IVF resident state -------------------------------------------------------------------------
@@ -20,6 +25,8 @@ struct mgpu_pq {
 //       unit u holds for lane l the 16 bytes t = 16u .. 16u+15 where byte t = code of subspace 32g + (l ^ t).
 //       A warp reads a unit with one fully coalesced 16-byte-per-lane load, and at step t the 32 lanes touch 32
 //       different LUT columns (l ^ t) -> shared-memory lookups are bank-conflict free for ANY code values.
+//       The chunk's 32 point ids follow its code units (one 128-byte line), so a chunk is ONE contiguous record of
+//       pq_fast_chunk_bytes(ng) = ng * 1024 + 128 bytes: the scan fetches it with a single bulk copy (cp.async.bulk).
 //   PQ generic layout: codes_rm[slot][m] row-major.
 //   flat layout: per chunk [dim4][32 lanes] float4 (dim padded to a multiple of 4): lane = row, coalesced 512 B reads.
 struct mgpu_ivf {
@@ -52,9 +59,21 @@ struct mgpu_ivf {
   uint32_t scan_bound_probes = 0;        // cache: upper bound of chunks any `scan_bound_probes` lists can hold
   uint64_t scan_bound_chunks = 0;
   // accessors (index.rs:350-384,469-471), built on first use
+  uint32_t *d_qstate = nullptr;          // per query: 1 = deferred by the 16-bit scan (scan_pq16.cu)
+  uint32_t qstate_cap = 0;
+  bool last_scan_was16 = false;
   uint32_t *d_pid_slot = nullptr;        // point id -> one slot holding its row (MGPU_EMPTY_SLOT: in no list)
   void *doc_map = nullptr;               // host std::unordered_map doc id -> point id (doc_id_to_point_id, index.rs:67-73)
 };
+
+// PQ fast layout: bytes / 16-byte words of one chunk record (code units of the ng groups, then the 32 point ids)
+__host__ __device__ inline size_t pq_fast_chunk_bytes(uint32_t ng) { return (size_t)ng * 1024 + 128; }
+__host__ __device__ inline size_t pq_fast_chunk_u4(uint32_t ng) { return (size_t)ng * 64 + 8; }
+// byte offset of the code of subspace s of the row in lane l of chunk `chunk`
+__host__ __device__ inline size_t pq_fast_code_offset(size_t chunk, uint32_t ng, uint32_t l, uint32_t s) {
+  const uint32_t g = s >> 5, t = (s & 31) ^ l;
+  return chunk * pq_fast_chunk_bytes(ng) + ((size_t)g * 2 + (t >> 4)) * 512 + l * 16 + (t & 15);
+}
 
 struct mgpu_hnsw {
   mgpu_ctx *ctx;
@@ -115,9 +134,14 @@ struct ScanArgs {
   // PQ table-driven scan: queries with more chunks than the shared-memory chunk table are deferred to a second launch
   unsigned int *overflow_count; uint32_t *overflow_list;
   int metric;
+  // exact fallback (scan.cu k_scan_pq_exact): rows scored with ProductQuantizer::distance itself; the queries come from
+  // overflow_list[0 .. *overflow_count)
+  int from_list;
+  const float *cb; uint32_t dsub;
 };
 
 int launch_pq_build_table(mgpu_pq *pq);
+int launch_pq_build_table16(mgpu_pq *pq);
 int launch_pq_quantize(mgpu_pq *pq, const float *dX, uint64_t n, uint8_t *dcodes, cudaStream_t st = nullptr);
 int launch_pq_distance_pairs(mgpu_pq *pq, const uint8_t *da, const uint8_t *db, uint64_t n, float *dout);
 int launch_build_layout(mgpu_ivf *ivf, const void *d_rows_by_pid);
@@ -125,6 +149,8 @@ int launch_scan(mgpu_ivf *ivf, const ScanArgs &a);
 int launch_plan_queries(mgpu_ivf *ivf, const uint32_t *d_probes, uint32_t max_probes, const uint32_t *d_counts, uint32_t B,
                         uint32_t *d_order, uint32_t *d_work, bool have_work = false);
 int launch_scan_pq_db(mgpu_ivf *ivf, const ScanArgs &a);  // MGPU_ERR_UNSUPPORTED => use launch_scan's generic kernels
+bool scan_pq16_applicable(mgpu_ivf *ivf, const ScanArgs &a);
+int launch_scan_pq16(mgpu_ivf *ivf, const ScanArgs &a, uint32_t *d_qstate);
 size_t scan_max_probes_supported(mgpu_ivf *ivf);
 
 struct FinalizeArgs {
@@ -138,10 +164,26 @@ struct FinalizeArgs {
   // exceeds the k-th smallest key by more than 2^-12 relative + 8192 units cannot be among the exact top k and is not
   // re-scored
   bool prune;
+  // Candidates of the 16-bit-LUT scan (scan_pq16.cu): key = sum of u16 table entries with the quantizer-wide scale, L2 only.
+  //   |key - gscale * exact score| <= E(key) = 0.51 m + 2 + 1.2e-5 key   (entry rounding + fp32 summation-order slack)
+  // so a candidate with key > (k-th smallest key) + 2 E cannot reach the exact top k (prune), and the answer is CERTIFIED
+  // exact when gscale * (exact score of the k-th best candidate) + E < (32nd key): no row outside the 32 candidates can beat
+  // it.  A query that cannot be certified is appended to uncert_list (count in uncert_count) for the exact fallback scan.
+  // qstate[q] != 0: the scan deferred this query itself (its candidate list was never written).
+  int key16;
+  float gscale;                // table16 scale of the quantizer
+  float cert_slack;            // multiplies E (test hook: a huge value sends every full query through the fallback)
+  const uint32_t *qstate;
+  uint32_t *uncert_count, *uncert_list;
   // outputs (either may be null)
   uint32_t *out_pids; mgpu_u128 *out_docs; float *out_scores; uint32_t *out_counts;
 };
+__host__ __device__ inline uint64_t key16_err(uint32_t m, uint32_t key, float slack) {
+  const float e = (0.51f * (float)m + 2.0f + 1.2e-5f * (float)key) * slack;
+  return e >= 4.0e9f ? 0xFFFFFFFFull : (uint64_t)e + 1ull;
+}
 int launch_finalize(mgpu_ctx *ctx, const FinalizeArgs &a);
+int launch_scan_pq_exact_list(mgpu_ivf *ivf, const ScanArgs &a, const FinalizeArgs &f);
 
 int launch_distance_matrix(mgpu_ctx *ctx, const float *dA, uint64_t nA, const float *dB, uint64_t nB, uint32_t dim,
                            int metric, int mode /*0 squared,1 sqrt*/, float *dout, int kernel_class);

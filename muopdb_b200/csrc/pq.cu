@@ -44,6 +44,52 @@ __global__ void k_pq_build_table(const float *__restrict__ cb, uint32_t dsub, ui
   }
 }
 
+// maximum row range of the table (one block) and the 16-bit image
+__global__ void k_pq_max_range(const float *__restrict__ rowmin, const float *__restrict__ rowmax, uint32_t n, float *__restrict__ out) {
+  __shared__ float sm[32];
+  float mx = 0.0f;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, rowmax[i] - rowmin[i]);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (uint32_t w = 1; w < (blockDim.x + 31) / 32; w++) mx = fmaxf(mx, sm[w]);
+    out[0] = mx;
+  }
+}
+__global__ void k_pq_table16(const float *__restrict__ table, const float *__restrict__ rowmin, uint64_t n, uint32_t K, float gscale,
+                             uint16_t *__restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = __fmul_rn(__fsub_rn(table[i], rowmin[i / K]), gscale);
+  out[i] = (uint16_t)min(__float2uint_rn(v), 65535u);
+}
+
+// d_table16 / gscale (needs the table, rowmin, rowmax); synchronises once to read the range back
+int launch_pq_build_table16(mgpu_pq *pq) {
+  mgpu_ctx *ctx = pq->ctx;
+  if (pq->K != 256) return MGPU_OK;
+  const uint64_t n = (uint64_t)pq->m * pq->K * pq->K;
+  float *d_mx = nullptr;
+  CUDA_TRY(ctx, cudaMalloc((void **)&d_mx, 16));
+  {
+    LaunchScope ls(ctx, MGPU_K_OTHER);
+    k_pq_max_range<<<1, 1024, 0, ctx->stream>>>(pq->d_rowmin, pq->d_rowmax, pq->m * pq->K, d_mx);
+  }
+  float mx = 0.0f;
+  cudaError_t e = cudaMemcpyAsync(&mx, d_mx, 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_mx);
+  CUDA_TRY(ctx, e);
+  if (!(mx > 0.0f) || !(mx < 3.0e38f)) { pq->gscale = 0.0f; return MGPU_OK; }   // degenerate codebook: the 32-bit scan handles it
+  pq->gscale = 65535.0f / mx;
+  CUDA_TRY(ctx, cudaMalloc((void **)&pq->d_table16, n * 2));
+  LaunchScope ls(ctx, MGPU_K_OTHER);
+  k_pq_table16<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(pq->d_table, pq->d_rowmin, n, pq->K, pq->gscale, pq->d_table16);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return MGPU_OK;
+}
+
 int launch_pq_build_table(mgpu_pq *pq) {
   mgpu_ctx *ctx = pq->ctx;
   dim3 grid(pq->K, pq->m);

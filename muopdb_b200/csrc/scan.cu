@@ -16,6 +16,8 @@
 // in finalize.cu, which also applies the reference's (distance, point_id) ordering.
 #include "internal.cuh"
 #include "scan_common.cuh"
+#include "pq_device.cuh"
+#include "finalize_device.cuh"
 
 #ifndef SCAN_FAST_NT
 #define SCAN_FAST_NT 768
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(NT, 1) k_scan(ScanArgs a, ScanSmemLayout L) {
 
       uint32_t key;
       if (MODE == SCAN_PQ_FAST) {
-        const uint4 *base = (const uint4 *)a.codes + (size_t)chunk * (NG * 2 * 32) + lane;
+        const uint4 *base = (const uint4 *)a.codes + (size_t)chunk * (NG * 64 + 8) + lane;
         uint4 u[NG * 2];
 #pragma unroll
         for (int i = 0; i < NG * 2; i++) u[i] = ldg_stream16(base + i * 32);
@@ -334,6 +336,123 @@ __global__ void __launch_bounds__(NT, 1) k_scan(ScanArgs a, ScanSmemLayout L) {
   }
 }
 
+// ---- exact fallback -------------------------------------------------------------------------------------------------------------
+// Queries the 16-bit scan could not certify (finalize.cu) or did not scan (more chunks than its chunk table) are answered here
+// with NO approximation: every row of the probed lists is scored with ProductQuantizer::distance itself (pq/mod.rs:231-266),
+// the per-warp top-32 lists hold exact (score key, point id) composites, and warp 0 runs the ordinary epilogue
+// (finalize_tail: (distance, point_id) order -> top k -> doc ids -> (score, doc_id) order).  Persistent CTAs take queries from
+// a.overflow_list[0 .. *a.overflow_count); the launch is a no-op when the list is empty.  Slow by design (96 codebook gathers
+// per row) -- it only has to be right.
+#define EXACT_WARPS 16
+template <int METRIC>
+__global__ void __launch_bounds__(EXACT_WARPS * 32, 1) k_scan_pq_exact(ScanArgs a, FinalizeArgs f) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint32_t *pref = (uint32_t *)smem;                    // maxp + 1
+  uint32_t *pcs = pref + a.max_probes + 1;              // maxp
+  uint64_t *mkey = (uint64_t *)(((uintptr_t)(pcs + a.max_probes) + 15) & ~(uintptr_t)15);
+  uint32_t *mpay = (uint32_t *)(mkey + EXACT_WARPS * 32);
+  uint32_t *sh = mpay + EXACT_WARPS * 32;               // [0] threshold, [1] total chunks, [2] query
+  uint32_t *b2 = sh + 4;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (;;) {
+    if (tid == 0) { uint32_t t = atomicAdd(a.next_query, 1u); sh[2] = t < *a.overflow_count ? a.overflow_list[t] : 0xFFFFFFFFu; }
+    __syncthreads();
+    const uint32_t q = sh[2];
+    if (q >= a.B) break;
+    const uint32_t np = a.probe_counts ? min(a.probe_counts[q], a.max_probes) : a.max_probes;
+    if (warp == 0) {
+      uint32_t run = 0;
+      for (uint32_t base = 0; base < np; base += 32) {
+        uint32_t i = base + lane, cnt = 0, cs = 0;
+        if (i < np) {
+          uint32_t c = a.probes[(size_t)q * a.max_probes + i];
+          cs = a.chunk_start[c];
+          cnt = a.chunk_start[c + 1] - cs;
+        }
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        if (i < np) { pref[i] = run + incl - cnt; pcs[i] = cs; }
+        run += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0) { pref[np] = run; sh[0] = 0xFFFFFFFFu; sh[1] = run; }
+      if (lane < EXACT_WARPS) b2[lane] = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    const uint32_t total = sh[1];
+    WarpTop32 top;
+    top.init();
+    uint32_t p = 0;
+    const RowMajorCode qc{a.qcodes + (size_t)q * a.m};
+    for (uint32_t it = warp; it < total; it += EXACT_WARPS) {
+      while (it >= pref[p + 1]) p++;
+      const uint32_t chunk = pcs[p] + (it - pref[p]);
+      const uint32_t slot = chunk * 32 + lane;
+      const uint32_t pid = a.slot_pid[slot];
+      bool valid = pid != MGPU_EMPTY_SLOT;
+      if (a.invalid && valid) valid = !((a.invalid[pid >> 5] >> (pid & 31)) & 1u);  // index.rs:198-200
+      if (a.filter && valid) valid = (a.filter[(size_t)q * a.filter_stride + (pid >> 5)] >> (pid & 31)) & 1u;  // index.rs:212-226
+      uint32_t key = 0xFFFFFFFFu;
+      if (valid) key = f2key(pq_distance_streaming<METRIC>(a.cb, a.m, a.K, a.dsub, qc, FastLayoutCode{a.codes, slot, a.ng}));
+      const uint32_t thr = *(volatile uint32_t *)&sh[0];
+      const bool pass = valid && key <= thr;
+      if (__any_sync(0xffffffffu, pass)) {
+        const uint32_t worst = top.offer(pass, ((uint64_t)key << 32) | pid, slot);
+        uint32_t second = (uint32_t)(shfl64(top.key, 1) >> 32);
+        if (lane == 0) b2[warp] = second;
+        __syncwarp();
+        uint32_t v = lane < EXACT_WARPS ? *(volatile uint32_t *)&b2[lane] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+        v = min(v, worst);
+        if (lane == 0 && v < thr) atomicMin(&sh[0], v);
+      }
+    }
+    mkey[warp * 32 + lane] = top.key;
+    mpay[warp * 32 + lane] = top.pay;
+    __syncthreads();
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+      if (warp < half && warp + half < EXACT_WARPS) {
+        top.merge(mkey[(warp + half) * 32 + lane], mpay[(warp + half) * 32 + lane]);
+        mkey[warp * 32 + lane] = top.key;
+        mpay[warp * 32 + lane] = top.pay;
+      }
+      __syncthreads();
+    }
+    if (warp == 0) {
+      const bool valid = top.pay != MGPU_EMPTY_SLOT;
+      finalize_tail(f, q, lane, valid, (uint32_t)(top.key >> 32), (uint32_t)top.key, top.pay);
+    }
+    __syncthreads();
+  }
+}
+
+int launch_scan_pq_exact_list(mgpu_ivf *ivf, const ScanArgs &a0, const FinalizeArgs &f0) {
+  mgpu_ctx *ctx = ivf->ctx;
+  ScanArgs a = a0;
+  FinalizeArgs f = f0;
+  f.key16 = 0; f.prune = false; f.qstate = nullptr; f.cb = nullptr;   // keys are exact: no certification, no re-score
+  a.from_list = 1; a.cb = ivf->pq->d_cb; a.dsub = ivf->pq->dsub;
+  const size_t smem = ((size_t)2 * a.max_probes + 1) * 4 + 16 + (size_t)EXACT_WARPS * 32 * 12 + 16 + 32 * 4 + 64;
+  if (smem > ctx->smem_optin) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "exact fallback scan: max_probes too large");
+  CUDA_TRY(ctx, cudaMemsetAsync(a.next_query, 0, 4, ctx->stream));
+  unsigned grid = a.B < (uint32_t)ctx->sm_count ? a.B : (unsigned)ctx->sm_count;
+  LaunchScope ls(ctx, MGPU_K_FALLBACK);
+  if (ivf->metric == MGPU_L2) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_scan_pq_exact<MGPU_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_scan_pq_exact<MGPU_L2><<<grid, EXACT_WARPS * 32, smem, ctx->stream>>>(a, f);
+  } else {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_scan_pq_exact<MGPU_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_scan_pq_exact<MGPU_DOT><<<grid, EXACT_WARPS * 32, smem, ctx->stream>>>(a, f);
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  return MGPU_OK;
+}
+
 // Longest-processing-time-first order for the persistent CTAs' dynamic scheduler (removes the ragged tail of the last
 // wave: ~3 % of the scan).  work(q) = chunks of q's probed lists (one warp per query), then a 64-bucket counting sort
 // by descending work in one CTA -- an exact sort is not needed, only "big queries first".
@@ -474,8 +593,10 @@ __global__ void k_layout_pq_fast(const uint8_t *__restrict__ codes_by_pid, const
       w[b >> 2] |= code << ((b & 3) * 8);
     }
   }
-  uint4 *dst = (uint4 *)out + ((chunk * ng + g) * 2 + u) * 32 + lane;
+  uint4 *dst = (uint4 *)out + chunk * pq_fast_chunk_u4(ng) + ((size_t)g * 2 + u) * 32 + lane;
   *dst = make_uint4(w[0], w[1], w[2], w[3]);
+  // the chunk's point ids ride behind its code units (one thread per row writes its own)
+  if (g == 0 && u == 0) ((uint32_t *)((uint4 *)out + chunk * pq_fast_chunk_u4(ng) + (size_t)ng * 64))[lane] = pid;
 }
 
 __global__ void k_layout_pq_generic(const uint8_t *__restrict__ codes_by_pid, const uint32_t *__restrict__ slot_pid,

@@ -122,7 +122,7 @@ struct DbConsumerCtx {
     uint32_t it = warp, e_n = 0, pid_n = MGPU_EMPTY_SLOT;
     if (it < total) {
       e_n = ct[it];
-      const uint4 *base = (const uint4 *)a.codes + (size_t)(e_n >> 5) * (NG * 2 * 32) + lane;
+      const uint4 *base = (const uint4 *)a.codes + (size_t)(e_n >> 5) * (NG * 64 + 8) + lane;
 #pragma unroll
       for (int i = 0; i < NG * 2; i++) u[i] = ldg_stream16(base + i * 32);
       pid_n = a.slot_pid[(e_n >> 5) * 32 + lane];
@@ -138,7 +138,7 @@ struct DbConsumerCtx {
       const uint4 *nbase = (const uint4 *)a.codes;
       if (more) {
         e_n = ct[it];
-        nbase = (const uint4 *)a.codes + (size_t)(e_n >> 5) * (NG * 2 * 32) + lane;
+        nbase = (const uint4 *)a.codes + (size_t)(e_n >> 5) * (NG * 64 + 8) + lane;
         pid_n = a.slot_pid[(e_n >> 5) * 32 + lane];
       }
       uint32_t key = 0;
@@ -182,7 +182,7 @@ struct DbConsumerCtx {
       hi_it = prefp[pi + 1]; base_off = pcsp[pi] - prefp[pi];
       const uint32_t chunk = base_off + it;
       slot_n = chunk * 32 + lane;
-      const uint4 *base = (const uint4 *)a.codes + (size_t)chunk * (NG * 2 * 32) + lane;
+      const uint4 *base = (const uint4 *)a.codes + (size_t)chunk * (NG * 64 + 8) + lane;
 #pragma unroll
       for (int i = 0; i < NG * 2; i++) u[i] = ldg_stream16(base + i * 32);
       pid_n = a.slot_pid[slot_n];
@@ -200,7 +200,7 @@ struct DbConsumerCtx {
         }
         const uint32_t chunk = base_off + it;
         slot_n = chunk * 32 + lane;
-        nbase = (const uint4 *)a.codes + (size_t)chunk * (NG * 2 * 32) + lane;
+        nbase = (const uint4 *)a.codes + (size_t)chunk * (NG * 64 + 8) + lane;
         pid_n = a.slot_pid[slot_n];
       }
       bool valid = pid != MGPU_EMPTY_SLOT;

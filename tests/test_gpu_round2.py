@@ -381,3 +381,45 @@ def test_shard_search_two_ranks():
            "--master-port", "29631", os.path.join(ROOT, "tools", "check_shard_search.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "shard search check: OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
+
+
+# ---- 16-bit-LUT scan: certification and the exact fallback ------------------------------------------------------------------------
+def test_scan16_uncertified_queries_take_the_exact_fallback():
+    """scan_pq16.cu ranks with 16-bit LUT entries; finalize.cu certifies each answer (k-th exact candidate's key + 2 E < 32nd key)
+    and sends the rest to the exact scan (scan.cu k_scan_pq_exact: every row scored with ProductQuantizer::distance itself).
+    MGPU_CERT_SLACK=1e30 makes E infinite, so EVERY query with a full candidate list goes through the fallback: the PQ parity
+    tests (ties, duplicates, invalidation, planner filters, SPANN, device buffers) must still be bit-exact.  MGPU_SCAN16=0 runs
+    the same tests on the previous 32-bit-LUT kernel (scan_pq.cu), which stays in the library for k > 16 and dot-product PQ."""
+    sel = "test_ivf_pq_parity or test_ivf_pq_exact_ties or test_ivf_invalidation or test_ivf_planner_filter_parity or " \
+          "test_spann_parity or test_ivf_device_buffers or test_ivf_pq_heavy"
+    for env_add in ({"MGPU_CERT_SLACK": "1e30"}, {"MGPU_SCAN16": "0"}):
+        env = dict(os.environ, **env_add)
+        p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-x", "-q", "-m", "gpu",
+                            "-k", sel, "-p", "no:cacheprovider"], capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+        assert p.returncode == 0, (env_add, p.stdout[-3000:], p.stderr[-2000:])
+
+
+def test_scan16_near_ties_are_certified_or_fall_back(M):
+    """Rows whose exact scores differ by less than the 16-bit key resolution around the k-th place: thousands of near-duplicates
+    of the query's neighbourhood (codes differing in one subspace by the closest pair of centroids).  Whatever the certificate
+    decides, ids, order and score bits must equal the oracle's."""
+    rng = np.random.default_rng(5)
+    dim, n = 256, 6000
+    base = synth.clustered(40, dim, n_blobs=4, seed=3)
+    X = np.repeat(base, n // 40, axis=0).astype(np.float32)
+    X += (1e-4 * rng.standard_normal(X.shape)).astype(np.float32)      # near-duplicates: most rows share their code word
+    cents, offsets, ids = synth.build_ivf_arrays(X, 6, seed=2)
+    docs = synth.doc_ids_for(n, seed=6)
+    cb = O.train_pq_codebook(X[rng.choice(n, 2000, replace=False)], 8, 8, iters=4, seed=1)
+    opq, gpq = O.ProductQuantizer(dim, 8, 8, cb), M.ProductQuantizer(dim, 8, 8, cb)
+    rows = opq.quantize(X)
+    oivf = O.Ivf(cents, offsets, ids, rows, doc_ids=docs, pq=opq)
+    givf = M.BlockBasedIvf(cents, offsets, ids, rows, gpq, doc_ids=docs)
+    Q = (base[:24] + 1e-4).astype(np.float32)
+    for k in (1, 10, 16):
+        od, os_, oc = oivf.search_batch(Q, k, 6)
+        r = givf.search_batch(Q, k, 6)
+        assert np.array_equal(np.asarray(r.counts, dtype=np.int64), oc.astype(np.int64))
+        for b in range(len(Q)):
+            assert np.array_equal(r.doc_ids[b, :oc[b]], od[b, :oc[b]]), (k, b)
+            assert _same_f32(r.scores[b, :oc[b]], os_[b, :oc[b]])

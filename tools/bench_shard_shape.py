@@ -87,7 +87,7 @@ def main():
     ok = np.array_equal(od, out[0][:ns].cpu().numpy().view(np.uint64)) and \
         np.array_equal(os_.view(np.uint32), out[1][:ns].cpu().numpy().view(np.uint32))
     print(json.dumps({"shape": f"shard 0 of {S}: {col['X'].shape[0]} rows, nlist {col['nlist']}, nprobe {nprobe}, batch {B}",
-                      "ms_per_step": ms, "qps_per_rank_equiv": B / (ms / 1e3), "kernel_ms_per_step": prof, "rows_per_launch": rows,
+                      "ms_per_step": ms, "qps_per_rank_equiv": B / (ms / 1e3), "kernel_ms_per_step": prof, "rows_per_launch": rows, "fallback_queries": ivf.last_scan_fallbacks(),
                       "parity_sample_ok": bool(ok)}))
 
 
