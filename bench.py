@@ -581,8 +581,10 @@ def main():
     barrier()
     with torch.cuda.stream(ext):
         e0.record(ext)
+        th0 = time.perf_counter()
         for i in range(args.steps):
             step_device(i)
+        host_enqueue_ms = (time.perf_counter() - th0) * 1e3 / args.steps
         join()
         e1.record(ext)
     barrier()
@@ -758,7 +760,7 @@ def main():
                 "ms_per_step": e2e_s * 1e3 / args.steps, "mode": e2e_mode,
                 "pipelined_equals_device_call_on_last_batch": e2e_same,
                 "blocking": {"value": nq_job * args.steps / e2e_blocking_s, "ms_per_step": e2e_blocking_s * 1e3 / args.steps}},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(shape_key),

@@ -63,6 +63,7 @@ int mgpu_init(int device, mgpu_ctx **out) {
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return MGPU_ERR_CUDA; }
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  ctx->l2_bytes = (size_t)prop.l2CacheSize;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MGPU_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return MGPU_ERR_CUDA; }
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
@@ -706,11 +707,14 @@ static int pipe_prepare(mgpu_ctx *ctx, mgpu_ctx::Pipe *pp, size_t q_bytes, size_
 }
 
 // first half of a pipelined host-buffer call: claims the slot, uploads Q on the H2D stream, makes the main stream wait for it
-static int pipe_begin(mgpu_ctx *ctx, const void *Q, size_t q_bytes, size_t out_bytes, mgpu_ctx::Pipe **out_pp) {
+// copy_off / copy_bytes: the part of Q this call uploads (the sharded calls upload one rank's slice and all-gather the rest)
+static int pipe_begin(mgpu_ctx *ctx, const void *Q, size_t q_bytes, size_t out_bytes, mgpu_ctx::Pipe **out_pp, size_t copy_off = 0,
+                      size_t copy_bytes = (size_t)-1) {
   mgpu_ctx::Pipe *pp = &ctx->pipe[ctx->pipe_seq & 1];
   MGPU_TRY(pipe_prepare(ctx, pp, q_bytes, out_bytes));
+  if (copy_bytes == (size_t)-1) copy_bytes = q_bytes;
   if (pp->used) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->h2d_stream, pp->ev_done, 0));  // the previous user of the buffer has read it
-  CUDA_TRY(ctx, cudaMemcpyAsync(pp->q, Q, q_bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
+  if (copy_bytes) CUDA_TRY(ctx, cudaMemcpyAsync((char *)pp->q + copy_off, (const char *)Q + copy_off, copy_bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
   CUDA_TRY(ctx, cudaEventRecord(pp->ev_h2d, ctx->h2d_stream));
   CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, pp->ev_h2d, 0));
   *out_pp = pp;
@@ -1217,7 +1221,15 @@ static int shard_search_impl(mgpu_ivf *ivf, mgpu_spann *sp, const float *Q, uint
   const uint32_t m = ivf->pq ? ivf->pq->m : 0;
   const uint32_t slice = (B + N - 1) / N;
   size_t need = 0;
-  need = ws_need(need, mem == MGPU_HOST ? (size_t)B * ivf->dim * 4 : 0);
+  // HOST buffers: every rank holds the same replicated batch, so rank r uploads only rows [r * slice, (r + 1) * slice) and
+  // one all-gather over NVLink completes the batch on every GPU (N x less PCIe traffic per rank; at N = 8 the full upload of
+  // 8192 x 768 floats per rank was what bounded the end-to-end rate)
+  static const bool no_split_upload = getenv("MGPU_SPLIT_UPLOAD") && getenv("MGPU_SPLIT_UPLOAD")[0] == '0';
+  const bool split_upload = mem == MGPU_HOST && N > 1 && !no_split_upload;
+  const size_t row_bytes = (size_t)ivf->dim * 4, slice_bytes = (size_t)slice * row_bytes;
+  const size_t q_alloc = split_upload ? (size_t)N * slice_bytes : (size_t)B * row_bytes;
+  const uint32_t up_lo = std::min(B, r * slice), up_cnt = std::min(B, up_lo + slice) - up_lo;
+  need = ws_need(need, mem == MGPU_HOST ? q_alloc : 0);
   need = ws_need(need, split_encode ? (size_t)N * slice * m : 0);
   need = ws_need(need, split_encode ? (size_t)slice * m : 0);
   if (ctx->shard_ws_bytes < need) {
@@ -1226,7 +1238,7 @@ static int shard_search_impl(mgpu_ivf *ivf, mgpu_spann *sp, const float *Q, uint
     ctx->shard_ws_bytes = need + need / 4 + 256;
   }
   WsAlloc w(ctx->shard_ws, ctx->shard_ws_bytes);
-  float *sQ = w.get<float>(mem == MGPU_HOST ? (size_t)B * ivf->dim : 0);
+  float *sQ = w.get<float>(mem == MGPU_HOST ? q_alloc / 4 : 0);
   uint8_t *codes_all = w.get<uint8_t>(split_encode ? (size_t)N * slice * m : 0);
   uint8_t *codes_mine = w.get<uint8_t>(split_encode ? (size_t)slice * m : 0);
   mgpu_ctx::ShardSlot *sl;
@@ -1235,12 +1247,22 @@ static int shard_search_impl(mgpu_ivf *ivf, mgpu_spann *sp, const float *Q, uint
   const void *dQv;
   mgpu_ctx::Pipe *pp = nullptr;
   if (ticket) {   // pipelined: this slot's staging for the queries and the merged results, copies on the side streams
-    MGPU_TRY(pipe_begin(ctx, Q, (size_t)B * ivf->dim * 4, (size_t)B * kk * 24 + (size_t)B * 4 + 768, &pp));
+    if (split_upload) MGPU_TRY(pipe_begin(ctx, Q, q_alloc, (size_t)B * kk * 24 + (size_t)B * 4 + 768, &pp, (size_t)up_lo * row_bytes, (size_t)up_cnt * row_bytes));
+    else MGPU_TRY(pipe_begin(ctx, Q, (size_t)B * row_bytes, (size_t)B * kk * 24 + (size_t)B * 4 + 768, &pp));
     dQv = pp->q;
+  } else if (split_upload) {
+    if (up_cnt) CUDA_TRY(ctx, cudaMemcpyAsync((char *)sQ + (size_t)up_lo * row_bytes, (const char *)Q + (size_t)up_lo * row_bytes, (size_t)up_cnt * row_bytes,
+                                              cudaMemcpyHostToDevice, ctx->stream));
+    dQv = sQ;
   } else {
-    MGPU_TRY(stage_in(ctx, Q, (size_t)B * ivf->dim * 4, mem, sQ, &dQv));
+    MGPU_TRY(stage_in(ctx, Q, (size_t)B * row_bytes, mem, sQ, &dQv));
   }
   const float *dQ = (const float *)dQv;
+  if (split_upload) {   // in-place all-gather of the query slices (rank r's slice sits at r * slice_bytes)
+    int rc = ag((const char *)dQv + (size_t)r * slice_bytes, (void *)dQv, slice_bytes, 0, ctx->nccl_comm, ctx->stream);
+    if (rc != 0) return mgpu_fail(ctx, MGPU_ERR_NCCL, "ncclAllGather (query slices) failed (%d)", rc);
+    ctx->launches += 1;
+  }
   const uint8_t *ext = nullptr;
   if (split_encode) {
     const uint32_t lo = std::min(B, r * slice), cnt = std::min(B, lo + slice) - lo;
@@ -1397,6 +1419,7 @@ int mgpu_hnsw_create(mgpu_ctx *ctx, uint32_t dim, uint32_t num_layers, const uin
       }
     }
   }
+  for (uint64_t i = 0; i + 1 < n_edge_offsets; i++) h->max_degree = std::max<uint32_t>(h->max_degree, (uint32_t)std::min<uint64_t>(edge_offsets[i + 1] - edge_offsets[i], 0xFFFFFFFFull));
   int s = dev_alloc_copy(ctx, &h->d_edges, edges, n_edges);
   if (s == MGPU_OK && !edges0.empty()) s = dev_alloc_copy(ctx, &h->d_edges0, edges0.data(), edges0.size());
   if (s == MGPU_OK && !dense.empty()) s = dev_alloc_copy(ctx, &h->d_upper_dense, dense.data(), dense.size());

@@ -21,6 +21,7 @@ struct mgpu_ctx {
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
+  size_t l2_bytes = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t aux_stream = nullptr;           // side stream for work that is independent of the main chain (query encode)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
