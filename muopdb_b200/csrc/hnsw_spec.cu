@@ -18,14 +18,16 @@
 //       meanwhile jumped the queue) ends the batch -- nothing is lost but the unused scores.
 //
 // Same total orders as hnsw.cu (W ascending (key, id), C ascending (key, ~id)); here both are sorted arrays in shared memory and
-// an expansion updates them ONCE with a warp-parallel merge (every element finds its final position by binary search) instead
-// of one sorted insertion per admitted neighbour: a lone warp retires a dependent instruction every ~5 cycles, and the
-// sequential admissions (about a thousand cycles each on the register lists) were 60 % of a batch.  The decisions that ARE
-// order dependent -- which neighbours get in, given that the furthest key shrinks with every admission -- run on the 32
-// largest entries of W, one per lane (about 20 instructions per admission).  Same counters (distance evaluations = fresh neighbours at replay, expansions = popped candidates with edges), so results AND
-// out_stats equal the oracle's.  The visited set is a per-query open-addressing hash table in shared memory (no global
-// bitmap, no atomics to L2); a query that outgrows it, or whose candidate list overflows its registers, raises err_flags[q] and
-// is redone by k_hnsw_search.
+// an expansion updates each of them ONCE, in place: every old element moves up by the number of newcomers below it and every
+// newcomer lands on the number of elements below it, all counted with warp shuffles and one redux per newcomer
+// (hs_merge_inplace) -- instead of one sorted insertion per admitted neighbour.  A lone warp retires a dependent instruction
+// every ~5 cycles and the per-neighbour insertions into register lists (several hundred cycles each, 4-5 per expansion on the
+// 768-dimensional benchmark graph) were 80 % of a batch.  The decisions that ARE order dependent -- which neighbours get in,
+// given that the furthest key shrinks with every admission -- run on the 32 largest entries of W held one per lane (about 20
+// instructions per admission).  Same counters (distance evaluations = fresh neighbours at replay, expansions = popped
+// candidates with edges), so results AND out_stats equal the oracle's.  The visited set is a bitmap (n <= 262144) or an
+// open-addressing hash table in shared memory (no global bitmap, no atomics to L2); a query that outgrows it, or whose
+// candidate array overflows, raises err_flags[q] and is redone by k_hnsw_search.
 #include "hnsw_device.cuh"
 
 #define HS_TMAX 8         /* speculated candidates per batch: T <= warps, T <= HS_TMAX */
@@ -37,7 +39,7 @@
 #ifdef MGPU_SCAN_DBG
 // experiment build only (make DBG=1): [0] batches [1] replayed expansions [2] rows scored [3] cycles speculate-1 [4] speculate-2
 // [5] replay (thread 0 of every CTA)
-__device__ unsigned long long g_hs_dbg[8];
+__device__ unsigned long long g_hs_dbg[16];
 #define HSD_T(v) const long long v = clock64()
 #define HSD_ADD(i, x) do { if (tid == 0) atomicAdd(&g_hs_dbg[i], (unsigned long long)(x)); } while (0)
 #else
@@ -66,6 +68,65 @@ __device__ __forceinline__ int hs_insert(uint32_t *hash, uint32_t e) {
   }
 }
 
+// ---- W and C: sorted arrays of unique 64-bit composites in shared memory, updated once per expansion.
+// number of entries of the ascending array A[0, n) that are < x
+__device__ __forceinline__ int hs_lower_bound(const uint64_t *A, int n, uint64_t x) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (A[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+// In-place merge into the ascending array A[0, n): every lane whose bit is set in `mask` brings one composite `a` (all distinct,
+// and distinct from A's); A[0, n + popc(mask)) is ascending afterwards.  Called by one full warp.  Chunks of 128 old elements
+// are taken from the top down, loaded to registers before any of them is stored, so that moving up never overwrites an element
+// that is still to be read.  Returns the number of entries of the merged array whose key (high word) is <= le_key.
+__device__ __forceinline__ int hs_merge_inplace(uint64_t *A, int n, uint64_t a, unsigned mask, uint32_t le_key) {
+  const int lane = threadIdx.x & 31;
+  const bool mine = (mask >> lane) & 1u;
+  int apos = 0;
+  int nle = (mine && (uint32_t)(a >> 32) <= le_key) ? 1 : 0;
+  for (unsigned m = mask; m; m &= m - 1) {
+    const uint64_t x = shfl64(a, __ffs(m) - 1);
+    apos += x < a ? 1 : 0;
+  }
+  for (int base = n > 0 ? ((n - 1) & ~127) : -1; base >= 0; base -= 128) {
+    uint64_t o[4];
+    int r[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int idx = base + k * 32 + lane;
+      o[k] = idx < n ? A[idx] : ~0ull;
+      r[k] = 0;
+      nle += (idx < n && (uint32_t)(o[k] >> 32) <= le_key) ? 1 : 0;
+    }
+    __syncwarp();
+    for (unsigned m = mask; m; m &= m - 1) {
+      const int t = __ffs(m) - 1;
+      const uint64_t x = shfl64(a, t);
+      int c = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const bool lt = o[k] < x;
+        c += lt ? 1 : 0;
+        r[k] += lt ? 0 : 1;
+      }
+      const int tot = __reduce_add_sync(0xffffffffu, c);
+      if (lane == t) apos += tot;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int idx = base + k * 32 + lane;
+      if (idx < n && r[k]) A[idx + r[k]] = o[k];
+    }
+    __syncwarp();
+  }
+  if (mine) A[apos] = a;
+  __syncwarp();
+  return __reduce_add_sync(0xffffffffu, nle);
+}
+
 // visited set in shared memory: bitmap over the point ids when it fits, else the hash table
 struct HsVisited {
   uint32_t *mem; bool bitmap;
@@ -76,13 +137,13 @@ struct HsVisited {
   }
 };
 
-template <int METRIC, int EPL, int HS_WARPS, int HS_T>
+template <int METRIC, int HS_WARPS, int HS_T>
 __global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : 2) k_hnsw_spec(HnswDev g, HnswSearchArgs a, uint32_t *__restrict__ err_flags, uint32_t vis_words) {
   constexpr int HS_THREADS = HS_WARPS * 32;
   static_assert(HS_T <= HS_WARPS && HS_T <= HS_TMAX, "one warp fetches the edges of one speculated candidate");
   extern __shared__ __align__(16) uint8_t smem[];
   const uint32_t ef = a.ef;
-  constexpr int CAP = EPL * 32;
+  const int WCAP = (int)ef + 32, CCAP = 2 * (int)ef + 96;
   float *sq = (float *)smem;                                   // dim floats
   uint32_t *hash = (uint32_t *)(sq + ((g.dim + 3) & ~3u));     // visited set: vis_words words (bitmap: ceil(n/32); hash: HS_HASH_CAP)
   const HsVisited vis{hash, g.n <= HS_BITMAP_MAX_N};
@@ -91,7 +152,15 @@ __global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : 2) k_hnsw_
   uint32_t *work = sp_key + HS_T * 32;                         // (t << 5 | j) of the rows to score
   uint32_t *sp_id = work + HS_T * 32;                          // [T] speculated candidate ids
   uint32_t *sp_deg = sp_id + HS_T;                             // [T] stored edges of each
-  int *st = (int *)(sp_deg + HS_T);                            // [0] nspec [1] stop [2] work count [3] next entry point [4] abort
+  uint32_t *sp_fresh = sp_deg + HS_T;                          // [T] lanes whose neighbour is fresh IF the candidates before it are replayed
+  int *st = (int *)(sp_fresh + HS_T);                          // [0] nspec [1] stop [2] work count [3] next entry point [4] abort
+                                                               // [5] candidates replayed by the last batch
+                                                               // [7] merge request, [8..14] its arguments (see REPLAY)
+  uint64_t *Wb = (uint64_t *)(((uintptr_t)(st + 16) + 15) & ~(uintptr_t)15);  // [WCAP] working list, ascending (key, id)
+  uint64_t *Cb = Wb + WCAP;                                    // [CCAP] candidates, ascending (key, ~id), live part [head, nC)
+  uint64_t *aw = Cb + CCAP;                                    // [32] newcomers that stay in W (W form)
+  uint64_t *ac = aw + 32;                                      // [32] newcomers pushed to C (C form)
+
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t q = blockIdx.x;
   for (uint32_t d = tid; d < g.dim; d += HS_THREADS) sq[d] = a.Q[(size_t)q * g.dim + d];
@@ -138,25 +207,47 @@ __global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : 2) k_hnsw_
     return -ret;
   };
 
-  RegList<EPL> W, Cd;  // only warp 0's copies are meaningful: W ascending (key, id), C ascending (key, ~id), lane-blocked registers
-  int nW = 0, nC = 0;
+  // warp 0 (uniform registers): sizes; the live candidates are Cb[head, nC)
+  int nW = 0, head = 0, nC = 0;
   bool overflow = false;
 
-  // warp 0: publish the next batch -- the first min(T, nC) entries of the candidate list
+  // warp 0: publish the next batch -- the first min(T, live) entries of the candidate list
   auto plan = [&](int stop) {
     int ns = 0;
     if (!stop) {
-      if (nC == 0) stop = 1;
+      const int live = nC - head;
+      if (live == 0) stop = 1;
       else {
-        ns = nC < HS_T ? nC : HS_T;
-#pragma unroll
-        for (int t = 0; t < HS_T; t++) {
-          const uint64_t c = Cd.get(t);
-          if (lane == 0 && t < ns) sp_id[t] = ~(uint32_t)c;
-        }
+        ns = live < HS_T ? live : HS_T;
+        if (lane < ns) sp_id[lane] = ~(uint32_t)Cb[head + lane];
       }
     }
     if (lane == 0) { st[0] = ns; st[1] = stop; st[2] = 0; }
+  };
+
+
+  // warp 0: the composites xc of the lanes in `mask` join the candidates; with a full W, candidates strictly farther than its
+  // furthest key fk can never be expanded (they only trigger the `break`) and are cut off the sorted tail
+  // warp 0: room for na more candidates behind nC -- slide the live part back to the start of the array if need be (moving
+  // down: chunks bottom up); false if it still does not fit
+  auto candidate_room = [&](int na) -> bool {
+    if (nC + na > CCAP && head > 0) {
+      const int live = nC - head;
+      for (int i0 = 0; i0 < live; i0 += 32) {
+        const uint64_t v = i0 + lane < live ? Cb[head + i0 + lane] : 0ull;
+        __syncwarp();
+        if (i0 + lane < live) Cb[i0 + lane] = v;
+        __syncwarp();
+      }
+      head = 0; nC = live;
+    }
+    return nC + na <= CCAP;
+  };
+  auto merge_candidates = [&](uint64_t xc, unsigned mask, uint32_t fk) {
+    const int na = __popc(mask);
+    if (!candidate_room(na)) { overflow = true; return; }
+    const int nle = hs_merge_inplace(Cb + head, nC - head, xc, mask, fk);
+    nC = nW == (int)ef ? head + nle : nC + na;
   };
 
   uint32_t ep = g.entry_point;
@@ -169,19 +260,26 @@ __global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : 2) k_hnsw_
       if (lane == 0 && ep < g.n) nvis += (uint32_t)vis.insert(ep);
       nvis = __shfl_sync(0xffffffffu, nvis, 0);
       const uint32_t kd = f2key(ed);
-      W.init(); Cd.init();
-      W.insert(((uint64_t)kd << 32) | ep);
-      Cd.insert(((uint64_t)kd << 32) | (uint32_t)~ep);
+      head = 0;
+      if (lane == 0) { Wb[0] = ((uint64_t)kd << 32) | ep; Cb[0] = ((uint64_t)kd << 32) | (uint32_t)~ep; }
+      __syncwarp();
       nW = 1; nC = 1;
       n_dist++;
       plan(0);
+      if (lane == 0) st[5] = 0;
     }
+    __syncthreads();                                    // (A) the first batch is published
     for (;;) {
-      __syncthreads();                                  // (A) the batch is published
+      // ---- the neighbours the last replay found fresh become visited now (set_visited, index.rs:255-259): the replay itself
+      // only reads the masks computed below, and candidates it did not reach must leave no trace
+      if (warp < st[5] && ((sp_fresh[warp] >> lane) & 1u)) vis.insert(sp_edge[warp * 32 + lane]);
+      __syncthreads();                                  // (I)
       if (st[1] || st[4]) break;
       const int nspec = st[0];
       HSD_T(d0);
       // ---- SPECULATE 1: edge rows of the speculated candidates, visited lookups, work list, L2 prefetch of the rows
+      uint32_t my_e = HS_EMPTY;
+      bool fresh0 = false;
       if (warp < nspec) {
         const uint32_t cur = sp_id[warp];
         uint32_t e = HS_EMPTY, deg = 0;
@@ -204,14 +302,18 @@ __global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : 2) k_hnsw_
           if ((uint32_t)lane < deg) e = g.edges[e_begin + lane];
         }
         const bool valid = e < g.n;                         // ids >= n are never visited nor scored (as in hnsw.cu)
-        const bool unv = valid && !vis.contains(e);
-        sp_edge[warp * 32 + lane] = valid ? e : HS_EMPTY;
+        if (!valid) e = HS_EMPTY;
+        // the first occurrence of an id in the edge list is the one that can be fresh (index.rs:255-259)
+        const unsigned peers = __match_any_sync(0xffffffffu, e);
+        fresh0 = valid && (__ffs(peers) - 1 == lane) && !vis.contains(e);
+        my_e = e;
+        sp_edge[warp * 32 + lane] = e;
         if (lane == 0) sp_deg[warp] = deg;
-        const unsigned mk = __ballot_sync(0xffffffffu, unv);
+        const unsigned mk = __ballot_sync(0xffffffffu, fresh0);
         int base = 0;
         if (lane == 0 && mk) base = atomicAdd(&st[2], __popc(mk));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (unv) {
+        if (fresh0) {
           work[base + __popc(mk & ((1u << lane) - 1))] = (uint32_t)(warp * 32 + lane);
           const char *rowp = (const char *)g.rows + (size_t)e * g.dim * 4;
           const uint32_t lines = (g.dim * 4 + 127) / 128;
@@ -220,6 +322,16 @@ __global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : 2) k_hnsw_
       }
       __syncthreads();                                  // (B)
       HSD_T(d1);
+      // a neighbour that an EARLIER candidate of this batch also lists is visited by the time this candidate is expanded
+      if (warp < nspec) {
+        bool dup = false;
+        for (int t = 0; t < warp; t++) {
+#pragma unroll
+          for (int l = 0; l < 32; l++) dup |= sp_edge[t * 32 + l] == my_e;
+        }
+        const unsigned fm = __ballot_sync(0xffffffffu, fresh0 && !dup);
+        if (lane == 0) sp_fresh[warp] = fm;
+      }
       // ---- SPECULATE 2: distances of the unvisited neighbours, half-warp per row
       {
         const int nwork = st[2];
@@ -235,73 +347,188 @@ __global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : 2) k_hnsw_
       __syncthreads();                                  // (C)
       HSD_T(d2);
       HSD_ADD(0, 1); HSD_ADD(2, st[2]); HSD_ADD(3, d1 - d0); HSD_ADD(4, d2 - d1);
-      // ---- REPLAY: the reference's loop on the speculated data (index.rs:235-281)
-      if (warp == 0) {
-        int s = 0, stop = 0;
-        for (;;) {
-          if (s >= nspec) break;
-          if (nC == 0) { stop = 1; break; }
-          const uint64_t c = Cd.get(0);
-          const uint32_t ck = (uint32_t)(c >> 32), cid = ~(uint32_t)c;
-          uint32_t fk = (uint32_t)(W.get(nW - 1) >> 32);           // furthest key of W (nW >= 1), kept in a register
-          if (ck > fk) { Cd.pop_front(); nC--; stop = 1; break; }   // strictly farther than the furthest: search_layer ends
-          if (cid != sp_id[s]) break;                              // not speculated: next batch starts with it
-          Cd.pop_front();
-          nC--;
-          if (sp_deg[s] != 0) {                                    // None => continue
-            n_expand++;
-            const uint32_t e = sp_edge[s * 32 + lane];
-            const bool valid = e != HS_EMPTY;
-            // the first occurrence of an id in the edge list is the one that can be fresh (index.rs:255-259)
-            const unsigned peers = __match_any_sync(0xffffffffu, e);
-            const bool leader = valid && (__ffs(peers) - 1 == lane);
-            const int isnew = leader ? vis.insert(e) : 0;
-            const unsigned fresh = __ballot_sync(0xffffffffu, isnew);
-            const uint32_t kd_lane = sp_key[s * 32 + lane];
-            nvis += (uint32_t)__popc(fresh);
-            n_dist += (unsigned long long)__popc(fresh);
-            // Admissions, sequential in edge order (index.rs:260-281): admit iff kd < furthest || |W| < ef, with the furthest
-            // re-read before every neighbour.  While W is full its furthest key never grows, so a fresh neighbour that is not
-            // below the furthest key of NOW can never be admitted later in this list: those are dropped in one ballot and
-            // only the possible admissions are walked one by one.
-            unsigned todo = __ballot_sync(0xffffffffu, isnew && (nW < (int)ef || kd_lane < fk));
-            bool changed = false;
-            while (todo) {
-              const int j = __ffs(todo) - 1;
-              todo &= todo - 1;
-              const uint32_t kd = __shfl_sync(0xffffffffu, kd_lane, j), ee = __shfl_sync(0xffffffffu, e, j);
-              if (kd < fk || nW < (int)ef) {
-                if (nC == CAP) {
-                  // the entry that falls off the end may only be lost if it can never be expanded
-                  const uint32_t lastk = (uint32_t)(Cd.get(CAP - 1) >> 32);
-                  if (!(nW == (int)ef && lastk > fk)) overflow = true;
-                  nC--;
+      // ---- REPLAY: the reference's loop on the speculated data (index.rs:235-281).  Warp 0 walks the speculated candidates;
+      // the other warps wait at (S1).  An expansion that admitted neighbours leaves the two sorted arrays to be updated: that is
+      // handed to the whole CTA (st[7] = 1) -- one or two elements per thread, every element computing its own final position
+      // -- because a lone warp looping over 128 + 100 entries was 60 % of the batch.
+      int s = 0, stop = 0, cadd_le = 0, resume = 0;
+      uint32_t e = HS_EMPTY, kd = 0;                    // warp 0: the expansion in progress
+      unsigned fresh = 0;
+      for (;;) {
+        if (warp == 0) {
+          int cmd = 0;
+          for (;;) {
+            if (!resume) {
+              if (s >= nspec) break;
+              if (nC == head) { stop = 1; break; }
+              HSD_T(ta);
+              const uint64_t c = Cb[head];
+              const uint32_t ck = (uint32_t)(c >> 32), cid = ~(uint32_t)c;
+              const uint32_t fk0 = (uint32_t)(Wb[nW - 1] >> 32);     // furthest key of W (nW >= 1)
+              if (ck > fk0) { head++; stop = 1; break; }             // strictly farther than the furthest: search_layer ends
+              if (cid != sp_id[s]) break;                            // not speculated: next batch starts with it
+              head++;                                                // pop
+              if (sp_deg[s] == 0) { s++; continue; }                 // None => continue
+              n_expand++;
+              fresh = sp_fresh[s];
+              e = sp_edge[s * 32 + lane];
+              kd = sp_key[s * 32 + lane];
+              nvis += (uint32_t)__popc(fresh);
+              n_dist += (unsigned long long)__popc(fresh);
+              HSD_T(tb);
+              HSD_ADD(9, tb - ta);
+              // ---- admissions (index.rs:260-281): in edge order, admit iff kd < furthest || |W| < ef, furthest re-read every
+              // time.  (1) W not full yet: the first ef - nW fresh neighbours are admitted unconditionally, nothing is evicted
+              if (nW < (int)ef && fresh) {
+                const uint64_t xw = ((uint64_t)kd << 32) | e, xc = ((uint64_t)kd << 32) | (uint32_t)~e;
+                const int room = (int)ef - nW;
+                const int rank = __popc(fresh & ((1u << lane) - 1));
+                const bool take = ((fresh >> lane) & 1u) && rank < room;
+                const unsigned admitted = __ballot_sync(0xffffffffu, take);
+                const int na = __popc(admitted);
+                fresh &= ~admitted;
+                if (!candidate_room(na)) overflow = true;
+                else if (nW <= HS_THREADS && nC - head <= HS_THREADS) {
+                  if (take) { aw[rank] = xw; ac[rank] = xc; }
+                  cadd_le = na;
+                  if (lane == 0) {
+                    st[8] = na; st[9] = nW; st[10] = na; st[11] = head; st[12] = nC - head; st[13] = -1 /* keep every candidate */; st[14] = 0;
+                  }
+                  nW += na;
+                  resume = 1;
+                  cmd = 1;
+                  break;
+                } else {
+                  hs_merge_inplace(Wb, nW, xw, admitted, 0u);
+                  nW += na;
+                  merge_candidates(xc, admitted, (uint32_t)(Wb[nW - 1] >> 32));
                 }
-                Cd.insert(((uint64_t)kd << 32) | (uint32_t)~ee);
-                nC++;
-                W.insert(((uint64_t)kd << 32) | ee);
-                nW++;
-                if (nW > (int)ef) nW--;  // pop the furthest (index.rs:277-279)
-                fk = (uint32_t)(W.get(nW - 1) >> 32);
-                changed = true;
               }
             }
-            // candidates strictly farther than the furthest can never be expanded (they only trigger the `break`): truncate
-            // the sorted tail once per expansion
-            if (changed && nW == (int)ef) nC = Cd.count_le(nC, fk);
+            resume = 0;
+            // (2) W full: its furthest key never grows, so a fresh neighbour that is not below the furthest key of NOW can never
+            // be admitted later in this list -- those are dropped with one ballot.  The rest is walked one by one against the
+            // 32 largest entries of W held one per lane (descending): an admission removes lane 0's entry (the furthest) and
+            // inserts the newcomer in place.
+            if (nW == (int)ef && fresh) {
+              uint32_t fk = (uint32_t)(Wb[nW - 1] >> 32);
+              unsigned todo = __ballot_sync(0xffffffffu, ((fresh >> lane) & 1u) && kd < fk);
+              if (todo) {
+                HSD_T(r0);
+                HSD_ADD(7, __popc(todo));
+                unsigned adm2 = 0;
+                uint64_t tk = lane < nW ? Wb[nW - 1 - lane] : 0ull;  // 0 = no entry (no real composite is 0)
+                while (todo) {
+                  const int j = __ffs(todo) - 1;
+                  todo &= todo - 1;
+                  const uint32_t kj = __shfl_sync(0xffffffffu, kd, j), ej = __shfl_sync(0xffffffffu, e, j);
+                  if (kj < fk) {
+                    const uint64_t x = ((uint64_t)kj << 32) | ej;
+                    const uint64_t nx = shfl64(tk, (lane + 1) & 31);
+                    const uint64_t below = lane == 31 ? 0ull : nx;          // tail after dropping lane 0's entry
+                    tk = below > x ? below : ((lane == 0 || tk > x) ? x : tk);
+                    fk = (uint32_t)(shfl64(tk, 0) >> 32);
+                    adm2 |= 1u << j;
+                  }
+                }
+                HSD_T(r1);
+                HSD_ADD(8, r1 - r0);
+                if (adm2) {
+                  HSD_ADD(6, __popc(adm2)); HSD_ADD(11, 1);
+                  // Every admission evicted the furthest entry of the moment, so what was evicted is: the newcomers above the
+                  // final furthest entry, and as many of the LARGEST old entries as newcomers stay.  The final furthest entry is
+                  // lane 0's, unless 32 admissions emptied the lanes of old entries and the 33rd largest old entry is above it.
+                  const uint64_t xw = ((uint64_t)kd << 32) | e, xc = ((uint64_t)kd << 32) | (uint32_t)~e;
+                  uint64_t top = shfl64(tk, 0);
+                  if (nW > 32) { const uint64_t w33 = Wb[nW - 33]; top = w33 > top ? w33 : top; }
+                  fk = (uint32_t)(top >> 32);
+                  const unsigned stay = __ballot_sync(0xffffffffu, ((adm2 >> lane) & 1u) && xw <= top);
+                  HSD_ADD(12, __popc(stay));
+                  // the newcomers evicted again were pushed to C as well (and are cut off unless tied with the furthest key)
+                  const int naW = __popc(stay), naC = __popc(adm2);
+                  if (!candidate_room(naC)) overflow = true;
+                  else if (nW - naW <= HS_THREADS && nC - head <= HS_THREADS) {
+                    const unsigned below = (1u << lane) - 1;
+                    if ((stay >> lane) & 1u) aw[__popc(stay & below)] = xw;
+                    if ((adm2 >> lane) & 1u) ac[__popc(adm2 & below)] = xc;
+                    cadd_le = __popc(__ballot_sync(0xffffffffu, ((adm2 >> lane) & 1u) && kd <= fk));
+                    if (lane == 0) {
+                      st[8] = naW; st[9] = nW - naW; st[10] = naC; st[11] = head; st[12] = nC - head; st[13] = (int)fk; st[14] = 0;
+                    }
+                    cmd = 1;
+                    s++;
+                    break;
+                  } else {
+                    hs_merge_inplace(Wb, nW - naW, xw, stay, 0u);
+                    merge_candidates(xc, adm2, fk);
+                  }
+                }
+              }
+            }
+            s++;
           }
-          s++;
+          if (!cmd) {
+            if ((!vis.bitmap && nvis > HS_HASH_CAP * 3 / 4) || overflow) { if (lane == 0) st[4] = 1; }
+            HSD_T(tp);
+            plan(stop);
+            if (lane == 0) st[5] = s;
+            HSD_T(d3);
+            HSD_ADD(1, s); HSD_ADD(5, d3 - d2); HSD_ADD(10, d3 - tp);
+          }
+          if (lane == 0) st[7] = cmd;
         }
-        if ((!vis.bitmap && nvis > HS_HASH_CAP * 3 / 4) || overflow) { if (lane == 0) st[4] = 1; }
-        plan(stop);
-        HSD_T(d3);
-        HSD_ADD(1, s); HSD_ADD(5, d3 - d2);
+        __syncthreads();                                // (S1) next batch published, or a merge request
+        if (!st[7]) break;
+        HSD_T(tm0);
+        {
+          // threads [0, HALF): W <- Wb[0, st[9]) + aw[0, st[8]);  threads [HALF, 2 HALF): C <- Cb[head, head + st[12]) + ac[0, st[10])
+          constexpr int HALF = HS_THREADS / 2;
+          const bool isC = tid >= HALF;
+          const int i = isC ? tid - HALF : tid;
+          uint64_t *A = isC ? Cb + st[11] : Wb;
+          const uint64_t *add = isC ? ac : aw;
+          const int n = isC ? st[12] : st[9], na = isC ? st[10] : st[8];
+          const uint32_t fkk = (uint32_t)st[13];
+          uint64_t x[2];
+          int r[2] = {0, 0};
+#pragma unroll
+          for (int k = 0; k < 2; k++) { const int idx = i + k * HALF; x[k] = idx < n ? A[idx] : ~0ull; }
+#pragma unroll 4
+          for (int j = 0; j < na; j++) {
+            const uint64_t v = add[j];
+            r[0] += v < x[0] ? 1 : 0;
+            r[1] += v < x[1] ? 1 : 0;
+          }
+          int apos = -1;
+          uint64_t amine = 0;
+          if (i >= HALF - na) {                         // a newcomer: elements below it, old and new
+            amine = add[HALF - 1 - i];
+            apos = hs_lower_bound(A, n, amine);
+#pragma unroll 4
+            for (int j = 0; j < na; j++) apos += add[j] < amine ? 1 : 0;
+          }
+          if (isC) {                                    // candidates strictly farther than the furthest key are cut off
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+              const int idx = i + k * HALF;
+              if (idx < n && (uint32_t)(x[k] >> 32) <= fkk && (idx + 1 == n || (uint32_t)(A[idx + 1] >> 32) > fkk)) st[14] = idx + 1;
+            }
+          }
+          __syncthreads();                              // (S2) every element is in a register
+#pragma unroll
+          for (int k = 0; k < 2; k++) { const int idx = i + k * HALF; if (idx < n && r[k]) A[idx + r[k]] = x[k]; }
+          if (apos >= 0) A[apos] = amine;
+          __syncthreads();                              // (S3)
+          if (warp == 0) nC = head + st[14] + cadd_le;
+          HSD_T(tm1);
+          HSD_ADD(13, tm1 - tm0);
+        }
       }
     }
     if (st[4]) break;
     // ---- next layer's entry: min_by distance over the sorted working list == W[0] (index.rs:176-181)
     if (layer > 0) {
-      if (warp == 0 && lane == 0) st[3] = nW > 0 ? (int)(uint32_t)W.v[0] : (int)ep;
+      if (warp == 0 && lane == 0) st[3] = nW > 0 ? (int)(uint32_t)Wb[0] : (int)ep;
       __syncthreads();
       ep = (uint32_t)st[3];
       __syncthreads();
@@ -314,20 +541,16 @@ __global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : 2) k_hnsw_
   // ---- results: working list is already sorted by (distance, point_id); truncate to k, map to doc ids (index.rs:185-204)
   if (warp == 0) {
     const uint32_t cnt = min((uint32_t)nW, a.k);
-#pragma unroll
-    for (int e = 0; e < EPL; e++) {
-      const uint32_t i = lane * EPL + e;
-      if (i < cnt) {
-        const uint64_t w = W.v[e];
-        const uint32_t pid = (uint32_t)w, kd = (uint32_t)(w >> 32);
-        const uint32_t u = (kd & 0x80000000u) ? (kd ^ 0x80000000u) : ~kd;
-        a.out_scores[(size_t)q * a.k + i] = __uint_as_float(u);
-        if (a.out_pids) a.out_pids[(size_t)q * a.k + i] = pid;
-        if (a.out_docs) {
-          mgpu_u128 d;
-          if (g.doc_ids) d = g.doc_ids[pid]; else { d.lo = pid; d.hi = 0; }
-          a.out_docs[(size_t)q * a.k + i] = d;
-        }
+    for (uint32_t i = lane; i < cnt; i += 32) {
+      const uint64_t w = Wb[i];
+      const uint32_t pid = (uint32_t)w, kd = (uint32_t)(w >> 32);
+      const uint32_t u = (kd & 0x80000000u) ? (kd ^ 0x80000000u) : ~kd;
+      a.out_scores[(size_t)q * a.k + i] = __uint_as_float(u);
+      if (a.out_pids) a.out_pids[(size_t)q * a.k + i] = pid;
+      if (a.out_docs) {
+        mgpu_u128 d;
+        if (g.doc_ids) d = g.doc_ids[pid]; else { d.lo = pid; d.hi = 0; }
+        a.out_docs[(size_t)q * a.k + i] = d;
       }
     }
     if (lane == 0) {
@@ -337,51 +560,51 @@ __global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : 2) k_hnsw_
   }
 }
 
-// Applies when: flat rows, ef in 1..224 (register lists), every adjacency list holds <= 32 edges, and the upper layers have the
+// Applies when: flat rows, ef in 1..2048, every adjacency list holds <= 32 edges, and the upper layers have the
 // dense position map.  *launched = false otherwise (the caller keeps its previous kernels).
 int launch_hnsw_spec(mgpu_hnsw *h, const HnswDev &g, const HnswSearchArgs &a, uint32_t *err_flags, bool *launched) {
   mgpu_ctx *ctx = h->ctx;
   *launched = false;
-  // MGPU_HNSW_SPEC=0: never; =1: whenever applicable; unset: when the rows do not fit L2 (measured: on a graph of a few
-  // thousand L2-resident rows -- the SPANN centroid graph -- one expansion per round trip is already cheap and the replay
-  // overhead makes this kernel slower than k_hnsw_search_reg)
+  // MGPU_HNSW_SPEC=0: never; =1: whenever applicable; unset: when the rows do not fit L2 (on a graph of a few thousand
+  // L2-resident rows -- the SPANN centroid graph -- one expansion per round trip is already cheap: measured per case)
   static const int mode = getenv("MGPU_HNSW_SPEC") ? (getenv("MGPU_HNSW_SPEC")[0] == '0' ? 0 : 1) : 2;
   if (mode == 2 && (size_t)h->n * h->dim * 4 <= (size_t)ctx->l2_bytes / 2) return MGPU_OK;
-  if (mode == 0 || h->quant != MGPU_QUANT_NONE || a.ef == 0 || a.ef > 224 || h->max_degree > 32 || h->max_degree == 0) return MGPU_OK;
+  if (mode == 0 || h->quant != MGPU_QUANT_NONE || a.ef == 0 || a.ef > 2048 || h->max_degree > 32 || h->max_degree == 0) return MGPU_OK;
   if (h->num_layers > 1 && !g.upper_dense) return MGPU_OK;
   if (g.edges0 && g.deg0 > 32) return MGPU_OK;
   const uint32_t vis_words = h->n <= HS_BITMAP_MAX_N ? (uint32_t)((h->n + 31) / 32) + 1 : HS_HASH_CAP;
   // few queries (config 4: 256): 16 warps and 8 speculated candidates per CTA -- more rows scored per memory round trip; many
   // queries (the Spann centroid search: 1024): 8 warps / 4 candidates so that the whole batch is resident at once
   const bool wide = a.B <= (uint32_t)ctx->sm_count;   // one 16-warp CTA per SM (its registers allow no second one)
-  static const bool t8 = getenv("MGPU_HNSW_T") && atoi(getenv("MGPU_HNSW_T")) == 8;
-  const int T = (wide || t8) ? 8 : 4;
-  const size_t smem = (size_t)((h->dim + 3) & ~3u) * 4 + (size_t)vis_words * 4 + (size_t)T * 32 * 4 * 3 + T * 8 + 64;
+  const int T = wide ? 8 : 4;
+  const size_t smem = (size_t)((h->dim + 3) & ~3u) * 4 + (size_t)vis_words * 4 + (size_t)T * 32 * 4 * 3 + T * 12 + 64 + 16 +
+                      (size_t)((a.ef + 32) + (2 * a.ef + 96) + 64) * 8;
   if (smem > ctx->smem_optin) return MGPU_OK;
-  const int epl = a.ef <= 48 ? 2 : (a.ef <= 128 ? 5 : 8);
 #ifdef MGPU_SCAN_DBG
   {
     static int nl = 0;
     if (++nl == 8) {
-      unsigned long long hd[8];
+      unsigned long long hd[16];
       cudaStreamSynchronize(ctx->stream);
       cudaMemcpyFromSymbol(hd, g_hs_dbg, sizeof(hd));
       fprintf(stderr, "[hnsw spec dbg] 7 launches: batches %llu replayed expansions %llu (%.2f per batch) rows scored %llu (%.1f per batch) | cycles "
                       "per batch: speculate-1 %.0f speculate-2 %.0f replay %.0f\n", hd[0], hd[1], (double)hd[1] / hd[0], hd[2], (double)hd[2] / hd[0],
               (double)hd[3] / hd[0], (double)hd[4] / hd[0], (double)hd[5] / hd[0]);
+      fprintf(stderr, "[hnsw spec dbg] per replayed expansion: walked %.2f admitted %.2f stay %.2f; expansions with admissions %.2f; cycles per such expansion: "
+                      "walk %.0f | fixed part per expansion %.0f, plan per batch %.0f, CTA merge %.0f\n", (double)hd[7] / hd[1], (double)hd[6] / hd[1], (double)hd[12] / hd[1],
+              (double)hd[11] / hd[1], (double)hd[8] / (hd[11] ? hd[11] : 1), (double)hd[9] / hd[1], (double)hd[10] / hd[0],
+              (double)hd[13] / (hd[11] ? hd[11] : 1));
     }
   }
 #endif
   LaunchScope ls(ctx, MGPU_K_HNSW);
-#define HS_LAUNCH(MT, E, NWARP, TT)                                                                                   \
-  do {                                                                                                                \
-    cudaFuncSetAttribute(k_hnsw_spec<MT, E, NWARP, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-    k_hnsw_spec<MT, E, NWARP, TT><<<a.B, NWARP * 32, smem, ctx->stream>>>(g, a, err_flags, vis_words);                \
+#define HS_LAUNCH(MT, NWARP, TT)                                                                                   \
+  do {                                                                                                             \
+    cudaFuncSetAttribute(k_hnsw_spec<MT, NWARP, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    k_hnsw_spec<MT, NWARP, TT><<<a.B, NWARP * 32, smem, ctx->stream>>>(g, a, err_flags, vis_words);                \
   } while (0)
-#define HS_LAUNCH_W(MT, E) do { if (wide) HS_LAUNCH(MT, E, 16, 8); else if (t8) HS_LAUNCH(MT, E, 8, 8); else HS_LAUNCH(MT, E, 8, 4); } while (0)
-#define HS_LAUNCH_E(MT) do { if (epl == 2) HS_LAUNCH_W(MT, 2); else if (epl == 5) HS_LAUNCH_W(MT, 5); else HS_LAUNCH_W(MT, 8); } while (0)
-  if (h->metric == MGPU_L2) HS_LAUNCH_E(MGPU_L2); else HS_LAUNCH_E(MGPU_DOT);
-#undef HS_LAUNCH_E
+#define HS_LAUNCH_W(MT) do { if (wide) HS_LAUNCH(MT, 16, 8); else HS_LAUNCH(MT, 8, 4); } while (0)
+  if (h->metric == MGPU_L2) HS_LAUNCH_W(MGPU_L2); else HS_LAUNCH_W(MGPU_DOT);
 #undef HS_LAUNCH_W
 #undef HS_LAUNCH
   CUDA_TRY(ctx, cudaGetLastError());
