@@ -184,8 +184,16 @@ __global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : 2) k_hnsw_
       float acc = 0.0f;
       for (int c0 = 0; c0 < chunks; c0 += 48) {
         float y[48];
+        if (c0 + 48 <= chunks) {
+          // all 48 loads of the block are issued before the first is consumed (volatile keeps their order; left to itself the
+          // compiler waits after every six -- eight L2 round trips per 3 KB row instead of one)
+          const float *rp = row + c0 * 16 + h;
 #pragma unroll
-        for (int i = 0; i < 48; i++) y[i] = (c0 + i < chunks) ? __ldg(row + (c0 + i) * 16 + h) : 0.0f;
+          for (int i = 0; i < 48; i++) asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(y[i]) : "l"(rp + i * 16));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 48; i++) y[i] = (c0 + i < chunks) ? __ldg(row + (c0 + i) * 16 + h) : 0.0f;
+        }
 #pragma unroll
         for (int i = 0; i < 48; i++) {
           if (c0 + i < chunks) {
