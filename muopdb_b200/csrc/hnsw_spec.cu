@@ -9,25 +9,29 @@
 // on the oracle).  So one CTA (8 warps) per query works in batches:
 //
 //   SPECULATE (all warps, parallel)  the first T entries of the candidate list are assumed to be the next T pops: their
-//       edge rows are fetched together, every neighbour that is not in the visited set NOW is scored (rows prefetched to L2 in
-//       one burst, half-warp per row, bit-exact 16-lane order), keys parked in shared memory;
-//   REPLAY (warp 0, sequential, exact)  the reference's loop runs on registers and shared memory only: pop (with the strict
-//       '>' stop rule); if the popped id is the next speculated one, its edges are walked in stored order, a neighbour is
-//       fresh iff inserting it into the visited set succeeds (the set only grows, so fresh-now implies scored-at-speculation),
-//       admissions happen one by one exactly like index.rs:255-281.  The first pop that was not speculated (a neighbour admitted
-//       meanwhile jumped the queue) ends the batch -- nothing is lost but the unused scores.
+//       edge rows are fetched together (one warp each); a neighbour is "fresh if its candidate is replayed" when it is the
+//       first occurrence in its own list, is not in the visited set NOW, and is not listed by an earlier candidate of the
+//       batch -- one 32-bit mask per candidate.  Every such neighbour is scored (rows prefetched to L2 in one burst, half-warp
+//       per row, all 48 loads of a row block in flight, bit-exact 16-lane order), keys parked in shared memory;
+//   REPLAY (warp 0 decides, the CTA updates)  the reference's loop runs on shared memory only: pop (with the strict '>' stop
+//       rule); if the popped id is the next speculated one, its fresh mask says which neighbours index.rs:255-281 would walk.
+//       While W is full only neighbours below the furthest key can be admitted; those are walked one by one against the 32
+//       largest entries of W held one per lane (an admission drops lane 0's entry and inserts the newcomer: ~20 instructions).
+//       What the expansion admitted is then merged into the two sorted arrays by ALL warps -- one or two elements per thread,
+//       each computing its final index (old index + newcomers below it; binary search for a newcomer) -- three barriers instead
+//       of a lone warp looping over 128 + ~100 entries.  The first pop that was not speculated (a neighbour admitted meanwhile
+//       jumped the queue) ends the batch -- nothing is lost but the unused scores;
+//   MARK (next batch, all warps)  the fresh neighbours of the candidates that WERE replayed enter the visited set; the ones
+//       behind the end of the replay leave no trace.
 //
-// Same total orders as hnsw.cu (W ascending (key, id), C ascending (key, ~id)); here both are sorted arrays in shared memory and
-// an expansion updates each of them ONCE, in place: every old element moves up by the number of newcomers below it and every
-// newcomer lands on the number of elements below it, all counted with warp shuffles and one redux per newcomer
-// (hs_merge_inplace) -- instead of one sorted insertion per admitted neighbour.  A lone warp retires a dependent instruction
-// every ~5 cycles and the per-neighbour insertions into register lists (several hundred cycles each, 4-5 per expansion on the
-// 768-dimensional benchmark graph) were 80 % of a batch.  The decisions that ARE order dependent -- which neighbours get in,
-// given that the furthest key shrinks with every admission -- run on the 32 largest entries of W held one per lane (about 20
-// instructions per admission).  Same counters (distance evaluations = fresh neighbours at replay, expansions = popped
-// candidates with edges), so results AND out_stats equal the oracle's.  The visited set is a bitmap (n <= 262144) or an
-// open-addressing hash table in shared memory (no global bitmap, no atomics to L2); a query that outgrows it, or whose
-// candidate array overflows, raises err_flags[q] and is redone by k_hnsw_search.
+// Measured on config 4 (1M x 768, ef 128, 256 queries; cycles per batch of 3.41 replayed expansions): register-list replay
+// 2.9k speculate-1 + 11.6k speculate-2 + 16-18k replay (kernel 2.39 ms); CTA merges + precomputed fresh masks: replay 8.7k
+// (1.79 ms); 48 loads in flight per row block: speculate-2 ~4k (1.34 ms, 182k QPS; round 1's kernel: 3.24 ms).
+//
+// Same total orders as hnsw.cu (W ascending (key, id), C ascending (key, ~id)).  Same counters (distance evaluations = fresh
+// neighbours at replay, expansions = popped candidates with edges), so results AND out_stats equal the oracle's.  The visited
+// set is a bitmap (n <= 262144) or an open-addressing hash table in shared memory (no global bitmap, no atomics to L2); a
+// query that outgrows it, or whose candidate array overflows, raises err_flags[q] and is redone by k_hnsw_search.
 #include "hnsw_device.cuh"
 
 #define HS_TMAX 8         /* speculated candidates per batch: T <= warps, T <= HS_TMAX */
@@ -584,7 +588,7 @@ int launch_hnsw_spec(mgpu_hnsw *h, const HnswDev &g, const HnswSearchArgs &a, ui
   // few queries (config 4: 256): 16 warps and 8 speculated candidates per CTA -- more rows scored per memory round trip; many
   // queries (the Spann centroid search: 1024): 8 warps / 4 candidates so that the whole batch is resident at once
   const bool wide = a.B <= (uint32_t)ctx->sm_count;   // one 16-warp CTA per SM (its registers allow no second one)
-  const int T = wide ? 8 : 4;
+  const int T = wide ? 8 : 4;   // measured on config 4: 8 candidates per batch with 8 warps is 16 % slower than 4
   const size_t smem = (size_t)((h->dim + 3) & ~3u) * 4 + (size_t)vis_words * 4 + (size_t)T * 32 * 4 * 3 + T * 12 + 64 + 16 +
                       (size_t)((a.ef + 32) + (2 * a.ef + 96) + 64) * 8;
   if (smem > ctx->smem_optin) return MGPU_OK;
