@@ -725,10 +725,8 @@ def main():
     peak, peak_src = measured_peak_gbs()
     dom_avg_ms = dom_ms / max(args.steps, 1)   # per step: HNSW launches a register kernel + a (normally empty) generic one
     achieved = dom_bytes / (dom_avg_ms / 1e3) / 1e9 if dom_avg_ms > 0 else 0.0
-    kernel_name = {"pq": "k_scan_pq_db<3,16,4,true> (PQ posting-list LUT scan, scan_pq.cu)",
-                   "spann": "k_scan_pq_db<3,16,4,true> (PQ posting-list LUT scan, scan_pq.cu)",
-                   "flat": "k_scan<SCAN_FLAT_L2,1,512> (flat posting-list scan, scan.cu)",
-                   "hnsw": "k_hnsw_search_reg (beam search, hnsw.cu)"}[cfg]
+    # the library reports which of a class's alternative kernels served the last call (mgpu_last_kernel): never a guess
+    kernel_name = ctx.last_kernel(dom_class)
     shape_key = f"{args.config}:n{world}"
     if cfg == "pq":
         workload = f"IVF-PQ (m={m}, 8-bit) {args.n}x{args.dim}, nlist={args.nlist}, nprobe={args.nprobe}, batch={args.batch}/GPU, k={k}"

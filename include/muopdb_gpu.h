@@ -96,6 +96,9 @@ int mgpu_profile_enable(mgpu_ctx *ctx, int on);
 int mgpu_profile_reset(mgpu_ctx *ctx);
 int mgpu_profile_get(mgpu_ctx *ctx, int kernel_class, float *total_ms, uint64_t *launches);
 uint64_t mgpu_launch_count(mgpu_ctx *ctx);       /* kernels launched by this ctx since creation */
+/* Name of the kernel this context launched last in a class (scan and HNSW classes; "" if none yet): which of the
+ * alternative kernels of a class served the last call -- bench.py quotes it as roofline.kernel.  Static string. */
+const char *mgpu_last_kernel(mgpu_ctx *ctx, int kernel_class);
 
 /* ---- DistanceCalculator (rs/utils/src/lib.rs:17-40) ---------------------------------------- */
 /* out[i*nB + j] = calculate(A[i], B[j]) (or calculate_squared when `squared` != 0; dot ignores it),

@@ -165,6 +165,10 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.mgpu_launch_count(self.h))
 
+    def last_kernel(self, kernel_class: int) -> str:
+        """Name of the kernel launched last in a class (which of the alternative scan / HNSW kernels served the call)."""
+        return (self.lib.mgpu_last_kernel(self.h, kernel_class) or b"").decode()
+
     # multi-GPU (one process per GPU)
     def comm_init(self, nranks: int, rank: int, unique_id: bytes):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)

@@ -183,6 +183,12 @@ int mgpu_profile_reset(mgpu_ctx *ctx) {
   }
   return MGPU_OK;
 }
+const char *mgpu_last_kernel(mgpu_ctx *ctx, int cls) {
+  if (!ctx || cls < 0 || cls >= MGPU_K_COUNT) return "";
+  std::lock_guard<std::mutex> g(ctx->mu);
+  return ctx->last_kernel[cls] ? ctx->last_kernel[cls] : "";
+}
+
 int mgpu_profile_get(mgpu_ctx *ctx, int cls, float *total_ms, uint64_t *launches) {
   if (!ctx || cls < 0 || cls >= MGPU_K_COUNT) return MGPU_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> g(ctx->mu);

@@ -6,8 +6,11 @@
 // caller blocks in mgpu_batcher_search with ONE query; a worker thread collects what has arrived, closes the batch when it
 // holds max_batch queries or when its oldest query has waited max_wait_us, issues one batched search through the same
 // C-ABI entry points a direct caller would use, and scatters the per-query results into the callers' own buffers.
-// Two staging buffers alternate, so the next batch fills while the previous one is on the GPU.
+// Three staging buffers rotate and unfiltered IVF batches go through mgpu_ivf_search_submit / mgpu_search_wait, so two
+// batches are in flight (upload of one next to the kernels and download of the other) while a third fills; filtered and
+// Spann batches use the blocking call.
 #include <chrono>
+#include <deque>
 #include <condition_variable>
 #include <thread>
 
@@ -42,10 +45,11 @@ struct mgpu_batcher {
   uint64_t words = 0;
   std::mutex mu;
   std::condition_variable cv_work, cv_done, cv_space;
-  Staging st[2];
+  static constexpr int NBUF = 3;
+  Staging st[NBUF];
   int fill = 0;                     // buffer callers are appending to
-  bool busy[2] = {false, false};    // buffer is on the GPU (not appendable)
-  uint64_t next_generation = 1, done_generation[2] = {0, 0};
+  bool busy[NBUF] = {false, false, false};   // buffer is closed / on the GPU (not appendable)
+  uint64_t next_generation = 1, done_generation[NBUF] = {0, 0, 0};
   bool stop = false;
   std::thread worker;
   // stats
@@ -54,59 +58,91 @@ struct mgpu_batcher {
   mgpu_ctx *ctx() const { return ivf ? ivf->ctx : spann->ctx; }
 };
 
+// scatter the results of the batch in buffer `cur` to its callers and release the buffer (lock NOT held on entry)
+static void batcher_complete(mgpu_batcher *b, int cur, int status) {
+  Staging &c = b->st[cur];
+  const uint32_t n = c.n;
+  if (status == MGPU_OK) {
+    for (uint32_t i = 0; i < n; i++) {
+      const Waiter &w = c.waiters[i];
+      const uint32_t cnt = c.counts[i];
+      const uint32_t ncopy = cnt == 0xFFFFFFFFu ? 0 : std::min(cnt, b->k);
+      memcpy(w.out_docs, c.docs + (size_t)i * b->k, (size_t)ncopy * sizeof(mgpu_u128));
+      memcpy(w.out_scores, c.scores + (size_t)i * b->k, (size_t)ncopy * sizeof(float));
+      *w.out_count = cnt;
+    }
+  }
+  for (uint32_t i = 0; i < n; i++) *c.waiters[i].status = status;
+  std::lock_guard<std::mutex> g(b->mu);
+  b->done_generation[cur] = c.generation;
+  c.n = 0; c.any_filter = false; c.waiters.clear();
+  b->busy[cur] = false;
+  b->cv_done.notify_all();
+  b->cv_space.notify_all();
+}
+
 static void batcher_run(mgpu_batcher *b) {
+  std::deque<std::pair<int, uint64_t>> inflight;   // (buffer, ticket) of the submitted batches, oldest first
   std::unique_lock<std::mutex> lk(b->mu);
+  auto finish_oldest = [&]() {                     // lock held on entry and on return
+    const std::pair<int, uint64_t> f = inflight.front();
+    inflight.pop_front();
+    lk.unlock();
+    const int status = mgpu_search_wait(b->ctx(), f.second);
+    batcher_complete(b, f.first, status);
+    lk.lock();
+  };
   for (;;) {
     Staging &s = b->st[b->fill];
-    if (s.n == 0) {
-      if (b->stop) return;
-      b->cv_work.wait(lk);
-      continue;
-    }
     // close the batch when it is full, when its oldest query has waited long enough, or on shutdown
     const auto deadline = s.first_arrival + std::chrono::microseconds(b->max_wait_us);
-    if (s.n < b->max_batch && !b->stop && std::chrono::steady_clock::now() < deadline) {
-      b->cv_work.wait_until(lk, deadline);
+    const bool closable = s.n > 0 && (s.n >= b->max_batch || b->stop || std::chrono::steady_clock::now() >= deadline);
+    if (!closable) {
+      if (!inflight.empty()) { finish_oldest(); continue; }   // nothing to launch: deliver what is on the GPU
+      if (s.n == 0) {
+        if (b->stop) return;
+        b->cv_work.wait(lk);
+      } else {
+        b->cv_work.wait_until(lk, deadline);
+      }
       continue;
     }
     const int cur = b->fill;
     Staging &c = b->st[cur];
+    const bool pipelined = b->ivf != nullptr && !c.any_filter;
+    // two submissions per context; the blocking call runs behind whatever is in flight anyway, so deliver those first
+    while (inflight.size() >= (pipelined ? 2u : 1u)) finish_oldest();
     b->busy[cur] = true;
-    b->fill = 1 - cur;                       // new arrivals go to the other buffer
+    int next = -1;
+    for (int i = 0; i < mgpu_batcher::NBUF; i++) if (!b->busy[i]) { next = i; break; }   // <= 1 in flight + cur: one is free
+    b->fill = next;                          // new arrivals go to a free buffer
     b->st[b->fill].generation = b->next_generation++;
     b->cv_space.notify_all();
     const uint32_t n = c.n;
     b->n_queries += n; b->n_batches++; b->max_seen = std::max<uint64_t>(b->max_seen, n);
     if (n == b->max_batch) b->full_batches++;
     lk.unlock();
+    if (pipelined) {
+      uint64_t ticket = 0;
+      const int status = mgpu_ivf_search_submit(b->ivf, c.Q, n, b->k, b->nprobe, c.docs, c.scores, c.counts, &ticket);
+      if (status != MGPU_OK) batcher_complete(b, cur, status);
+      lk.lock();
+      if (status == MGPU_OK) inflight.emplace_back(cur, ticket);
+      continue;
+    }
     const uint32_t *fb = c.any_filter ? c.filters.data() : nullptr;
     int status;
     if (b->ivf) status = mgpu_ivf_search_filtered(b->ivf, c.Q, n, b->k, b->nprobe, fb, fb ? b->words : 0, c.docs, c.scores, c.counts, MGPU_HOST);
     else status = mgpu_spann_search_filtered(b->spann, c.Q, n, b->k, b->ef, b->nexp, b->ratio, fb, fb ? b->words : 0, c.docs, c.scores, c.counts, MGPU_HOST);
-    if (status == MGPU_OK) {
-      for (uint32_t i = 0; i < n; i++) {
-        const Waiter &w = c.waiters[i];
-        const uint32_t cnt = c.counts[i];
-        const uint32_t ncopy = cnt == 0xFFFFFFFFu ? 0 : std::min(cnt, b->k);
-        memcpy(w.out_docs, c.docs + (size_t)i * b->k, (size_t)ncopy * sizeof(mgpu_u128));
-        memcpy(w.out_scores, c.scores + (size_t)i * b->k, (size_t)ncopy * sizeof(float));
-        *w.out_count = cnt;
-      }
-    }
-    for (uint32_t i = 0; i < n; i++) *c.waiters[i].status = status;
+    batcher_complete(b, cur, status);
     lk.lock();
-    b->done_generation[cur] = c.generation;
-    c.n = 0; c.any_filter = false; c.waiters.clear();
-    b->busy[cur] = false;
-    b->cv_done.notify_all();
-    b->cv_space.notify_all();
   }
 }
 
 static int batcher_alloc(mgpu_batcher *b) {
   mgpu_ctx *ctx = b->ctx();
   cudaSetDevice(ctx->device);
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < mgpu_batcher::NBUF; i++) {
     Staging &s = b->st[i];
     CUDA_TRY(ctx, cudaMallocHost((void **)&s.Q, (size_t)b->max_batch * b->dim * sizeof(float)));
     CUDA_TRY(ctx, cudaMallocHost((void **)&s.docs, (size_t)b->max_batch * b->k * sizeof(mgpu_u128)));
@@ -162,7 +198,7 @@ void mgpu_batcher_destroy(mgpu_batcher *b) {
   b->cv_space.notify_all();
   if (b->worker.joinable()) b->worker.join();
   cudaSetDevice(b->ctx()->device);
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < mgpu_batcher::NBUF; i++) {
     cudaFreeHost(b->st[i].Q); cudaFreeHost(b->st[i].docs); cudaFreeHost(b->st[i].scores); cudaFreeHost(b->st[i].counts);
   }
   delete b;

@@ -22,6 +22,7 @@ struct mgpu_ctx {
   int sm_count = 0;
   size_t smem_optin = 0;
   size_t l2_bytes = 0;
+  const char *last_kernel[16] = {};            // per kernel class: name of the kernel launched last (string literals)
   cudaStream_t stream = nullptr;
   cudaStream_t aux_stream = nullptr;           // side stream for work that is independent of the main chain (query encode)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -79,8 +80,10 @@ int mgpu_fail(mgpu_ctx *ctx, int code, const char *fmt, ...);
 // Brackets one kernel launch for the per-class profiler and counts launches.
 struct LaunchScope {
   mgpu_ctx *ctx; int cls; cudaStream_t st;
-  LaunchScope(mgpu_ctx *c, int k, cudaStream_t s = nullptr) : ctx(c), cls(k), st(s ? s : c->stream) {
+  // `name` (a string literal) is remembered as the class's most recent kernel: mgpu_last_kernel reports what actually ran
+  LaunchScope(mgpu_ctx *c, int k, cudaStream_t s = nullptr, const char *name = nullptr) : ctx(c), cls(k), st(s ? s : c->stream) {
     ctx->launches++; ctx->prof[cls].launches++;
+    if (name) ctx->last_kernel[cls] = name;
     if (ctx->profiling >> cls & 1u) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ctx->prof[cls].ev.push_back(e); }
   }
   ~LaunchScope() {

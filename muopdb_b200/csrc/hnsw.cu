@@ -597,7 +597,7 @@ int launch_hnsw_search(mgpu_hnsw *h, const HnswSearchArgs &a) {
   if (s == MGPU_OK) s = launch_hnsw_spec(h, g, a, err, &spec);
   if (spec) epl = -1;
   if (s == MGPU_OK && epl > 0) {
-    LaunchScope ls(ctx, MGPU_K_HNSW);
+    LaunchScope ls(ctx, MGPU_K_HNSW, nullptr, "k_hnsw_search_reg (hnsw.cu)");
 #define HN_LAUNCH_R(QT, MT, E)                                                                                          \
   do {                                                                                                                  \
     cudaFuncSetAttribute(k_hnsw_search_reg<QT, MT, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_reg);     \
@@ -616,7 +616,7 @@ int launch_hnsw_search(mgpu_hnsw *h, const HnswSearchArgs &a) {
   if (s == MGPU_OK) {
     // generic kernel: the whole batch when the register kernel does not apply, otherwise only the flagged queries
     const int only_flagged = epl ? 1 : 0;
-    LaunchScope ls(ctx, MGPU_K_HNSW);
+    LaunchScope ls(ctx, MGPU_K_HNSW, nullptr, only_flagged ? nullptr : "k_hnsw_search (hnsw.cu)");
 #define HN_LAUNCH(QT, MT)                                                                                       \
   do {                                                                                                          \
     cudaFuncSetAttribute(k_hnsw_search<QT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \

@@ -609,7 +609,7 @@ int launch_hnsw_spec(mgpu_hnsw *h, const HnswDev &g, const HnswSearchArgs &a, ui
     }
   }
 #endif
-  LaunchScope ls(ctx, MGPU_K_HNSW);
+  LaunchScope ls(ctx, MGPU_K_HNSW, nullptr, wide ? "k_hnsw_spec<16 warps,T=8> (hnsw_spec.cu)" : "k_hnsw_spec<8 warps,T=4> (hnsw_spec.cu)");
 #define HS_LAUNCH(MT, NWARP, TT)                                                                                   \
   do {                                                                                                             \
     cudaFuncSetAttribute(k_hnsw_spec<MT, NWARP, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \

@@ -533,7 +533,7 @@ static int launch_scan_t(mgpu_ivf *ivf, const ScanArgs &a, const ScanSmemLayout 
   CUDA_TRY(ctx, cudaFuncSetAttribute(k_scan<MODE, NG, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   unsigned grid = a.B < (uint32_t)ctx->sm_count ? a.B : (unsigned)ctx->sm_count;
   CUDA_TRY(ctx, cudaMemsetAsync(a.next_query, 0, 4, ctx->stream));
-  LaunchScope ls(ctx, MGPU_K_SCAN);
+  LaunchScope ls(ctx, MGPU_K_SCAN, nullptr, (MODE == SCAN_FLAT_L2 || MODE == SCAN_FLAT_DOT) ? "k_scan<flat> (scan.cu)" : "k_scan<pq> (scan.cu)");
   k_scan<MODE, NG, NT><<<grid, NT, L.total, ctx->stream>>>(a, L);
   CUDA_TRY(ctx, cudaGetLastError());
   return MGPU_OK;

@@ -476,7 +476,7 @@ static int launch_db_t(mgpu_ivf *ivf, const ScanArgs &a0) {
   }
 #endif
   {
-    LaunchScope ls(ctx, MGPU_K_SCAN);
+    LaunchScope ls(ctx, MGPU_K_SCAN, nullptr, "k_scan_pq_db (32-bit LUT, scan_pq.cu)");
     k_scan_pq_db<NG, NCW, NPW, true><<<grid, (NCW + NPW) * 32, L.total, ctx->stream>>>(a, L);
     CUDA_TRY(ctx, cudaGetLastError());
   }

@@ -429,7 +429,7 @@ static int launch_p16_t(mgpu_ivf *ivf, const ScanArgs &a0, uint32_t *d_qstate) {
     }
   }
 #endif
-  LaunchScope ls(ctx, MGPU_K_SCAN);
+  LaunchScope ls(ctx, MGPU_K_SCAN, nullptr, NG == 3 ? "k_scan_pq16<3,16,4> (scan_pq16.cu)" : (NG == 2 ? "k_scan_pq16<2,16,4> (scan_pq16.cu)" : "k_scan_pq16<1,16,4> (scan_pq16.cu)"));
   k_scan_pq16<NG, NCW, NPW><<<grid, (NCW + NPW) * 32, L.total, ctx->stream>>>(a, L, ivf->pq->d_table16, d_qstate);
   CUDA_TRY(ctx, cudaGetLastError());
   return MGPU_OK;

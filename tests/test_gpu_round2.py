@@ -423,3 +423,53 @@ def test_scan16_near_ties_are_certified_or_fall_back(M):
         for b in range(len(Q)):
             assert np.array_equal(r.doc_ids[b, :oc[b]], od[b, :oc[b]]), (k, b)
             assert _same_f32(r.scores[b, :oc[b]], os_[b, :oc[b]])
+
+
+def test_micro_batcher_pipelined_batches_match_oracle(M):
+    """Unfiltered IVF batches go through mgpu_ivf_search_submit / mgpu_search_wait with three staging buffers (two batches on
+    the GPU while a third fills, batcher.cu).  Many callers with a small max_batch keep several batches in flight; every caller
+    must still get the oracle's answer for ITS query, and the stats must show real batching."""
+    import threading
+    X = synth.clustered(6000, 64, n_blobs=12, seed=77)
+    cents = O.kmeans(X, 24, iters=4, seed=2)
+    offsets, ids = O.build_posting_lists(X, cents)
+    docs = synth.doc_ids_for(len(X), seed=9)
+    oivf = O.Ivf(cents, offsets, ids, X, doc_ids=docs)
+    givf = M.BlockBasedIvf(cents, offsets, ids, X, M.NoQuantizer(64), doc_ids=docs)
+    nthreads, per_thread = 48, 10
+    Q = (X[:nthreads * per_thread] * np.float32(1.001) + 0.003).astype(np.float32)
+    mb = M.MicroBatcher(givf, k=7, num_probes=5, max_batch=8, max_wait_us=200)
+    got, errs = [None] * len(Q), []
+
+    def worker(t):
+        try:
+            for j in range(per_thread):
+                i = t * per_thread + j
+                got[i] = mb.search(Q[i])
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(nthreads)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    st = mb.stats()
+    mb.close()
+    assert st["queries"] == len(Q) and st["batches"] < len(Q) and st["largest_batch"] > 1
+    od, os_, oc = oivf.search_batch(Q, 7, 5)
+    for i in range(len(Q)):
+        n = int(oc[i])
+        assert [x.doc_id for x in got[i].id_with_scores] == [int(lo) | (int(hi) << 64) for lo, hi in od[i, :n]], i
+        assert _same_f32(np.array([x.score for x in got[i].id_with_scores], dtype=np.float32), os_[i, :n])
+
+
+def test_last_kernel_reports_the_kernel_that_ran(M):
+    """mgpu_last_kernel: bench.py quotes it as roofline.kernel (the name must be the timed kernel's)."""
+    from muopdb_b200 import _lib
+    X = synth.clustered(3000, 64, n_blobs=6, seed=5)
+    cents = O.kmeans(X, 8, iters=3, seed=1)
+    offsets, ids = O.build_posting_lists(X, cents)
+    givf = M.BlockBasedIvf(cents, offsets, ids, X, M.NoQuantizer(64))
+    givf.search_batch(X[:4], 3, 2)
+    assert givf.ctx.last_kernel(_lib.K_SCAN).startswith("k_scan<flat>")
+    assert givf.ctx.last_kernel(_lib.K_HNSW) == "" or givf.ctx.last_kernel(_lib.K_HNSW).startswith("k_hnsw")   # shared default context
