@@ -69,6 +69,7 @@ extern "C" {
     pub fn mgpu_profile_get(ctx: *mut mgpu_ctx, kernel_class: c_int, total_ms: *mut c_float, launches: *mut u64) -> c_int;
     pub fn mgpu_launch_count(ctx: *mut mgpu_ctx) -> u64;
     pub fn mgpu_last_kernel(ctx: *mut mgpu_ctx, kernel_class: c_int) -> *const c_char;
+    pub fn mgpu_coarse_band_stats(ctx: *mut mgpu_ctx, out: *mut u64, reset: c_int) -> c_int;
     pub fn mgpu_distance_batch(ctx: *mut mgpu_ctx, A: *const c_float, nA: u64, B: *const c_float, nB: u64, dim: u32,
         metric: c_int, squared: c_int, out: *mut c_float, mem: c_int) -> c_int;
     pub fn mgpu_distance_batch_lanes(ctx: *mut mgpu_ctx, A: *const c_float, nA: u64, B: *const c_float, nB: u64, dim: u32,

@@ -99,6 +99,11 @@ uint64_t mgpu_launch_count(mgpu_ctx *ctx);       /* kernels launched by this ctx
 /* Name of the kernel this context launched last in a class (scan and HNSW classes; "" if none yet): which of the
  * alternative kernels of a class served the last call -- bench.py quotes it as roofline.kernel.  Static string. */
 const char *mgpu_last_kernel(mgpu_ctx *ctx, int kernel_class);
+/* Diagnostic of the tensor-core coarse selection (find_nearest_centroids, index.rs:147-163): out[0] = centroids that fell
+ * into the uncertain band tau + 2 eps and were re-scored exactly, out[1] = queries, both summed over every selection on this
+ * device since the last reset (reset != 0 clears them).  A band near C per query means un-centred data (|x|^2 >> distances):
+ * results stay exact, the selection degenerates to a full exact scoring. */
+int mgpu_coarse_band_stats(mgpu_ctx *ctx, uint64_t out[2], int reset);
 
 /* ---- DistanceCalculator (rs/utils/src/lib.rs:17-40) ---------------------------------------- */
 /* out[i*nB + j] = calculate(A[i], B[j]) (or calculate_squared when `squared` != 0; dot ignores it),

@@ -165,6 +165,12 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.mgpu_launch_count(self.h))
 
+    def coarse_band_stats(self, reset: bool = False):
+        """(centroids re-scored exactly in the tensor-core selection's uncertain band, queries) since the last reset."""
+        out = (C.c_uint64 * 2)()
+        _lib.check(self.lib.mgpu_coarse_band_stats(self.h, out, 1 if reset else 0), self.h)
+        return int(out[0]), int(out[1])
+
     def last_kernel(self, kernel_class: int) -> str:
         """Name of the kernel launched last in a class (which of the alternative scan / HNSW kernels served the call)."""
         return (self.lib.mgpu_last_kernel(self.h, kernel_class) or b"").decode()

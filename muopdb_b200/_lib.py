@@ -62,6 +62,7 @@ SIGNATURES = {
     "mgpu_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     "mgpu_launch_count": (C.c_uint64, [C.c_void_p]),
     "mgpu_last_kernel": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "mgpu_coarse_band_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),
     "mgpu_distance_batch": (C.c_int, [C.c_void_p, _f32p, C.c_uint64, _f32p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, _f32p, C.c_int]),
     "mgpu_distance_batch_lanes": (C.c_int, [C.c_void_p, _f32p, C.c_uint64, _f32p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, _f32p, C.c_int]),
     "mgpu_pq_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _f32p, C.c_int, C.POINTER(C.c_void_p)]),

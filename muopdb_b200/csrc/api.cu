@@ -183,6 +183,13 @@ int mgpu_profile_reset(mgpu_ctx *ctx) {
   }
   return MGPU_OK;
 }
+int mgpu_coarse_band_stats(mgpu_ctx *ctx, uint64_t out[2], int reset) {
+  if (!ctx || !out) return MGPU_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  return coarse_band_stats(ctx, out, reset);
+}
+
 const char *mgpu_last_kernel(mgpu_ctx *ctx, int cls) {
   if (!ctx || cls < 0 || cls >= MGPU_K_COUNT) return "";
   std::lock_guard<std::mutex> g(ctx->mu);

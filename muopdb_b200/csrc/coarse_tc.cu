@@ -25,6 +25,13 @@
 #define TC_THREADS 192
 #define TC_ERR_REL 3.0e-4f
 
+// Diagnostic for the margin rule's silent cliff: [0] centroids in the uncertain band (re-scored exactly),
+// [1] queries, summed over every selection since the last reset.  On centred data the band holds a handful of centroids per
+// query; on un-centred data (|x|^2 >> distances) it grows towards all C -- still exact, but the selection then costs a full
+// exact scoring.  Read by mgpu_coarse_band_stats.
+__device__ unsigned long long g_coarse_band[2];
+
+
 // ---- split ---------------------------------------------------------------------------------------------------------------
 __global__ void k_split_bf16(const float *__restrict__ X, uint64_t n, uint32_t dim, uint32_t Kp, int is_centroid,
                              __nv_bfloat16 *__restrict__ out, float *__restrict__ norms) {
@@ -309,6 +316,7 @@ k_coarse_select(const float *__restrict__ Dt, const float *__restrict__ Q, const
   const uint32_t nsure = min(misc[3], nprobe);
   const uint32_t need = nprobe - nsure;
   if (ncand > cand_cap) { if (tid == 0) atomicAdd(overflow, 1u); ncand = cand_cap; }
+  if (tid == 0) { atomicAdd(&g_coarse_band[0], (unsigned long long)ncand); atomicAdd(&g_coarse_band[1], 1ull); }
   if (!need_order && ncand <= need) {
     // the whole band belongs to the answer: nothing to decide, nothing to re-score
     for (uint32_t i = tid; i < ncand; i += SEL_THREADS) out_ids[(size_t)q * nprobe + nsure + i] = cand[i];
@@ -587,6 +595,7 @@ k_coarse_select_q(const float *__restrict__ Dt, const float *__restrict__ Q, con
     if (tid == 0) { flags[q] = 1u; if (work_out) work_out[q] = 0; }
     return;
   }
+  if (tid == 0) { atomicAdd(&g_coarse_band[0], (unsigned long long)ncand); atomicAdd(&g_coarse_band[1], 1ull); }
   const uint32_t need = nprobe - nsure;
   uint32_t *oi = out_ids + (size_t)q * nprobe;
   uint32_t mywork = 0;
@@ -800,5 +809,14 @@ int launch_coarse_tc(mgpu_ctx *ctx, const float *dQ, uint32_t B, const float *d_
                                                             out_dist, d_overflow, only_flagged);
     CUDA_TRY(ctx, cudaGetLastError());
   }
+  return MGPU_OK;
+}
+
+int coarse_band_stats(mgpu_ctx *ctx, uint64_t out[2], int reset) {
+  unsigned long long h[2] = {0, 0};
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyFromSymbol(h, g_coarse_band, sizeof(h)));
+  out[0] = h[0]; out[1] = h[1];
+  if (reset) { h[0] = h[1] = 0; CUDA_TRY(ctx, cudaMemcpyToSymbol(g_coarse_band, h, sizeof(h))); }
   return MGPU_OK;
 }

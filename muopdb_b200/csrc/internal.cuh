@@ -204,6 +204,7 @@ int launch_merge_rounds(mgpu_ctx *ctx, const uint32_t *pids, const float *scores
 uint32_t coarse_tc_kp(uint32_t dim);
 bool coarse_tc_applicable(mgpu_ctx *ctx, uint32_t dim, uint32_t C, uint32_t nprobe);
 int launch_split_bf16(mgpu_ctx *ctx, const float *dX, uint64_t n, uint32_t dim, int is_centroid, void *d_out, float *d_norms);
+int coarse_band_stats(mgpu_ctx *ctx, uint64_t out[2], int reset);
 int launch_coarse_tc(mgpu_ctx *ctx, const float *dQ, uint32_t B, const float *d_centroids, const void *d_csplit, const float *d_cn,
                      float cn_max, uint32_t C, uint32_t dim, uint32_t nprobe, void *d_qsplit, float *d_qn, float *d_Dt,
                      uint32_t *d_overflow, uint32_t *d_flags, int need_order, uint32_t *out_ids, float *out_dist,

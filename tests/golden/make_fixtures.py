@@ -1,7 +1,7 @@
 """Generates tests/golden/* from the reference checkout (run in the build container only).
 
-  rows_2048x128.f32 : first 2048 rows of rs/index/resources/10000_rows_128_dim (LE f32, uniform[0,1));
-                      the reference's own committed dataset for BASELINE config 1.
+  rows_10000x128.f32 : rs/index/resources/10000_rows_128_dim, all 10 000 rows (LE f32, uniform[0,1)): the reference's own
+                       committed dataset for BASELINE config 1.
 """
 import os
 import numpy as np
@@ -24,5 +24,5 @@ def copy_hnsw_sample():
 if __name__ == "__main__":
     copy_hnsw_sample()
     a = np.fromfile(REF, dtype="<f4").reshape(10000, 128)
-    a[:2048].tofile(os.path.join(HERE, "rows_2048x128.f32"))
-    print("wrote rows_2048x128.f32", a[:2048].shape, float(a.min()), float(a.max()))
+    a.tofile(os.path.join(HERE, "rows_10000x128.f32"))
+    print("wrote rows_10000x128.f32", a.shape, float(a.min()), float(a.max()))

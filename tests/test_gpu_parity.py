@@ -138,10 +138,10 @@ def _check_ivf(M, X, nlist, nprobe, k, pq_params=None, max_clusters=1, metric="l
 
 
 def test_ivf_flat_config1_fixture(M):
-    """BASELINE config 1 shape on the reference's own committed rows (rs/index/resources/10000_rows_128_dim, first
-    2048 rows committed under tests/golden): IVF flat-L2, 128-d, nlist 64, nprobe 8."""
+    """BASELINE config 1 on the reference's own committed rows (rs/index/resources/10000_rows_128_dim, all 10 000 rows
+    committed under tests/golden): IVF flat-L2, 10k x 128, nlist 64, nprobe 8."""
     import os
-    X = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "rows_2048x128.f32"), dtype="<f4").reshape(2048, 128)
+    X = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "rows_10000x128.f32"), dtype="<f4").reshape(10000, 128)
     _check_ivf(M, X, nlist=64, nprobe=8, k=10, nq=100)
 
 

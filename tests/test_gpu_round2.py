@@ -306,7 +306,12 @@ def test_coarse_tensor_core_margin_adversarial(M, case):
     oivf = O.Ivf(cents, offsets, ids, X)
     givf = M.BlockBasedIvf(cents, offsets, ids, X, M.NoQuantizer(dim))
     Q = (X[rng.integers(0, n, 48)] * np.float32(1.0001)).astype(np.float32)
+    givf.ctx.coarse_band_stats(reset=True)
     gp, gd = givf.find_nearest_centroids_batch(Q, 16, with_distances=True)
+    band, nq = givf.ctx.coarse_band_stats()
+    # the size of the uncertain band is the cost of the margin rule: recorded (pytest -s / -rP) and bounded by C per query
+    print(f"coarse band [{case}]: {band / max(nq, 1):.1f} of {nlist} centroids re-scored per query ({nq} selections)")
+    assert nq >= len(Q) and band <= nq * nlist
     for b in range(len(Q)):
         op, od = oivf.find_nearest_centroids(Q[b], 16, with_dist=True)
         assert _same_f32(od, gd[b]), (case, b)
@@ -461,6 +466,21 @@ def test_micro_batcher_pipelined_batches_match_oracle(M):
         n = int(oc[i])
         assert [x.doc_id for x in got[i].id_with_scores] == [int(lo) | (int(hi) << 64) for lo, hi in od[i, :n]], i
         assert _same_f32(np.array([x.score for x in got[i].id_with_scores], dtype=np.float32), os_[i, :n])
+
+
+def test_coarse_band_is_small_on_centred_data(M):
+    """On centred, well-spread data the tensor-core selection re-scores only a few centroids per query (the margin rule's
+    normal regime); the counter is what exposes the un-centred cliff of the test above."""
+    rng = np.random.default_rng(8)
+    dim, nlist = 128, 1024
+    cents = rng.standard_normal((nlist, dim)).astype(np.float32)
+    X = (cents[rng.integers(0, nlist, 4000)] + 0.1 * rng.standard_normal((4000, dim))).astype(np.float32)
+    offsets, ids = O.build_posting_lists(X, cents)
+    givf = M.BlockBasedIvf(cents, offsets, ids, X, M.NoQuantizer(dim))
+    givf.ctx.coarse_band_stats(reset=True)
+    givf.find_nearest_centroids_batch(X[:64], 16)
+    band, nq = givf.ctx.coarse_band_stats()
+    assert nq >= 64 and band / nq < 64, (band, nq)
 
 
 def test_last_kernel_reports_the_kernel_that_ran(M):
