@@ -142,8 +142,10 @@ struct HsVisited {
 };
 
 template <int METRIC, int HS_WARPS, int HS_T>
-__global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : 2) k_hnsw_spec(HnswDev g, HnswSearchArgs a, uint32_t *__restrict__ err_flags, uint32_t vis_words) {
+__global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : (HS_WARPS == 4 ? 4 : (HS_WARPS == 2 ? 7 : 2))) k_hnsw_spec(HnswDev g, HnswSearchArgs a, uint32_t *__restrict__ err_flags, uint32_t vis_words) {
   constexpr int HS_THREADS = HS_WARPS * 32;
+  constexpr int HS_KPT = HS_WARPS >= 4 ? 2 : 4;       // elements per thread in the CTA merges: each half of the CTA holds
+  constexpr int HS_MCAP = HS_THREADS / 2 * HS_KPT;    // up to HS_MCAP (>= 128) entries of W or of C
   static_assert(HS_T <= HS_WARPS && HS_T <= HS_TMAX, "one warp fetches the edges of one speculated candidate");
   extern __shared__ __align__(16) uint8_t smem[];
   const uint32_t ef = a.ef;
@@ -400,7 +402,7 @@ __global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : 2) k_hnsw_
                 const int na = __popc(admitted);
                 fresh &= ~admitted;
                 if (!candidate_room(na)) overflow = true;
-                else if (nW <= HS_THREADS && nC - head <= HS_THREADS) {
+                else if (nW <= HS_MCAP && nC - head <= HS_MCAP) {
                   if (take) { aw[rank] = xw; ac[rank] = xc; }
                   cadd_le = na;
                   if (lane == 0) {
@@ -459,7 +461,7 @@ __global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : 2) k_hnsw_
                   // the newcomers evicted again were pushed to C as well (and are cut off unless tied with the furthest key)
                   const int naW = __popc(stay), naC = __popc(adm2);
                   if (!candidate_room(naC)) overflow = true;
-                  else if (nW - naW <= HS_THREADS && nC - head <= HS_THREADS) {
+                  else if (nW - naW <= HS_MCAP && nC - head <= HS_MCAP) {
                     const unsigned below = (1u << lane) - 1;
                     if ((stay >> lane) & 1u) aw[__popc(stay & below)] = xw;
                     if ((adm2 >> lane) & 1u) ac[__popc(adm2 & below)] = xc;
@@ -501,15 +503,15 @@ __global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : 2) k_hnsw_
           const uint64_t *add = isC ? ac : aw;
           const int n = isC ? st[12] : st[9], na = isC ? st[10] : st[8];
           const uint32_t fkk = (uint32_t)st[13];
-          uint64_t x[2];
-          int r[2] = {0, 0};
+          uint64_t x[HS_KPT];
+          int r[HS_KPT];
 #pragma unroll
-          for (int k = 0; k < 2; k++) { const int idx = i + k * HALF; x[k] = idx < n ? A[idx] : ~0ull; }
+          for (int k = 0; k < HS_KPT; k++) { const int idx = i + k * HALF; x[k] = idx < n ? A[idx] : ~0ull; r[k] = 0; }
 #pragma unroll 4
           for (int j = 0; j < na; j++) {
             const uint64_t v = add[j];
-            r[0] += v < x[0] ? 1 : 0;
-            r[1] += v < x[1] ? 1 : 0;
+#pragma unroll
+            for (int k = 0; k < HS_KPT; k++) r[k] += v < x[k] ? 1 : 0;
           }
           int apos = -1;
           uint64_t amine = 0;
@@ -521,14 +523,14 @@ __global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : 2) k_hnsw_
           }
           if (isC) {                                    // candidates strictly farther than the furthest key are cut off
 #pragma unroll
-            for (int k = 0; k < 2; k++) {
+            for (int k = 0; k < HS_KPT; k++) {
               const int idx = i + k * HALF;
               if (idx < n && (uint32_t)(x[k] >> 32) <= fkk && (idx + 1 == n || (uint32_t)(A[idx + 1] >> 32) > fkk)) st[14] = idx + 1;
             }
           }
           __syncthreads();                              // (S2) every element is in a register
 #pragma unroll
-          for (int k = 0; k < 2; k++) { const int idx = i + k * HALF; if (idx < n && r[k]) A[idx + r[k]] = x[k]; }
+          for (int k = 0; k < HS_KPT; k++) { const int idx = i + k * HALF; if (idx < n && r[k]) A[idx + r[k]] = x[k]; }
           if (apos >= 0) A[apos] = amine;
           __syncthreads();                              // (S3)
           if (warp == 0) nC = head + st[14] + cadd_le;
@@ -577,18 +579,23 @@ __global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : 2) k_hnsw_
 int launch_hnsw_spec(mgpu_hnsw *h, const HnswDev &g, const HnswSearchArgs &a, uint32_t *err_flags, bool *launched) {
   mgpu_ctx *ctx = h->ctx;
   *launched = false;
-  // MGPU_HNSW_SPEC=0: never; =1: whenever applicable; unset: when the rows do not fit L2 (on a graph of a few thousand
-  // L2-resident rows -- the SPANN centroid graph -- one expansion per round trip is already cheap: measured per case)
-  static const int mode = getenv("MGPU_HNSW_SPEC") ? (getenv("MGPU_HNSW_SPEC")[0] == '0' ? 0 : 1) : 2;
-  if (mode == 2 && (size_t)h->n * h->dim * 4 <= (size_t)ctx->l2_bytes / 2) return MGPU_OK;
+  // MGPU_HNSW_SPEC=0: never (hnsw.cu's kernels); unset / 1: whenever applicable
+  static const int mode = getenv("MGPU_HNSW_SPEC") ? (getenv("MGPU_HNSW_SPEC")[0] == '0' ? 0 : 1) : 1;
   if (mode == 0 || h->quant != MGPU_QUANT_NONE || a.ef == 0 || a.ef > 2048 || h->max_degree > 32 || h->max_degree == 0) return MGPU_OK;
   if (h->num_layers > 1 && !g.upper_dense) return MGPU_OK;
   if (g.edges0 && g.deg0 > 32) return MGPU_OK;
   const uint32_t vis_words = h->n <= HS_BITMAP_MAX_N ? (uint32_t)((h->n + 31) / 32) + 1 : HS_HASH_CAP;
-  // few queries (config 4: 256): 16 warps and 8 speculated candidates per CTA -- more rows scored per memory round trip; many
-  // queries (the Spann centroid search: 1024): 8 warps / 4 candidates so that the whole batch is resident at once
   const bool wide = a.B <= (uint32_t)ctx->sm_count;   // one 16-warp CTA per SM (its registers allow no second one)
-  const int T = wide ? 8 : 4;   // measured on config 4: 8 candidates per batch with 8 warps is 16 % slower than 4
+  // Three shapes (measured): few queries (<= one per SM): 16 warps, 8 candidates per batch; a graph whose
+  // rows stay in L2 searched by many queries (the Spann centroid graph: 4096 x 768, 1024 queries): 2 warps, 2 candidates --
+  // seven CTAs per SM keep the whole batch resident (the replay is one warp's latency chain: what counts is how many of
+  // them an SM interleaves) and the L2-resident rows make a batch's scoring short, so speculating further only wastes it.
+  // Kernel time per 1024 queries: 1.15 ms, vs 1.49 with 4 warps (MGPU_HNSW_SMALL=1), 2.1 with 8 warps / 4 candidates and
+  // 1.54 for hnsw.cu's register-list kernel.  Otherwise 8 warps, 4 candidates.
+  static const int small_env = getenv("MGPU_HNSW_SMALL") ? atoi(getenv("MGPU_HNSW_SMALL")) : -1;
+  const bool l2_resident = (size_t)h->n * h->dim * 4 <= (size_t)ctx->l2_bytes / 2;
+  const bool small = !wide && (small_env >= 0 ? small_env != 0 : (l2_resident && a.B >= 2u * (uint32_t)ctx->sm_count));
+  const int T = wide ? 8 : (small ? 2 : 4);
   const size_t smem = (size_t)((h->dim + 3) & ~3u) * 4 + (size_t)vis_words * 4 + (size_t)T * 32 * 4 * 3 + T * 12 + 64 + 16 +
                       (size_t)((a.ef + 32) + (2 * a.ef + 96) + 64) * 8;
   if (smem > ctx->smem_optin) return MGPU_OK;
@@ -609,13 +616,13 @@ int launch_hnsw_spec(mgpu_hnsw *h, const HnswDev &g, const HnswSearchArgs &a, ui
     }
   }
 #endif
-  LaunchScope ls(ctx, MGPU_K_HNSW, nullptr, wide ? "k_hnsw_spec<16 warps,T=8> (hnsw_spec.cu)" : "k_hnsw_spec<8 warps,T=4> (hnsw_spec.cu)");
+  LaunchScope ls(ctx, MGPU_K_HNSW, nullptr, wide ? "k_hnsw_spec<16 warps,T=8> (hnsw_spec.cu)" : (small ? "k_hnsw_spec<2 warps,T=2> (hnsw_spec.cu)" : "k_hnsw_spec<8 warps,T=4> (hnsw_spec.cu)"));
 #define HS_LAUNCH(MT, NWARP, TT)                                                                                   \
   do {                                                                                                             \
     cudaFuncSetAttribute(k_hnsw_spec<MT, NWARP, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     k_hnsw_spec<MT, NWARP, TT><<<a.B, NWARP * 32, smem, ctx->stream>>>(g, a, err_flags, vis_words);                \
   } while (0)
-#define HS_LAUNCH_W(MT) do { if (wide) HS_LAUNCH(MT, 16, 8); else HS_LAUNCH(MT, 8, 4); } while (0)
+#define HS_LAUNCH_W(MT) do { if (wide) HS_LAUNCH(MT, 16, 8); else if (small && small_env == 1) HS_LAUNCH(MT, 4, 2); else if (small) HS_LAUNCH(MT, 2, 2); else HS_LAUNCH(MT, 8, 4); } while (0)
   if (h->metric == MGPU_L2) HS_LAUNCH_W(MGPU_L2); else HS_LAUNCH_W(MGPU_DOT);
 #undef HS_LAUNCH_W
 #undef HS_LAUNCH
