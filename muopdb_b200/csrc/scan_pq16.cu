@@ -340,7 +340,16 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1) k_scan_pq16(ScanArgs a, P
         uint32_t *ct = ctab + p * P16_CTAB_CAP;
         for (uint32_t i = pwarp; i < np; i += NPW) {
           const uint32_t first_it = prefp[i], cnt = prefp[i + 1] - first_it, cs = pcsp[i], len = plenp[i];
-          for (uint32_t j = lane; j < cnt; j += 32) ct[first_it + j] = ((cs + j) << 5) | (min(32u, len - 32u * j) - 1u);
+          for (uint32_t j = lane; j < cnt; j += 32) {
+            ct[first_it + j] = ((cs + j) << 5) | (min(32u, len - 32u * j) - 1u);
+            // every consumer warp starts a query with a cold load of its first chunk record: bring those records to L2 now,
+            // one query ahead (the producers idle half of the time at the sharded shape)
+            if (first_it + j < (uint32_t)NCW) {
+              const char *rec = (const char *)a.codes + (size_t)(cs + j) * (NG * 1024u + 128u);
+#pragma unroll 1
+              for (uint32_t o = 0; o < NG * 1024u + 128u; o += 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + o));
+            }
+          }
         }
       }
       DBG_T(pt2);
