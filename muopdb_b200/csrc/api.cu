@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" boundary declared in include/muopdb_gpu.h: contexts, resident index handles and the
 // per-call orchestration (H2D staging -> kernels on the ctx stream -> D2H).  No CPU compute fallback exists:
 // every entry point that computes needs a CUDA device.
+#include <chrono>
 #include <dlfcn.h>
 #include <stdarg.h>
 
@@ -1154,6 +1155,15 @@ static int shard_slot_begin(mgpu_ctx *ctx, uint32_t B, uint32_t k, mgpu_ctx::Sha
 
 // All-gather of the per-shard top-k over NVLink + merge (snapshot.rs:60-61,105-106), on the exchange stream: it starts when
 // the local search of this batch is done and does not hold up the main stream.
+// MGPU_HOST_PROF=1: host microseconds spent inside the NCCL enqueue calls and inside the whole sharded call, printed every 64
+// calls (where does the host's time per step go at N = 8?)
+struct HostProf {
+  double nccl_us = 0, call_us = 0, pre_us = 0, local_us = 0, xchg_us = 0; uint64_t calls = 0;
+  static bool on() { static const bool v = getenv("MGPU_HOST_PROF") && getenv("MGPU_HOST_PROF")[0] == '1'; return v; }
+  static double now() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+};
+static HostProf g_hostprof;
+
 static int shard_exchange(mgpu_ctx *ctx, mgpu_ctx::ShardSlot *sl, const ShardBufs &b, const mgpu_u128 *locD, const float *locS,
                           const uint32_t *locC, uint32_t B, uint32_t k, mgpu_u128 *oD, float *oS, uint32_t *oC) {
   auto ag = (fn_ncclAllGather)nccl_sym("ncclAllGather");
@@ -1167,11 +1177,13 @@ static int shard_exchange(mgpu_ctx *ctx, mgpu_ctx::ShardSlot *sl, const ShardBuf
   // exchange is latency bound: three separate collectives cost three launch + handshake latencies)
   auto gs = (fn_ncclGroup)nccl_sym("ncclGroupStart");
   auto ge = (fn_ncclGroup)nccl_sym("ncclGroupEnd");
+  const double hp0 = HostProf::on() ? HostProf::now() : 0;
   const bool grouped = gs && ge && gs() == 0;
   int r = ag(locD, b.gD, nloc * 16, 0, comm, ctx->comm_stream);
   if (r == 0) r = ag(locS, b.gS, nloc * 4, 0, comm, ctx->comm_stream);
   if (r == 0) r = ag(locC, b.gC, (size_t)B * 4, 0, comm, ctx->comm_stream);
   if (grouped) { const int r2 = ge(); if (r == 0) r = r2; }
+  if (HostProf::on()) g_hostprof.nccl_us += HostProf::now() - hp0;
   if (r != 0) return mgpu_fail(ctx, MGPU_ERR_NCCL, "ncclAllGather failed (%d)", r);
   ctx->launches += 3;
   MGPU_TRY(launch_merge_topk(ctx, b.gD, b.gS, b.gC, S, B, k, oD, oS, oC, ctx->comm_stream));
@@ -1223,6 +1235,21 @@ static int shard_search_impl(mgpu_ivf *ivf, mgpu_spann *sp, const float *Q, uint
   std::lock_guard<std::mutex> g(ctx->mu);
   cudaSetDevice(ctx->device);
   if (B == 0) return MGPU_OK;
+  struct CallTimer {
+    double t0 = HostProf::on() ? HostProf::now() : 0;
+    ~CallTimer() {
+      if (!HostProf::on()) return;
+      g_hostprof.call_us += HostProf::now() - t0;
+      static const int win = getenv("MGPU_HOST_PROF_N") ? std::max(1, atoi(getenv("MGPU_HOST_PROF_N"))) : 64;
+      if (++g_hostprof.calls % win == 0) {
+        const double n = (double)win;
+        fprintf(stderr, "[host prof] last window of sharded calls: %.1f us per call on the host (before the local search %.1f, local search %.1f, "
+                        "exchange %.1f), %.1f us inside NCCL enqueues\n", g_hostprof.call_us / n, g_hostprof.pre_us / n, g_hostprof.local_us / n,
+                g_hostprof.xchg_us / n, g_hostprof.nccl_us / n);
+        g_hostprof.call_us = g_hostprof.pre_us = g_hostprof.local_us = g_hostprof.xchg_us = g_hostprof.nccl_us = 0;
+      }
+    }
+  } call_timer;
   if (k == 0 && !sp) {
     if (mem == MGPU_HOST) memset(out_counts, 0, (size_t)B * 4);
     else CUDA_TRY(ctx, cudaMemsetAsync(out_counts, 0, (size_t)B * 4, ctx->stream));
@@ -1280,13 +1307,19 @@ static int shard_search_impl(mgpu_ivf *ivf, mgpu_spann *sp, const float *Q, uint
   if (split_encode) {
     const uint32_t lo = std::min(B, r * slice), cnt = std::min(B, lo + slice) - lo;
     if (cnt) MGPU_TRY(launch_pq_quantize(ivf->pq, dQ + (size_t)lo * ivf->dim, cnt, codes_mine));
+    const double hp0 = HostProf::on() ? HostProf::now() : 0;
     int rc = ag(codes_mine, codes_all, (size_t)slice * m, 0, ctx->nccl_comm, ctx->stream);
+    if (HostProf::on()) g_hostprof.nccl_us += HostProf::now() - hp0;
     if (rc != 0) return mgpu_fail(ctx, MGPU_ERR_NCCL, "ncclAllGather (query codes) failed (%d)", rc);
     ctx->launches += 1;
     ext = codes_all;  // rank j's slice starts at j*slice*m = (first query of the slice)*m: query q sits at q*m
   }
+  const double hp1 = HostProf::on() ? HostProf::now() : 0;
+  if (HostProf::on()) g_hostprof.pre_us += hp1 - call_timer.t0;
   if (sp) MGPU_TRY(spann_search_impl(sp, dQ, B, k, ef, num_explored, ratio, nullptr, 0, b.locD, b.locS, b.locC, MGPU_DEVICE, true, ext));
   else MGPU_TRY(ivf_search_impl(ivf, dQ, B, nullptr, 0, nullptr, nprobe, k, nullptr, b.locD, b.locS, b.locC, MGPU_DEVICE, nullptr, 0, nullptr, ext, true));
+  const double hp2 = HostProf::on() ? HostProf::now() : 0;
+  if (HostProf::on()) g_hostprof.local_us += hp2 - hp1;
   mgpu_u128 *oD = mem == MGPU_DEVICE ? out_doc_ids : b.outD;
   float *oS = mem == MGPU_DEVICE ? out_scores : b.outS;
   uint32_t *oC = mem == MGPU_DEVICE ? out_counts : b.outC;
@@ -1295,6 +1328,7 @@ static int shard_search_impl(mgpu_ivf *ivf, mgpu_spann *sp, const float *Q, uint
     oD = wo.get<mgpu_u128>((size_t)B * kk); oS = wo.get<float>((size_t)B * kk); oC = wo.get<uint32_t>(B);
   }
   MGPU_TRY(shard_exchange(ctx, sl, b, b.locD, b.locS, b.locC, B, kk, oD, oS, oC));
+  if (HostProf::on()) g_hostprof.xchg_us += HostProf::now() - hp2;
   if (pp) return pipe_end(ctx, pp, B, k, oD, oS, oC, out_doc_ids, out_scores, out_counts, ticket, sl->ev_xdone);
   if (mem == MGPU_DEVICE) {
     // stream-ordered contract: later work on the ctx stream sees the merged result -- unless the caller opted into overlap

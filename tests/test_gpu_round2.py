@@ -493,3 +493,32 @@ def test_last_kernel_reports_the_kernel_that_ran(M):
     givf.search_batch(X[:4], 3, 2)
     assert givf.ctx.last_kernel(_lib.K_SCAN).startswith("k_scan<flat>")
     assert givf.ctx.last_kernel(_lib.K_HNSW) == "" or givf.ctx.last_kernel(_lib.K_HNSW).startswith("k_hnsw")   # shared default context
+
+
+@pytest.mark.parametrize("B,ef,n,dim,k", [(200, 64, 3000, 32, 10),    # 148 < B < 296: 8 warps, 4 candidates per batch
+                                          (320, 128, 4000, 64, 64),   # B >= 296 on an L2-resident graph: 2 warps, 2 candidates
+                                          (320, 300, 2500, 16, 100),  # ... whose CTA merge holds 128 entries: warp-level merges
+                                          (200, 300, 2500, 16, 32),   # 8 warps, ef beyond the CTA merge's 256 entries
+                                          (40, 600, 1500, 8, 10),     # <= one query per SM: 16 warps, 8 candidates; large ef
+                                          (300, 1, 600, 4, 1)])       # ef = 1
+def test_hnsw_batch_kernel_shapes(M, B, ef, n, dim, k):
+    """Every shape of k_hnsw_spec (hnsw_spec.cu: chosen by batch size and graph size) and both merge paths must give the
+    oracle's ids, scores and traversal counts (hnsw/block_based/index.rs:159-298)."""
+    from muopdb_b200 import _lib
+    X = synth.clustered(n, dim, n_blobs=9, seed=dim + ef)
+    g = O.hnsw_build(X, 16, 5, 60, seed=ef)
+    docs = synth.doc_ids_for(n, seed=2)
+    oh = O.Hnsw(g["num_layers"], g["edges"], g["points"], g["edge_offsets"], g["level_offsets"], X, doc_ids=docs)
+    gh = M.BlockBasedHnsw(g["num_layers"], g["edges"], g["points"], g["edge_offsets"], g["level_offsets"], X,
+                          M.NoQuantizer(dim), doc_ids=docs)
+    rng = np.random.default_rng(ef)
+    Q = np.vstack([X[rng.integers(0, n, B // 2)] + 0.02 * rng.standard_normal((B // 2, dim)).astype(np.float32),
+                   rng.random((B - B // 2, dim), dtype=np.float32)]).astype(np.float32)
+    od, os_, oc, ost = oh.search_batch(Q, k, ef)
+    r, st = gh.ann_search_batch(Q, k, ef, with_stats=True)
+    assert gh.ctx.last_kernel(_lib.K_HNSW).startswith("k_hnsw_spec"), gh.ctx.last_kernel(_lib.K_HNSW)
+    assert np.array_equal(np.asarray(r.counts, dtype=np.int64), oc.astype(np.int64))
+    for b in range(B):
+        assert np.array_equal(r.doc_ids[b, :oc[b]], od[b, :oc[b]]), b
+        assert _same_f32(r.scores[b, :oc[b]], os_[b, :oc[b]]), b
+    assert np.array_equal(st, ost)
