@@ -586,7 +586,12 @@ static int ivf_scan_dev(mgpu_ivf *ivf, const float *dQ, uint32_t B, const uint32
     mgpu_pq *pq = ivf->pq;
     a.m = pq->m; a.K = pq->K; a.table = pq->d_table; a.rowmin = pq->d_rowmin; a.rowmax = pq->d_rowmax;
     // the query is quantized with the same codebook (index.rs:193) -- once per query here, not once per list
-    if (have_codes) {}  // the caller already holds the query codes (sharded search: encoded once across the ranks)
+    if (have_codes) {   // the caller already holds the query codes (sharded search: encoded once across the ranks) ...
+      if (ctx->ext_codes_on_aux) {   // ... or is still gathering them on the side stream
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        ctx->ext_codes_on_aux = false;
+      }
+    }
     else if (qcodes_on_aux) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // encoded on the side stream
     else MGPU_TRY(launch_pq_quantize(pq, dQ, B, d_qcodes));
     a.qcodes = d_qcodes;
@@ -1305,10 +1310,21 @@ static int shard_search_impl(mgpu_ivf *ivf, mgpu_spann *sp, const float *Q, uint
   }
   const uint8_t *ext = nullptr;
   if (split_encode) {
+    // on the side stream: neither the coarse GEMM nor the selection needs the codes, only the scan does (it waits for ev_join)
+    static const bool aux_off = getenv("MGPU_AUX_STREAM") && getenv("MGPU_AUX_STREAM")[0] == '0';
+    cudaStream_t es = aux_off ? ctx->stream : ctx->aux_stream;
+    if (!aux_off) {
+      CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));          // the batch is on the device
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    }
     const uint32_t lo = std::min(B, r * slice), cnt = std::min(B, lo + slice) - lo;
-    if (cnt) MGPU_TRY(launch_pq_quantize(ivf->pq, dQ + (size_t)lo * ivf->dim, cnt, codes_mine));
+    if (cnt) MGPU_TRY(launch_pq_quantize(ivf->pq, dQ + (size_t)lo * ivf->dim, cnt, codes_mine, es));
     const double hp0 = HostProf::on() ? HostProf::now() : 0;
-    int rc = ag(codes_mine, codes_all, (size_t)slice * m, 0, ctx->nccl_comm, ctx->stream);
+    int rc = ag(codes_mine, codes_all, (size_t)slice * m, 0, ctx->nccl_comm, es);
+    if (!aux_off && rc == 0) {
+      CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+      ctx->ext_codes_on_aux = true;
+    }
     if (HostProf::on()) g_hostprof.nccl_us += HostProf::now() - hp0;
     if (rc != 0) return mgpu_fail(ctx, MGPU_ERR_NCCL, "ncclAllGather (query codes) failed (%d)", rc);
     ctx->launches += 1;

@@ -26,6 +26,7 @@ struct mgpu_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t aux_stream = nullptr;           // side stream for work that is independent of the main chain (query encode)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool ext_codes_on_aux = false;               // sharded search: the gathered query codes are ready at ev_join (side stream)
   std::mutex mu;
   std::string err;
   // workspace (grown on demand)
