@@ -34,6 +34,8 @@
 // query that outgrows it, or whose candidate array overflows, raises err_flags[q] and is redone by k_hnsw_search.
 #include "hnsw_device.cuh"
 
+#include <algorithm>
+
 #define HS_TMAX 8         /* speculated candidates per batch: T <= warps, T <= HS_TMAX */
 #define HS_HASH_LOG 13
 #define HS_BITMAP_MAX_N 262144u   /* up to this many points the visited set is a plain bitmap in shared memory (32 KB) */
@@ -142,7 +144,7 @@ struct HsVisited {
 };
 
 template <int METRIC, int HS_WARPS, int HS_T>
-__global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : (HS_WARPS == 4 ? 4 : (HS_WARPS == 2 ? 7 : 2))) k_hnsw_spec(HnswDev g, HnswSearchArgs a, uint32_t *__restrict__ err_flags, uint32_t vis_words) {
+__global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : (HS_WARPS == 4 ? 4 : (HS_WARPS == 2 ? 7 : 2))) k_hnsw_spec(HnswDev g, HnswSearchArgs a, uint32_t *__restrict__ err_flags, uint32_t vis_words, uint32_t vis_bitmap) {
   constexpr int HS_THREADS = HS_WARPS * 32;
   constexpr int HS_KPT = HS_WARPS >= 4 ? 2 : 4;       // elements per thread in the CTA merges: each half of the CTA holds
   constexpr int HS_MCAP = HS_THREADS / 2 * HS_KPT;    // up to HS_MCAP (>= 128) entries of W or of C
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(HS_WARPS * 32, HS_WARPS == 16 ? 1 : (HS_WARPS 
   const int WCAP = (int)ef + 32, CCAP = 2 * (int)ef + 96;
   float *sq = (float *)smem;                                   // dim floats
   uint32_t *hash = (uint32_t *)(sq + ((g.dim + 3) & ~3u));     // visited set: vis_words words (bitmap: ceil(n/32); hash: HS_HASH_CAP)
-  const HsVisited vis{hash, g.n <= HS_BITMAP_MAX_N};
+  const HsVisited vis{hash, vis_bitmap != 0};
   uint32_t *sp_edge = hash + vis_words;                        // [T][32] neighbour ids (HS_EMPTY = no edge)
   uint32_t *sp_key = sp_edge + HS_T * 32;                      // [T][32] distance keys of the neighbours scored this batch
   uint32_t *work = sp_key + HS_T * 32;                         // (t << 5 | j) of the rows to score
@@ -584,7 +586,10 @@ int launch_hnsw_spec(mgpu_hnsw *h, const HnswDev &g, const HnswSearchArgs &a, ui
   if (mode == 0 || h->quant != MGPU_QUANT_NONE || a.ef == 0 || a.ef > 2048 || h->max_degree > 32 || h->max_degree == 0) return MGPU_OK;
   if (h->num_layers > 1 && !g.upper_dense) return MGPU_OK;
   if (g.edges0 && g.deg0 > 32) return MGPU_OK;
-  const uint32_t vis_words = h->n <= HS_BITMAP_MAX_N ? (uint32_t)((h->n + 31) / 32) + 1 : HS_HASH_CAP;
+  // MGPU_HNSW_BITMAP_MAX=<n>: test knob -- graphs above n points use the hash table (default 262144)
+  static const uint32_t bitmap_max = getenv("MGPU_HNSW_BITMAP_MAX") ? (uint32_t)atoll(getenv("MGPU_HNSW_BITMAP_MAX")) : HS_BITMAP_MAX_N;
+  const uint32_t vis_bitmap = h->n <= std::min(bitmap_max, HS_BITMAP_MAX_N) ? 1u : 0u;
+  const uint32_t vis_words = vis_bitmap ? (uint32_t)((h->n + 31) / 32) + 1 : HS_HASH_CAP;
   const bool wide = a.B <= (uint32_t)ctx->sm_count;   // one 16-warp CTA per SM (its registers allow no second one)
   // Three shapes (measured): few queries (<= one per SM): 16 warps, 8 candidates per batch; a graph whose
   // rows stay in L2 searched by many queries (the Spann centroid graph: 4096 x 768, 1024 queries): 2 warps, 2 candidates --
@@ -620,7 +625,7 @@ int launch_hnsw_spec(mgpu_hnsw *h, const HnswDev &g, const HnswSearchArgs &a, ui
 #define HS_LAUNCH(MT, NWARP, TT)                                                                                   \
   do {                                                                                                             \
     cudaFuncSetAttribute(k_hnsw_spec<MT, NWARP, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-    k_hnsw_spec<MT, NWARP, TT><<<a.B, NWARP * 32, smem, ctx->stream>>>(g, a, err_flags, vis_words);                \
+    k_hnsw_spec<MT, NWARP, TT><<<a.B, NWARP * 32, smem, ctx->stream>>>(g, a, err_flags, vis_words, vis_bitmap);                \
   } while (0)
 #define HS_LAUNCH_W(MT) do { if (wide) HS_LAUNCH(MT, 16, 8); else if (small && small_env == 1) HS_LAUNCH(MT, 4, 2); else if (small) HS_LAUNCH(MT, 2, 2); else HS_LAUNCH(MT, 8, 4); } while (0)
   if (h->metric == MGPU_L2) HS_LAUNCH_W(MGPU_L2); else HS_LAUNCH_W(MGPU_DOT);

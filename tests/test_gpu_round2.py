@@ -522,3 +522,33 @@ def test_hnsw_batch_kernel_shapes(M, B, ef, n, dim, k):
         assert np.array_equal(r.doc_ids[b, :oc[b]], od[b, :oc[b]]), b
         assert _same_f32(r.scores[b, :oc[b]], os_[b, :oc[b]]), b
     assert np.array_equal(st, ost)
+
+
+def test_hnsw_hash_visited_set_and_overflow_redo():
+    """Graphs above 262 144 points keep the visited set of a query in an 8192-slot hash table in shared memory (config 4: 1M
+    points), and a query that visits more than 6144 points is flagged and redone by the generic kernel.  MGPU_HNSW_BITMAP_MAX=0
+    forces that mode on the small graphs of the HNSW / SPANN parity tests (ef up to 600 on 1500..4000 points: both the
+    in-table case and the redo), which must stay bit-exact, traversal counts included."""
+    env = dict(os.environ, MGPU_HNSW_BITMAP_MAX="0")
+    sel = "test_hnsw_flat_parity or test_hnsw_batch_kernel_shapes or test_spann_parity or test_hnsw_big_visited"
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-x", "-q", "-m", "gpu", "-k", sel,
+                        "-p", "no:cacheprovider"], capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert p.returncode == 0, (p.stdout[-3000:], p.stderr[-2000:])
+
+
+def test_hnsw_big_visited(M):
+    """ef = 2048 on 12 000 points: every query visits most of the graph (more than the hash table holds when the hash mode is
+    forced: the redo path), W and C exceed the CTA merge's capacity (warp-level merges)."""
+    n, dim = 12000, 24
+    X = synth.clustered(n, dim, n_blobs=7, seed=4)
+    g = O.hnsw_build(X, 16, 4, 40, seed=4)
+    oh = O.Hnsw(g["num_layers"], g["edges"], g["points"], g["edge_offsets"], g["level_offsets"], X)
+    gh = M.BlockBasedHnsw(g["num_layers"], g["edges"], g["points"], g["edge_offsets"], g["level_offsets"], X, M.NoQuantizer(dim))
+    Q = (X[:12] + 0.01).astype(np.float32)
+    od, os_, oc, ost = oh.search_batch(Q, 100, 2048)
+    r, st = gh.ann_search_batch(Q, 100, 2048, with_stats=True)
+    assert np.array_equal(np.asarray(r.counts, dtype=np.int64), oc.astype(np.int64))
+    for b in range(len(Q)):
+        assert np.array_equal(r.doc_ids[b, :oc[b]], od[b, :oc[b]]), b
+        assert _same_f32(r.scores[b, :oc[b]], os_[b, :oc[b]]), b
+    assert np.array_equal(st, ost)
