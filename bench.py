@@ -638,8 +638,9 @@ def main():
         if cfg == "spann":
             if sharded:
                 return o.shard_search_batch_submit(Qh[i % nbatches], params, outs[i & 1], shared_codebook=True)
-            r = o.search_batch(Qh[i % nbatches].numpy(), params)   # blocking host call (no pipelined form for the unsharded Spann)
-            return None
+            return o.search_batch_submit(Qh[i % nbatches], params, outs[i & 1])
+        if cfg == "hnsw":
+            return o.ann_search_batch_submit(Qh[i % nbatches], k, HNSW_EF, outs[i & 1])
         if sharded:
             return o.shard_search_batch_submit(Qh[i % nbatches], k, nprobe, outs[i & 1], shared_codebook=True)
         return o.search_batch_submit(Qh[i % nbatches], k, nprobe, outs[i & 1])
@@ -666,7 +667,7 @@ def main():
             else:
                 o.search_batch(Qh[i % nbatches], k, nprobe, out=outs[0])
 
-    pipelined = cfg in ("pq", "flat") or (cfg == "spann" and sharded)
+    pipelined = True   # every config has a pipelined submit / wait form
     run_blocking(3)
     barrier()
     t0 = time.perf_counter()
@@ -683,7 +684,8 @@ def main():
         barrier()
         e2e_mode = ("pipelined host-buffer calls (mgpu_%s_search_submit / mgpu_search_wait, 2 batches in flight): wall clock of %d "
                     "steps, every H2D/D2H copy inside, nothing subtracted" % (
-                        ("shard_spann" if cfg == "spann" else "shard_ivf") if sharded else "ivf", args.steps))
+                        ("shard_spann" if cfg == "spann" else "shard_ivf") if sharded else {"spann": "spann", "hnsw": "hnsw"}.get(cfg, "ivf"),
+                        args.steps))
         # the pipelined results are the device call's results (same batch, same index copy)
         last = args.steps - 1
         with torch.cuda.stream(ext):

@@ -130,12 +130,17 @@ extern "C" {
     pub fn mgpu_hnsw_destroy(h: *mut mgpu_hnsw);
     pub fn mgpu_hnsw_search(h: *mut mgpu_hnsw, Q: *const c_float, B: u32, k: u32, ef: u32, out_doc_ids: *mut mgpu_u128,
         out_scores: *mut c_float, out_counts: *mut u32, out_stats: *mut u64, mem: c_int) -> c_int;
+    pub fn mgpu_hnsw_search_submit(h: *mut mgpu_hnsw, Q: *const c_float, B: u32, k: u32, ef: u32,
+        out_doc_ids: *mut mgpu_u128, out_scores: *mut c_float, out_counts: *mut u32, ticket: *mut u64) -> c_int;
     pub fn mgpu_spann_create(ctx: *mut mgpu_ctx, centroids: *mut mgpu_hnsw, posting_lists: *mut mgpu_ivf,
         out: *mut *mut mgpu_spann) -> c_int;
     pub fn mgpu_spann_destroy(s: *mut mgpu_spann);
     pub fn mgpu_spann_search(s: *mut mgpu_spann, Q: *const c_float, B: u32, top_k: u32, ef: u32,
         num_explored_centroids: u32, centroid_distance_ratio: c_float, out_doc_ids: *mut mgpu_u128,
         out_scores: *mut c_float, out_counts: *mut u32, mem: c_int) -> c_int;
+    pub fn mgpu_spann_search_submit(s: *mut mgpu_spann, Q: *const c_float, B: u32, top_k: u32, ef: u32,
+        num_explored_centroids: u32, centroid_distance_ratio: c_float, out_doc_ids: *mut mgpu_u128,
+        out_scores: *mut c_float, out_counts: *mut u32, ticket: *mut u64) -> c_int;
     pub fn mgpu_spann_search_filtered(s: *mut mgpu_spann, Q: *const c_float, B: u32, top_k: u32, ef: u32,
         num_explored_centroids: u32, centroid_distance_ratio: c_float, filter_bits: *const u32, filter_stride_words: u64,
         out_doc_ids: *mut mgpu_u128, out_scores: *mut c_float, out_counts: *mut u32, mem: c_int) -> c_int;

@@ -235,6 +235,10 @@ void mgpu_hnsw_destroy(mgpu_hnsw *h);
 /* ann_search (index.rs:159-210) for B queries.  out_stats (may be NULL): B x 2 = {#distance evals, #expansions}. */
 int mgpu_hnsw_search(mgpu_hnsw *h, const float *Q, uint32_t B, uint32_t k, uint32_t ef, mgpu_u128 *out_doc_ids,
                      float *out_scores, uint32_t *out_counts, uint64_t *out_stats, int mem);
+/* Pipelined form over page-locked HOST buffers, as mgpu_ivf_search_submit (ticket completed by mgpu_search_wait; a batch
+ * with nothing to search returns ticket 0 and its counts at once).  No traversal statistics. */
+int mgpu_hnsw_search_submit(mgpu_hnsw *h, const float *Q, uint32_t B, uint32_t k, uint32_t ef, mgpu_u128 *out_doc_ids,
+                            float *out_scores, uint32_t *out_counts, uint64_t *ticket);
 
 /* ---- Spann<Q> (rs/index/src/spann/index.rs:15-266) ---------------------------------------- */
 /* centroids: HNSW over the IVF centroids with NoQuantizer<L2> whose doc ids are centroid indices. */
@@ -245,6 +249,10 @@ void mgpu_spann_destroy(mgpu_spann *s);
 int mgpu_spann_search(mgpu_spann *s, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef,
                       uint32_t num_explored_centroids, float centroid_distance_ratio, mgpu_u128 *out_doc_ids,
                       float *out_scores, uint32_t *out_counts, int mem);
+/* Pipelined form over page-locked HOST buffers, as mgpu_ivf_search_submit (ticket completed by mgpu_search_wait). */
+int mgpu_spann_search_submit(mgpu_spann *s, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef, uint32_t num_explored_centroids,
+                             float centroid_distance_ratio, mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts,
+                             uint64_t *ticket);
 
 /* Spann::search with Some(planner) (spann/index.rs:253-263): filter semantics as mgpu_ivf_search_filtered. */
 int mgpu_spann_search_filtered(mgpu_spann *s, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef,

@@ -899,6 +899,24 @@ class BlockBasedHnsw:
         r = BatchResult(ids, scores, cnt)
         return (r, stats) if with_stats else r
 
+    def ann_search_batch_submit(self, Q, k: int, ef: int, out) -> int:
+        """Pipelined ann_search_batch over page-locked HOST buffers (mgpu_hnsw_search_submit); `search_wait(ticket)` completes
+        it (ticket 0: nothing was in flight, `out` is already valid)."""
+        q = _Buf(Q, np.float32, (None, self.dim))
+        if q.mem != HOST:
+            raise ValueError("ann_search_batch_submit takes host buffers (device buffers are asynchronous already)")
+        ip, sp, cp = (x.data_ptr() if _is_torch(x) else x.ctypes.data for x in out)
+        t = C.c_uint64(0)
+        _lib.check(self.ctx.lib.mgpu_hnsw_search_submit(self.handle, q.ptr, q.shape[0], k, ef, ip, sp, cp, C.byref(t)), self.ctx.h)
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[t.value] = (Q, out)  # keep the buffers alive until the wait
+        return int(t.value)
+
+    def search_wait(self, ticket: int) -> None:
+        if ticket:
+            _lib.check(self.ctx.lib.mgpu_search_wait(self.ctx.h, ticket), self.ctx.h)
+        getattr(self, "_inflight", {}).pop(ticket, None)
+
     def ann_search(self, query, k: int, ef: int) -> SearchResult:
         """index.rs:159-210"""
         return self.ann_search_batch(np.asarray(query, dtype=np.float32).reshape(1, -1), k, ef).to_results()[0]
@@ -964,6 +982,20 @@ class Spann:
                                                             float(params.centroid_distance_ratio), 1 if shared_codebook else 0, ip, sp, cp,
                                                             q.mem), self.ctx.h)
         return BatchResult(ids, scores, cnt)
+
+    def search_batch_submit(self, Q, params: SearchParams, out) -> int:
+        """Pipelined search_batch over page-locked HOST buffers (mgpu_spann_search_submit); `search_wait(ticket)` completes it."""
+        q = _Buf(Q, np.float32, (None, self.posting_lists.dim))
+        if q.mem != HOST:
+            raise ValueError("search_batch_submit takes host buffers (device buffers are asynchronous already)")
+        ip, sp, cp = (x.data_ptr() if _is_torch(x) else x.ctypes.data for x in out)
+        t = C.c_uint64(0)
+        _lib.check(self.ctx.lib.mgpu_spann_search_submit(self.handle, q.ptr, q.shape[0], params.top_k, params.ef_construction,
+                                                         params.explored(), float(params.centroid_distance_ratio), ip, sp, cp,
+                                                         C.byref(t)), self.ctx.h)
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[t.value] = (Q, out)
+        return int(t.value)
 
     def shard_search_batch_submit(self, Q, params: SearchParams, out, shared_codebook: bool = True) -> int:
         """Pipelined form over page-locked HOST buffers; `search_wait(ticket)` completes it."""

@@ -101,6 +101,9 @@ SIGNATURES = {
                                    _u64p, C.c_int, C.c_int, C.c_void_p, _vp, C.c_int, C.c_uint64, _vp, C.POINTER(C.c_void_p)]),
     "mgpu_hnsw_destroy": (None, [C.c_void_p]),
     "mgpu_hnsw_search": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _f32p, _u32p, _u64p, C.c_int]),
+    "mgpu_hnsw_search_submit": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _f32p, _u32p, C.POINTER(C.c_uint64)]),
+    "mgpu_spann_search_submit": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, _vp, _f32p, _u32p,
+                                           C.POINTER(C.c_uint64)]),
     "mgpu_spann_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "mgpu_spann_destroy": (None, [C.c_void_p]),
     "mgpu_spann_search": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, _vp, _f32p, _u32p, C.c_int]),

@@ -1547,6 +1547,29 @@ int mgpu_hnsw_search(mgpu_hnsw *h, const float *Q, uint32_t B, uint32_t k, uint3
   return MGPU_OK;
 }
 
+/* Pipelined form of mgpu_hnsw_search for page-locked host buffers (see mgpu_ivf_search_submit). */
+int mgpu_hnsw_search_submit(mgpu_hnsw *h, const float *Q, uint32_t B, uint32_t k, uint32_t ef, mgpu_u128 *out_doc_ids,
+                            float *out_scores, uint32_t *out_counts, uint64_t *ticket) {
+  if (!h || !ticket) return MGPU_ERR_INVALID_ARG;
+  *ticket = 0;
+  mgpu_ctx *ctx = h->ctx;
+  if (B && (!Q || !out_doc_ids || !out_scores || !out_counts)) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "hnsw_search_submit: null buffer");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (B == 0) return MGPU_OK;
+  if (h->n == 0 || k == 0) { memset(out_counts, 0, (size_t)B * 4); return MGPU_OK; }   // nothing in flight: ticket 0
+  mgpu_ctx::Pipe *pp = nullptr;
+  MGPU_TRY(pipe_begin(ctx, Q, (size_t)B * h->dim * 4, (size_t)B * k * 24 + (size_t)B * 4 + 768, &pp));
+  WsAlloc wo(pp->out, pp->out_bytes);
+  mgpu_u128 *dD = wo.get<mgpu_u128>((size_t)B * k); float *dS = wo.get<float>((size_t)B * k); uint32_t *dC = wo.get<uint32_t>(B);
+  HnswSearchArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.k = k; a.ef = ef;
+  a.Q = (const float *)pp->q; a.out_docs = dD; a.out_scores = dS; a.out_counts = dC; a.out_stats = nullptr;
+  MGPU_TRY(launch_hnsw_search(h, a));
+  return pipe_end(ctx, pp, B, k, dD, dS, dC, out_doc_ids, out_scores, out_counts, ticket);
+}
+
 int mgpu_spann_create(mgpu_ctx *ctx, mgpu_hnsw *centroids, mgpu_ivf *posting_lists, mgpu_spann **out) {
   if (!ctx || !out) return MGPU_ERR_INVALID_ARG;
   *out = nullptr;
@@ -1660,6 +1683,26 @@ int mgpu_spann_search(mgpu_spann *sp, const float *Q, uint32_t B, uint32_t top_k
                       uint32_t num_explored_centroids, float ratio, mgpu_u128 *out_doc_ids, float *out_scores,
                       uint32_t *out_counts, int mem) {
   return spann_search_impl(sp, Q, B, top_k, ef, num_explored_centroids, ratio, nullptr, 0, out_doc_ids, out_scores, out_counts, mem);
+}
+
+/* Pipelined form of mgpu_spann_search for page-locked host buffers (see mgpu_ivf_search_submit). */
+int mgpu_spann_search_submit(mgpu_spann *sp, const float *Q, uint32_t B, uint32_t top_k, uint32_t ef, uint32_t num_explored_centroids,
+                             float ratio, mgpu_u128 *out_doc_ids, float *out_scores, uint32_t *out_counts, uint64_t *ticket) {
+  if (!sp || !ticket) return MGPU_ERR_INVALID_ARG;
+  *ticket = 0;
+  mgpu_ctx *ctx = sp->ctx;
+  if (B && (!Q || !out_doc_ids || !out_scores || !out_counts)) return mgpu_fail(ctx, MGPU_ERR_INVALID_ARG, "spann_search_submit: null buffer");
+  if (top_k > MGPU_MAX_K) return mgpu_fail(ctx, MGPU_ERR_UNSUPPORTED, "k = %u > %d is not supported", top_k, MGPU_MAX_K);
+  if (B == 0 || top_k == 0)   // nothing to pipeline: the blocking call answers (None / empty per query), ticket 0
+    return spann_search_impl(sp, Q, B, top_k, ef, num_explored_centroids, ratio, nullptr, 0, out_doc_ids, out_scores, out_counts, MGPU_HOST);
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  mgpu_ctx::Pipe *pp = nullptr;
+  MGPU_TRY(pipe_begin(ctx, Q, (size_t)B * sp->lists->dim * 4, (size_t)B * top_k * 24 + (size_t)B * 4 + 768, &pp));
+  WsAlloc wo(pp->out, pp->out_bytes);
+  mgpu_u128 *dD = wo.get<mgpu_u128>((size_t)B * top_k); float *dS = wo.get<float>((size_t)B * top_k); uint32_t *dC = wo.get<uint32_t>(B);
+  MGPU_TRY(spann_search_impl(sp, (const float *)pp->q, B, top_k, ef, num_explored_centroids, ratio, nullptr, 0, dD, dS, dC, MGPU_DEVICE, true));
+  return pipe_end(ctx, pp, B, top_k, dD, dS, dC, out_doc_ids, out_scores, out_counts, ticket);
 }
 
 /* Spann::search with Some(planner): the filter reaches the posting-list scan (spann/index.rs:253-263). */

@@ -6,9 +6,9 @@
 // caller blocks in mgpu_batcher_search with ONE query; a worker thread collects what has arrived, closes the batch when it
 // holds max_batch queries or when its oldest query has waited max_wait_us, issues one batched search through the same
 // C-ABI entry points a direct caller would use, and scatters the per-query results into the callers' own buffers.
-// Three staging buffers rotate and unfiltered IVF batches go through mgpu_ivf_search_submit / mgpu_search_wait, so two
-// batches are in flight (upload of one next to the kernels and download of the other) while a third fills; filtered and
-// Spann batches use the blocking call.
+// Three staging buffers rotate and unfiltered batches go through mgpu_ivf_search_submit / mgpu_spann_search_submit +
+// mgpu_search_wait, so two batches are in flight (upload of one next to the kernels and download of the other) while a third
+// fills; filtered batches use the blocking call.
 #include <chrono>
 #include <deque>
 #include <condition_variable>
@@ -109,7 +109,7 @@ static void batcher_run(mgpu_batcher *b) {
     }
     const int cur = b->fill;
     Staging &c = b->st[cur];
-    const bool pipelined = b->ivf != nullptr && !c.any_filter;
+    const bool pipelined = !c.any_filter;   // the filtered searches have no submit form
     // two submissions per context; the blocking call runs behind whatever is in flight anyway, so deliver those first
     while (inflight.size() >= (pipelined ? 2u : 1u)) finish_oldest();
     b->busy[cur] = true;
@@ -124,7 +124,8 @@ static void batcher_run(mgpu_batcher *b) {
     lk.unlock();
     if (pipelined) {
       uint64_t ticket = 0;
-      const int status = mgpu_ivf_search_submit(b->ivf, c.Q, n, b->k, b->nprobe, c.docs, c.scores, c.counts, &ticket);
+      const int status = b->ivf ? mgpu_ivf_search_submit(b->ivf, c.Q, n, b->k, b->nprobe, c.docs, c.scores, c.counts, &ticket)
+                                : mgpu_spann_search_submit(b->spann, c.Q, n, b->k, b->ef, b->nexp, b->ratio, c.docs, c.scores, c.counts, &ticket);
       if (status != MGPU_OK) batcher_complete(b, cur, status);
       lk.lock();
       if (status == MGPU_OK) inflight.emplace_back(cur, ticket);

@@ -552,3 +552,46 @@ def test_hnsw_big_visited(M):
         assert np.array_equal(r.doc_ids[b, :oc[b]], od[b, :oc[b]]), b
         assert _same_f32(r.scores[b, :oc[b]], os_[b, :oc[b]]), b
     assert np.array_equal(st, ost)
+
+
+def test_hnsw_and_spann_submit_wait_match_blocking(M):
+    """mgpu_hnsw_search_submit / mgpu_spann_search_submit + mgpu_search_wait: two batches in flight through the staging slots
+    must return what the blocking host call returns (and therefore the oracle's answer, which the blocking call is tested
+    against), including a slot reused before its ticket was waited for."""
+    import torch
+    from tests.test_gpu_parity import _spann_pair
+    X = synth.clustered(5000, 64, n_blobs=12, seed=13)
+    docs = synth.doc_ids_for(len(X), seed=4)
+    _, gs, _, givf = _spann_pair(M, X, docs, 40, pq_params=(8, 8, 1500))
+    g = O.hnsw_build(X, 16, 4, 60, seed=5)
+    gh = M.BlockBasedHnsw(g["num_layers"], g["edges"], g["points"], g["edge_offsets"], g["level_offsets"], X, M.NoQuantizer(64), doc_ids=docs)
+    rng = np.random.default_rng(9)
+    k, B, nb = 8, 80, 5
+    params = M.SearchParams(k, 40, False, 6, 0.3)
+    Qs = [torch.from_numpy((X[rng.integers(0, len(X), B)] + 0.02 * rng.standard_normal((B, 64))).astype(np.float32)).pin_memory()
+          for _ in range(nb)]
+
+    def outs():
+        return [(torch.zeros((B, k, 2), dtype=torch.int64).pin_memory(), torch.zeros((B, k), dtype=torch.float32).pin_memory(),
+                 torch.zeros((B,), dtype=torch.int32).pin_memory()) for _ in range(nb)]
+
+    for name, submit, wait, blocking in (
+            ("hnsw", lambda q, o: gh.ann_search_batch_submit(q, k, 48, o), gh.search_wait, lambda q: gh.ann_search_batch(q.numpy(), k, 48)),
+            ("spann", lambda q, o: gs.search_batch_submit(q, params, o), gs.search_wait, lambda q: gs.search_batch(q.numpy(), params))):
+        o = outs()
+        tickets = []
+        for i in range(nb):
+            tickets.append(submit(Qs[i], o[i]))
+            if i >= 1 and i != 3:
+                wait(tickets[i - 1])
+        for t in reversed(tickets):
+            wait(t)
+        for i in range(nb):
+            r = blocking(Qs[i])
+            ids, sc, cn = (x.numpy() for x in o[i])
+            rc = np.asarray(r.counts, dtype=np.int64)
+            assert np.array_equal(cn.astype(np.int64) & 0xFFFFFFFF, rc & 0xFFFFFFFF), (name, i)
+            for b in range(B):
+                n = int(rc[b]) if 0 <= int(rc[b]) <= k else 0
+                assert np.array_equal(ids[b, :n].view(np.uint64).reshape(-1), np.asarray(r.doc_ids[b, :n], dtype=np.uint64).reshape(-1)), (name, i, b)
+                assert _same_f32(sc[b, :n], np.asarray(r.scores[b, :n], dtype=np.float32)), (name, i, b)
