@@ -573,7 +573,6 @@ int launch_hnsw_search(mgpu_hnsw *h, const HnswSearchArgs &a) {
   uint32_t *visited = w.get<uint32_t>((size_t)a.B * vis_words);
   uint8_t *qcodes = w.get<uint8_t>((size_t)a.B * (h->pq ? h->pq->m : 0));
   uint32_t *err = w.get<uint32_t>(a.B);
-  CUDA_TRY(ctx, cudaMemsetAsync(visited, 0, (size_t)a.B * vis_words * 4, ctx->stream));
   CUDA_TRY(ctx, cudaMemsetAsync(err, 0, (size_t)a.B * 4, ctx->stream));
   HnswDev g;
   g.edges = h->d_edges; g.points = h->d_points; g.upper_pid = h->d_upper_sorted_pid; g.upper_pos = h->d_upper_sorted_pos;
@@ -596,6 +595,10 @@ int launch_hnsw_search(mgpu_hnsw *h, const HnswSearchArgs &a) {
   bool spec = false;
   if (s == MGPU_OK) s = launch_hnsw_spec(h, g, a, err, &spec);
   if (spec) epl = -1;
+  // the global visited bitmaps (B x n bits: 32 MB for 256 queries on 1M points) serve the kernels below; after the batch kernel
+  // only flagged queries are redone, and those clear their own bitmap
+  if (s == MGPU_OK && !spec && cudaMemsetAsync(visited, 0, (size_t)a.B * vis_words * 4, ctx->stream) != cudaSuccess)
+    s = mgpu_fail(ctx, MGPU_ERR_CUDA, "hnsw search: memset failed");
   if (s == MGPU_OK && epl > 0) {
     LaunchScope ls(ctx, MGPU_K_HNSW, nullptr, "k_hnsw_search_reg (hnsw.cu)");
 #define HN_LAUNCH_R(QT, MT, E)                                                                                          \
