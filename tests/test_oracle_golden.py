@@ -335,3 +335,88 @@ def test_hnsw_hand_built_graph():
     assert hn.entry_point() == 4
     ids, sc = hn.ann_search([0.9], 2, 4)
     assert ids == [1, 0] and np.allclose(sc, [0.1, 0.9], atol=1e-6)
+
+
+# ---- k-means assignment step / lane-conforming calculators (round 2 oracle functions) -----------------------------------
+def _np_lane_conforming_l2(a, b, lanes):
+    """Independent numpy restatement of LaneConformingDistanceCalculator<LANES, L2>::calculate_squared
+    (lane_conforming.rs:16-27 -> l2.rs:77-89 accumulate_lanes, ordered reduce_sum starting from -0.0)."""
+    acc = np.zeros(lanes, dtype=np.float32)
+    for c in range(len(a) // lanes):
+        d = a[c * lanes:(c + 1) * lanes] - b[c * lanes:(c + 1) * lanes]
+        acc = acc + d * d
+    s = np.float32(-0.0)
+    for x in acc:
+        s = np.float32(s + x)
+    return s
+
+
+def test_lane_conforming_batch_exact():
+    """All LANES of kmeans_builder.rs:126-136, bit for bit against the numpy restatement (dimension a multiple of LANES)."""
+    rng = np.random.default_rng(21)
+    for lanes, dim in ((16, 64), (8, 24), (4, 12), (4, 4), (8, 8), (16, 16)):
+        A, B = rng.random((5, dim), dtype=np.float32), rng.random((7, dim), dtype=np.float32)
+        got = O.lane_conforming_batch(A, B, lanes, O.L2)
+        for i in range(5):
+            for j in range(7):
+                assert got[i, j] == _np_lane_conforming_l2(A[i], B[j], lanes), (lanes, dim, i, j)
+
+
+def test_kmeans_assign_rule_exact():
+    """kmeans_builder.rs:199-221: cost = calculate_squared(point, centroid) + penalty with the calculator chosen by the
+    dimension (:126-136), strict '<' fold from (0, f32::MAX) -> the FIRST minimum wins.  Labels and costs bit for bit against
+    numpy, with penalties, exact ties (duplicated centroids) included."""
+    rng = np.random.default_rng(22)
+    for dim in (16, 24, 12, 6):        # LaneConforming<16>, <8>, <4>, plain D
+        lanes = 16 if dim % 16 == 0 else 8 if dim % 8 == 0 else 4 if dim % 4 == 0 else 0
+        X = rng.random((40, dim), dtype=np.float32)
+        Cn = rng.random((9, dim), dtype=np.float32)
+        Cn[5] = Cn[2]                  # exact tie: label 2 must win over 5
+        pen = (rng.random(9, dtype=np.float32) * np.float32(0.05)).astype(np.float32)
+        pen[5] = pen[2]
+        lab, cost = O.kmeans_assign(X, Cn, penalties=pen, with_costs=True)
+        for i in range(len(X)):
+            best, bl = np.float32(np.finfo(np.float32).max), 0
+            for c in range(len(Cn)):
+                d = _np_lane_conforming_l2(X[i], Cn[c], lanes) if lanes else np.float32(O.l2_squared(X[i], Cn[c]))
+                v = np.float32(d + pen[c])
+                if v < best:
+                    best, bl = v, c
+            assert lab[i] == bl and cost[i] == best, (dim, i)
+        assert 5 not in set(lab.tolist())
+
+
+def _lloyd(data, k, tol, init, iters=100):
+    """KMeansBuilder::run_lloyd (kmeans_builder.rs:162-358) with the oracle's assignment step; centroid update and penalties
+    as in the reference (no empty-cluster repair: the restated cases never produce one)."""
+    X = np.asarray(data, dtype=np.float32)
+    cents = X[init].copy()
+    sizes = np.zeros(k, dtype=np.int64)
+    pen = np.zeros(k, dtype=np.float32)
+    labels = np.zeros(len(X), dtype=np.int64)
+    for it in range(iters + 1):
+        last = labels.copy()
+        labels = O.kmeans_assign(X, cents, penalties=pen if tol > 0 else None).astype(np.int64)
+        sizes = np.bincount(labels, minlength=k)
+        assert (sizes > 0).all()
+        cents = np.stack([X[labels == c].sum(0) / np.float32(sizes[c]) for c in range(k)]).astype(np.float32)
+        if tol > 0:
+            pen = (np.float32(tol) * sizes.astype(np.float32)).astype(np.float32)
+        if np.array_equal(labels, last):
+            break
+    return labels
+
+
+def test_kmeans_lloyd_reference_case():
+    """kmeans_builder.rs:374-415 (test_kmeans_lloyd): three well separated groups, unbalanced penalty 1e-4."""
+    data = [[0, 0], [40, 40], [90, 90], [1, 1], [41, 41], [91, 91], [2, 2], [42, 42], [92, 92]]
+    a = _lloyd(data, 3, 1e-4, [0, 1, 2])
+    assert a[0] == a[3] == a[6] and a[1] == a[4] == a[7] and a[2] == a[5] == a[8]
+
+
+def test_kmeans_no_distance_penalty_reference_case():
+    """kmeans_builder.rs:417-454 (test_kmeans_no_distance_penalty): with tolerance 0 point 7 = (5, 5) joins the cluster of
+    points 0, 3, 6."""
+    data = [[0, 0], [40, 40], [90, 90], [1, 1], [41, 41], [91, 91], [2, 2], [5, 5], [92, 92]]
+    a = _lloyd(data, 3, 0.0, [0, 1, 2])
+    assert a[0] == a[3] == a[6] == a[7] and a[1] == a[4] and a[2] == a[5] == a[8]
